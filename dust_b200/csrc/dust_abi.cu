@@ -1,0 +1,629 @@
+// C ABI of libdust_b200.so (include/dust_b200.h): context, one-time tree re-layout + upload,
+// instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
+// launches sm_100a kernels or fails.
+#include "trace_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace dust;
+
+struct DustCtx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // scratch for DUST_MEM_HOST frames / ray batches
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    DCounters *d_counters = nullptr;
+    DustStats stats{};
+};
+
+struct DustTree {
+    uint32_t n_levels = 0;
+    void *blob = nullptr;            // one device allocation
+    size_t blob_bytes = 0;
+    const DNode16 *n16 = nullptr;
+    const uint4 *mids = nullptr;
+    const uint4 *leaves = nullptr;
+    const uint8_t *materials = nullptr;
+    const float4 *palette_lin = nullptr;
+    uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0;
+    int32_t bmin[3] = { 0, 0, 0 }, bmax[3] = { 0, 0, 0 };   // occupied bounds in object voxels
+};
+
+struct DustScene {
+    DInstance *d_inst = nullptr;
+    DBvhNode *d_bvh = nullptr;
+    uint32_t n_inst = 0, n_bvh = 0, max_levels = 3;
+};
+
+namespace {
+
+int32_t fail(DustCtx *ctx, int32_t code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? DUST_ERR_OUT_OF_MEMORY : DUST_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+int32_t ensure_scratch(DustCtx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->scratch_bytes) return DUST_OK;
+    if (ctx->scratch) { CU_TRY(ctx, cudaFree(ctx->scratch)); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+    CU_TRY(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return DUST_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- reading the reference's host layout (crates/vdb) ------------------------------------------
+
+struct HostTree {
+    const DustTreeDesc *d;
+    // LEVEL-indexed (0 = leaf)
+    uint32_t fanout[4];
+    bool ok(std::string &why) const
+    {
+        const uint32_t nl = d->n_levels;
+        if (nl != 3 && nl != 4) { why = "only hierarchy!(4,2,2) and hierarchy!(4,4,2,2) are supported"; return false; }
+        static const uint32_t h3[3] = { 4, 2, 2 }, h4[4] = { 4, 4, 2, 2 };
+        for (uint32_t i = 0; i < nl; i++)
+            if (d->fanout_log2[i] != (nl == 3 ? h3[i] : h4[i])) { why = "unsupported fan-out"; return false; }
+        if (!d->root || d->root_bytes != 16896) { why = "root must be an InternalNode<_,{4,4,4}> (16896 bytes)"; return false; }
+        const uint32_t want[3] = { 24, 264, 16896 };
+        for (uint32_t lv = 0; lv + 1 < nl; lv++) {
+            if (d->item_bytes[lv] != want[lv]) { why = "pool item size does not match the #[repr(C)] node layout"; return false; }
+            if (d->n_items[lv] && (!d->pool_chunks[lv] || (uint64_t)d->n_chunks[lv] * 1024u < d->n_items[lv])) { why = "pool chunks missing"; return false; }
+        }
+        if (!d->palette) { why = "palette is NULL"; return false; }
+        return true;
+    }
+    const uint8_t *item(uint32_t level, uint32_t ptr) const
+    {
+        // Pool::get, crates/vdb/src/pool.rs:109-116 (chunk_size_log2 = 10, tree.rs:36)
+        if (ptr >= d->n_items[level]) return nullptr;
+        return static_cast<const uint8_t *>(d->pool_chunks[level][ptr >> 10]) + (size_t)(ptr & 1023u) * d->item_bytes[level];
+    }
+};
+
+// InternalNode<_, {4,4,4}>: 64 mask words then 4096 u32 (internal.rs:22-32)
+inline const uint64_t *n16_mask(const uint8_t *node) { return reinterpret_cast<const uint64_t *>(node); }
+inline const uint32_t *n16_ptrs(const uint8_t *node) { return reinterpret_cast<const uint32_t *>(node + 512); }
+
+struct Relayout {
+    std::vector<DNode16> n16;
+    std::vector<uint4> mids, leaves;
+    int32_t bmin[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, bmax[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
+    bool bad_ptr = false;
+};
+
+// Emit the children of one 16^3 node whose children are 4^3 mid nodes (LEVEL 1), in ascending bit
+// order; leaves of each mid node are appended in ascending bit order => Tree::iter_leaf order.
+void emit_n16_over_mids(const HostTree &ht, const uint8_t *node, int32_t ox, int32_t oy, int32_t oz, DNode16 &out, Relayout &r)
+{
+    const uint64_t *mask = n16_mask(node);
+    const uint32_t *ptrs = n16_ptrs(node);
+    for (uint32_t w = 0; w < 64; w++) {
+        out.mask[w] = mask[w];
+        out.child[w] = (uint32_t)r.mids.size();
+        for (uint64_t m = mask[w]; m; m &= m - 1) {
+            const uint32_t idx = w * 64u + (uint32_t)__builtin_ctzll(m);
+            const uint8_t *mid = ht.item(1, ptrs[idx]);
+            if (!mid) { r.bad_ptr = true; continue; }
+            const int32_t mx = ox + (int32_t)(idx >> 8) * 16, my = oy + (int32_t)((idx >> 4) & 15) * 16, mz = oz + (int32_t)(idx & 15) * 16;
+            uint64_t mm;
+            memcpy(&mm, mid, 8);
+            const uint32_t *mptrs = reinterpret_cast<const uint32_t *>(mid + 8);
+            r.mids.push_back(make_uint4((uint32_t)mm, (uint32_t)(mm >> 32), (uint32_t)r.leaves.size(), 0));
+            for (uint64_t b = mm; b; b &= b - 1) {
+                const uint32_t li = (uint32_t)__builtin_ctzll(b);
+                const uint8_t *leaf = ht.item(0, mptrs[li]);
+                if (!leaf) { r.bad_ptr = true; continue; }
+                uint64_t occ; uint32_t mat;
+                memcpy(&occ, leaf, 8); memcpy(&mat, leaf + 16, 4);      // leaf.rs:13-25
+                r.leaves.push_back(make_uint4((uint32_t)occ, (uint32_t)(occ >> 32), mat, 0));
+                const int32_t l[3] = { mx + (int32_t)(li >> 4) * 4, my + (int32_t)((li >> 2) & 3) * 4, mz + (int32_t)(li & 3) * 4 };
+                for (int a = 0; a < 3; a++) { r.bmin[a] = std::min(r.bmin[a], l[a]); r.bmax[a] = std::max(r.bmax[a], l[a] + 4); }
+            }
+        }
+    }
+}
+
+void relayout(const HostTree &ht, Relayout &r)
+{
+    const uint8_t *root = static_cast<const uint8_t *>(ht.d->root);
+    if (ht.d->n_levels == 3) {
+        r.n16.resize(1);
+        emit_n16_over_mids(ht, root, 0, 0, 0, r.n16[0], r);
+        return;
+    }
+    // (4,4,2,2): root 16^3 over 16^3 nodes (LEVEL 2) over mids over leaves
+    const uint64_t *mask = n16_mask(root);
+    const uint32_t *ptrs = n16_ptrs(root);
+    uint32_t n_children = 0;
+    for (uint32_t w = 0; w < 64; w++) n_children += (uint32_t)__builtin_popcountll(mask[w]);
+    r.n16.resize(1 + (size_t)n_children);
+    uint32_t next = 1;
+    for (uint32_t w = 0; w < 64; w++) {
+        r.n16[0].mask[w] = mask[w];
+        r.n16[0].child[w] = next;
+        for (uint64_t m = mask[w]; m; m &= m - 1) {
+            const uint32_t idx = w * 64u + (uint32_t)__builtin_ctzll(m);
+            const uint8_t *child = ht.item(2, ptrs[idx]);
+            DNode16 tmp;
+            memset(&tmp, 0, sizeof tmp);
+            if (!child) r.bad_ptr = true;
+            else emit_n16_over_mids(ht, child, (int32_t)(idx >> 8) * 256, (int32_t)((idx >> 4) & 15) * 256, (int32_t)(idx & 15) * 256, tmp, r);
+            r.n16[next++] = tmp;
+        }
+    }
+}
+
+// SRGBToLinear, assets/shaders/headers/color.glsl:1-5, applied to palette[i].rgb / 255 (hit.rchit:72-74)
+inline float srgb_to_linear(float c)
+{
+    return c < 0.04045f ? c / 12.92f : powf(fabsf(c + 0.055f) / 1.055f, 2.4f);
+}
+
+// ---- instance transforms and BVH ----------------------------------------------------------------
+
+// gl_WorldToObjectEXT: inverse of the row-major 3x4 affine, adjugate / determinant in double,
+// rounded once to f32 (DESIGN.md "Instance transforms")
+void world2obj(const float m[12], float w[12])
+{
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double A = e * i - f * h, B = c * h - b * i, C = b * f - c * e;
+    const double D = f * g - d * i, E = a * i - c * g, F = c * d - a * f;
+    const double G = d * h - e * g, H = b * g - a * h, I = a * e - b * d;
+    const double det = a * A + b * D + c * G;
+    const double inv[9] = { A / det, B / det, C / det, D / det, E / det, F / det, G / det, H / det, I / det };
+    const double t[3] = { m[3], m[7], m[11] };
+    for (int r = 0; r < 3; r++) {
+        w[4 * r + 0] = (float)inv[3 * r + 0];
+        w[4 * r + 1] = (float)inv[3 * r + 1];
+        w[4 * r + 2] = (float)inv[3 * r + 2];
+        w[4 * r + 3] = (float)(-(inv[3 * r + 0] * t[0] + inv[3 * r + 1] * t[1] + inv[3 * r + 2] * t[2]));
+    }
+}
+
+struct Box { float lo[3], hi[3]; };
+
+int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const std::vector<Box> &boxes, uint32_t begin, uint32_t end)
+{
+    const int me = (int)nodes.size();
+    nodes.emplace_back();
+    Box b = boxes[ids[begin]];
+    float clo[3], chi[3];
+    for (int a = 0; a < 3; a++) clo[a] = chi[a] = 0.5f * (b.lo[a] + b.hi[a]);
+    for (uint32_t k = begin + 1; k < end; k++) {
+        const Box &x = boxes[ids[k]];
+        for (int a = 0; a < 3; a++) {
+            b.lo[a] = std::min(b.lo[a], x.lo[a]); b.hi[a] = std::max(b.hi[a], x.hi[a]);
+            const float c = 0.5f * (x.lo[a] + x.hi[a]);
+            clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+        }
+    }
+    for (int a = 0; a < 3; a++) { nodes[me].lo[a] = b.lo[a]; nodes[me].hi[a] = b.hi[a]; }
+    if (end - begin == 1) {
+        nodes[me].left = ~(int32_t)ids[begin];
+        nodes[me].right = 0;
+        return me;
+    }
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    const uint32_t mid = (begin + end) / 2;
+    std::nth_element(ids.begin() + begin, ids.begin() + mid, ids.begin() + end, [&](uint32_t x, uint32_t y) {
+        const float cx = boxes[x].lo[axis] + boxes[x].hi[axis], cy = boxes[y].lo[axis] + boxes[y].hi[axis];
+        return cx < cy || (cx == cy && x < y);
+    });
+    const int l = build_bvh(nodes, ids, boxes, begin, mid);
+    const int r = build_bvh(nodes, ids, boxes, mid, end);
+    nodes[me].left = l;
+    nodes[me].right = r;
+    return me;
+}
+
+void count_launch(DustCtx *ctx) { ctx->stats.kernel_launches++; }
+
+int32_t fetch_counters(DustCtx *ctx)
+{
+    DCounters h;
+    CU_TRY(ctx, cudaMemcpyAsync(&h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.primary_rays = h.primary_rays; ctx->stats.bounce_rays = h.bounce_rays; ctx->stats.shadow_rays = h.shadow_rays;
+    ctx->stats.mask_words = h.mask_words; ctx->stats.child_ptrs = h.child_ptrs; ctx->stats.hits_shaded = h.hits_shaded;
+    return DUST_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t dust_abi_version(void) { return DUST_ABI_VERSION; }
+
+int32_t dust_ctx_create(int32_t device, DustCtx **out)
+{
+    if (!out) return DUST_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return DUST_ERR_NO_DEVICE;
+    DustCtx *ctx = new (std::nothrow) DustCtx();
+    if (!ctx) return DUST_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess) {
+        delete ctx;
+        return DUST_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return DUST_OK;
+}
+
+int32_t dust_ctx_destroy(DustCtx *ctx)
+{
+    if (!ctx) return DUST_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return DUST_OK;
+}
+
+int32_t dust_ctx_set_stream(DustCtx *ctx, void *cuda_stream)
+{
+    if (!ctx) return DUST_ERR_INVALID_ARGUMENT;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return DUST_OK;
+}
+
+int32_t dust_ctx_synchronize(DustCtx *ctx)
+{
+    if (!ctx) return DUST_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DUST_OK;
+}
+
+const char *dust_last_error_string(const DustCtx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
+{
+    if (!ctx || !desc || !out) return DUST_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    HostTree ht{ desc, { 0, 0, 0, 0 } };
+    std::string why;
+    if (!ht.ok(why)) return fail(ctx, desc->n_levels == 3 || desc->n_levels == 4 ? DUST_ERR_INVALID_ARGUMENT : DUST_ERR_UNSUPPORTED, why);
+    Relayout r;
+    relayout(ht, r);
+    if (r.bad_ptr) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "child pointer outside its pool");
+    // material_ptr + popcount(mask) must stay inside `materials`
+    for (const uint4 &l : r.leaves) {
+        const uint64_t need = (uint64_t)l.z + (uint64_t)__builtin_popcountll(((uint64_t)l.y << 32) | l.x);
+        if (need > desc->n_materials) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "leaf material_ptr runs past the material array");
+    }
+    if (desc->n_materials && !desc->materials) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "materials is NULL");
+
+    float4 pal[256];
+    memset(pal, 0, sizeof pal);
+    for (int i = 0; i < 255; i++) {
+        const uint8_t *c = desc->palette + 4 * i;
+        pal[i] = make_float4(srgb_to_linear((float)c[0] / 255.0f), srgb_to_linear((float)c[1] / 255.0f), srgb_to_linear((float)c[2] / 255.0f), 0.0f);
+    }
+
+    // one allocation: [n16 | mids | leaves | palette_lin | materials], each 256-byte aligned
+    const size_t off_n16 = 0;
+    const size_t off_mids = align_up(off_n16 + r.n16.size() * sizeof(DNode16), 256);
+    const size_t off_leaves = align_up(off_mids + r.mids.size() * sizeof(uint4), 256);
+    const size_t off_pal = align_up(off_leaves + r.leaves.size() * sizeof(uint4), 256);
+    const size_t off_mat = align_up(off_pal + sizeof pal, 256);
+    const size_t total = align_up(off_mat + (size_t)desc->n_materials + 16, 256);
+
+    DustTree *t = new (std::nothrow) DustTree();
+    if (!t) return DUST_ERR_OUT_OF_MEMORY;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(&t->blob, total);
+    if (e != cudaSuccess) { delete t; return fail(ctx, DUST_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+    uint8_t *base = static_cast<uint8_t *>(t->blob);
+    auto put = [&](size_t off, const void *src, size_t bytes) {
+        return bytes ? cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+    };
+    e = put(off_n16, r.n16.data(), r.n16.size() * sizeof(DNode16));
+    if (e == cudaSuccess) e = put(off_mids, r.mids.data(), r.mids.size() * sizeof(uint4));
+    if (e == cudaSuccess) e = put(off_leaves, r.leaves.data(), r.leaves.size() * sizeof(uint4));
+    if (e == cudaSuccess) e = put(off_pal, pal, sizeof pal);
+    if (e == cudaSuccess) e = put(off_mat, desc->materials, (size_t)desc->n_materials);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);     // host vectors die at return
+    if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e)); }
+    t->n_levels = desc->n_levels;
+    t->blob_bytes = total;
+    t->n16 = reinterpret_cast<const DNode16 *>(base + off_n16);
+    t->mids = reinterpret_cast<const uint4 *>(base + off_mids);
+    t->leaves = reinterpret_cast<const uint4 *>(base + off_leaves);
+    t->palette_lin = reinterpret_cast<const float4 *>(base + off_pal);
+    t->materials = base + off_mat;
+    t->n_leaves = r.leaves.size(); t->n_mids = r.mids.size(); t->n_n16 = r.n16.size();
+    if (r.leaves.empty()) { for (int a = 0; a < 3; a++) { t->bmin[a] = 0; t->bmax[a] = 0; } }
+    else for (int a = 0; a < 3; a++) { t->bmin[a] = r.bmin[a]; t->bmax[a] = r.bmax[a]; }
+    *out = t;
+    return DUST_OK;
+}
+
+int32_t dust_tree_destroy(DustCtx *ctx, DustTree *tree)
+{
+    if (!ctx || !tree) return DUST_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (tree->blob) cudaFree(tree->blob);
+    delete tree;
+    return DUST_OK;
+}
+
+int32_t dust_tree_leaf_count(const DustTree *tree, uint64_t *out)
+{
+    if (!tree || !out) return DUST_ERR_INVALID_ARGUMENT;
+    *out = tree->n_leaves;
+    return DUST_OK;
+}
+
+int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out)
+{
+    if (!tree || !out) return DUST_ERR_INVALID_ARGUMENT;
+    *out = tree->blob_bytes;
+    return DUST_OK;
+}
+
+int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t n, DustScene **out)
+{
+    if (!ctx || !out || (n && !instances)) return DUST_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::vector<DInstance> inst(n);
+    std::vector<Box> boxes(n);
+    uint32_t max_levels = 3;
+    for (uint32_t k = 0; k < n; k++) {
+        const DustTree *t = instances[k].tree;
+        if (!t) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "instance without a tree");
+        DInstance &d = inst[k];
+        const float *m = instances[k].obj2world;
+        world2obj(m, d.w2o);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
+        d.n_levels = t->n_levels;
+        d.n16 = t->n16; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin;
+        max_levels = std::max(max_levels, t->n_levels);
+        // world box of the occupied object-space bounds, padded so that culling can never remove
+        // a hit the exact per-instance traversal would report (DESIGN.md "Instance BVH")
+        Box b;
+        for (int a = 0; a < 3; a++) { b.lo[a] = INFINITY; b.hi[a] = -INFINITY; }
+        float big = 0.0f;
+        for (int corner = 0; corner < 8; corner++) {
+            const float p[3] = { (float)(corner & 1 ? t->bmax[0] : t->bmin[0]), (float)(corner & 2 ? t->bmax[1] : t->bmin[1]),
+                                 (float)(corner & 4 ? t->bmax[2] : t->bmin[2]) };
+            for (int a = 0; a < 3; a++) {
+                const float w = m[4 * a] * p[0] + m[4 * a + 1] * p[1] + m[4 * a + 2] * p[2] + m[4 * a + 3];
+                b.lo[a] = std::min(b.lo[a], w); b.hi[a] = std::max(b.hi[a], w);
+                big = std::max(big, std::fabs(w));
+            }
+        }
+        const float pad = 0.02f + 1e-5f * big;
+        for (int a = 0; a < 3; a++) { b.lo[a] -= pad; b.hi[a] += pad; }
+        boxes[k] = b;
+    }
+    std::vector<DBvhNode> nodes;
+    if (n) {
+        std::vector<uint32_t> ids(n);
+        for (uint32_t k = 0; k < n; k++) ids[k] = k;
+        nodes.reserve(2 * (size_t)n);
+        build_bvh(nodes, ids, boxes, 0, n);
+    }
+    DustScene *s = new (std::nothrow) DustScene();
+    if (!s) return DUST_ERR_OUT_OF_MEMORY;
+    s->n_inst = n; s->n_bvh = (uint32_t)nodes.size(); s->max_levels = max_levels;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n) {
+        cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * nodes.size());
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            if (s->d_inst) cudaFree(s->d_inst);
+            if (s->d_bvh) cudaFree(s->d_bvh);
+            delete s;
+            return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    *out = s;
+    return DUST_OK;
+}
+
+int32_t dust_scene_destroy(DustCtx *ctx, DustScene *scene)
+{
+    if (!ctx || !scene) return DUST_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (scene->d_inst) cudaFree(scene->d_inst);
+    if (scene->d_bvh) cudaFree(scene->d_bvh);
+    delete scene;
+    return DUST_OK;
+}
+
+int32_t dust_shard_layout(uint32_t width, uint32_t height, uint32_t shard_count, uint32_t *tiles_per_shard, uint64_t *pixels_per_shard)
+{
+    if (!width || !height || !shard_count) return DUST_ERR_INVALID_ARGUMENT;
+    const uint32_t tiles = ((width + 31) / 32) * ((height + 31) / 32);
+    const uint32_t per = (tiles + shard_count - 1) / shard_count;
+    if (tiles_per_shard) *tiles_per_shard = per;
+    if (pixels_per_shard) *pixels_per_shard = (uint64_t)per * 1024u;
+    return DUST_OK;
+}
+
+int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
+                   const DustTraceConfig *config, const DustFrame *frame)
+{
+    if (!ctx || !scene || !camera || !sky || !config || !frame) return DUST_ERR_INVALID_ARGUMENT;
+    const DustTraceConfig &cfg = *config;
+    if (!cfg.width || !cfg.height || !cfg.spp || !cfg.shard_count || cfg.shard_index >= cfg.shard_count || !frame->radiance)
+        return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad trace config");
+    if ((uint64_t)cfg.width * cfg.height > 0x7FFFFFFFull) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "frame too large");
+    const bool want_hits = (cfg.flags & DUST_TRACE_WRITE_HITS) != 0;
+    if (want_hits && (cfg.shard_count != 1 || !frame->hit_instance || !frame->hit_leaf || !frame->hit_voxel || !frame->hit_t))
+        return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "hit buffers need shard_count == 1 and all four arrays");
+    if (frame->radiance_format != DUST_FMT_RGBA32F && frame->radiance_format != DUST_FMT_RGBA16F)
+        return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad radiance format");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+
+    uint32_t tiles_per_shard = 0; uint64_t shard_pixels = 0;
+    dust_shard_layout(cfg.width, cfg.height, cfg.shard_count, &tiles_per_shard, &shard_pixels);
+    const uint64_t out_pixels = cfg.shard_count > 1 ? shard_pixels : (uint64_t)cfg.width * cfg.height;
+    const size_t px_bytes = frame->radiance_format == DUST_FMT_RGBA32F ? 16 : 8;
+
+    FrameParams p;
+    memset(&p, 0, sizeof p);
+    p.scene.inst = scene->d_inst; p.scene.bvh = scene->d_bvh; p.scene.n_inst = scene->n_inst; p.scene.n_bvh = scene->n_bvh;
+    p.scene.max_levels = scene->max_levels;
+    p.cam = *camera; p.sky = *sky; p.cfg = cfg;
+    {
+        // uniform-only terms hoisted out of the shaders (ambient_occlusion.rgen:45, nee.rmiss:18-19, sky.glsl:88-89)
+        const float *d = sky->direction;
+        const float l = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+        p.sun_dir[0] = d[0] / l; p.sun_dir[1] = d[1] / l; p.sun_dir[2] = d[2] / l;
+        p.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
+        const float s = sinf(sky->sunlight_intensity[3]);
+        p.sun_ar2 = 1.0f / (s * s);
+    }
+    p.tiles_x = (cfg.width + 31) / 32; p.tiles_y = (cfg.height + 31) / 32; p.n_local_tiles = tiles_per_shard;
+
+    uint8_t *scratch = nullptr;
+    size_t off_hi = 0, off_hl = 0, off_hv = 0, off_ht = 0;
+    const uint64_t npx = (uint64_t)cfg.width * cfg.height;
+    if (frame->memory == DUST_MEM_HOST) {
+        size_t need = align_up(out_pixels * px_bytes, 256);
+        if (want_hits) {
+            off_hi = need; need += align_up(npx * 4, 256);
+            off_hl = need; need += align_up(npx * 4, 256);
+            off_ht = need; need += align_up(npx * 4, 256);
+            off_hv = need; need += align_up(npx, 256);
+        }
+        int32_t rc = ensure_scratch(ctx, need);
+        if (rc != DUST_OK) return rc;
+        scratch = static_cast<uint8_t *>(ctx->scratch);
+        if (frame->radiance_format == DUST_FMT_RGBA32F) p.radiance32 = reinterpret_cast<float4 *>(scratch);
+        else p.radiance16 = reinterpret_cast<__half *>(scratch);
+        if (want_hits) {
+            p.hit_instance = reinterpret_cast<uint32_t *>(scratch + off_hi); p.hit_leaf = reinterpret_cast<uint32_t *>(scratch + off_hl);
+            p.hit_t = reinterpret_cast<float *>(scratch + off_ht); p.hit_voxel = scratch + off_hv;
+        }
+    } else if (frame->memory == DUST_MEM_DEVICE) {
+        if (frame->radiance_format == DUST_FMT_RGBA32F) p.radiance32 = static_cast<float4 *>(frame->radiance);
+        else p.radiance16 = static_cast<__half *>(frame->radiance);
+        if (want_hits) { p.hit_instance = frame->hit_instance; p.hit_leaf = frame->hit_leaf; p.hit_voxel = frame->hit_voxel; p.hit_t = frame->hit_t; }
+    } else return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+
+    const bool stats = (cfg.flags & DUST_TRACE_STATS) != 0;
+    p.counters = ctx->d_counters;
+    if (stats) CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DCounters), ctx->stream));
+    if (cfg.shard_count > 1 && tiles_per_shard * cfg.shard_count != p.tiles_x * p.tiles_y)
+        CU_TRY(ctx, cudaMemsetAsync(p.radiance32 ? (void *)p.radiance32 : (void *)p.radiance16, 0, out_pixels * px_bytes, ctx->stream));
+
+    const uint32_t grid = tiles_per_shard * 8u;
+    if (stats) frame_kernel<true><<<grid, 128, 0, ctx->stream>>>(p);
+    else frame_kernel<false><<<grid, 128, 0, ctx->stream>>>(p);
+    CU_TRY(ctx, cudaGetLastError());
+    count_launch(ctx);
+
+    if (frame->memory == DUST_MEM_HOST) {
+        CU_TRY(ctx, cudaMemcpyAsync(frame->radiance, scratch, out_pixels * px_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_hits) {
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_instance, scratch + off_hi, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_leaf, scratch + off_hl, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_t, scratch + off_ht, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_voxel, scratch + off_hv, npx, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (stats) return fetch_counters(ctx);
+    return DUST_OK;
+}
+
+int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *rays, uint64_t n, DustHit *hits,
+                        uint32_t memory, uint32_t flags)
+{
+    if (!ctx || !scene || (n && (!rays || !hits))) return DUST_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DUST_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    RayParams p;
+    memset(&p, 0, sizeof p);
+    p.scene.inst = scene->d_inst; p.scene.bvh = scene->d_bvh; p.scene.n_inst = scene->n_inst; p.scene.n_bvh = scene->n_bvh;
+    p.scene.max_levels = scene->max_levels;
+    p.n = n;
+    p.counters = ctx->d_counters;
+    uint8_t *scratch = nullptr;
+    const size_t ray_bytes = align_up((size_t)n * sizeof(DustRay), 256);
+    if (memory == DUST_MEM_HOST) {
+        int32_t rc = ensure_scratch(ctx, ray_bytes + (size_t)n * sizeof(DustHit));
+        if (rc != DUST_OK) return rc;
+        scratch = static_cast<uint8_t *>(ctx->scratch);
+        CU_TRY(ctx, cudaMemcpyAsync(scratch, rays, (size_t)n * sizeof(DustRay), cudaMemcpyHostToDevice, ctx->stream));
+        p.rays = reinterpret_cast<const DustRay *>(scratch);
+        p.hits = reinterpret_cast<DustHit *>(scratch + ray_bytes);
+    } else if (memory == DUST_MEM_DEVICE) {
+        p.rays = rays; p.hits = hits;
+    } else return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    const bool stats = (flags & DUST_TRACE_STATS) != 0;
+    if (stats) CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DCounters), ctx->stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const uint64_t want = (n + 127) / 128;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 16u);
+    if (stats) rays_kernel<true><<<grid, 128, 0, ctx->stream>>>(p);
+    else rays_kernel<false><<<grid, 128, 0, ctx->stream>>>(p);
+    CU_TRY(ctx, cudaGetLastError());
+    count_launch(ctx);
+    if (memory == DUST_MEM_HOST) {
+        CU_TRY(ctx, cudaMemcpyAsync(hits, scratch + ray_bytes, (size_t)n * sizeof(DustHit), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (stats) return fetch_counters(ctx);
+    return DUST_OK;
+}
+
+int32_t dust_resolve_shards(DustCtx *ctx, uint32_t width, uint32_t height, uint32_t shard_count, const void *gathered, void *out)
+{
+    if (!ctx || !gathered || !out || !width || !height || !shard_count) return DUST_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint32_t tiles_per_shard = 0;
+    dust_shard_layout(width, height, shard_count, &tiles_per_shard, nullptr);
+    dim3 grid((width + 31) / 32, (height + 7) / 8);
+    resolve_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float4 *>(gathered), static_cast<float4 *>(out), width, height,
+                                                 shard_count, (width + 31) / 32, tiles_per_shard);
+    CU_TRY(ctx, cudaGetLastError());
+    count_launch(ctx);
+    return DUST_OK;
+}
+
+int32_t dust_get_stats(DustCtx *ctx, DustStats *out)
+{
+    if (!ctx || !out) return DUST_ERR_INVALID_ARGUMENT;
+    *out = ctx->stats;
+    return DUST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+"""Thin object wrappers over the C ABI (include/dust_b200.h): Context / DeviceTree / Scene and the
+two trace entry points.  Host buffers are numpy arrays, device buffers are torch CUDA tensors
+(torch is only the allocator / stream / collective plumbing; every kernel is ours).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (DUST_FMT_RGBA16F, DUST_FMT_RGBA32F, DUST_MEM_DEVICE, DUST_MEM_HOST, DUST_TRACE_STATS,
+                   DUST_TRACE_WRITE_HITS, DustFrame, DustInstance, DustStats, DustTraceConfig, check)
+
+MISS = 0xFFFFFFFF
+HIT_DTYPE = np.dtype([("t", "<f4"), ("instance", "<u4"), ("leaf", "<u4"), ("voxel", "<u4")])
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
+assert HIT_DTYPE.itemsize == 16 and RAY_DTYPE.itemsize == 32
+
+
+class Context:
+    """One per GPU (dust_ctx_create).  Raises DustError(DUST_ERR_NO_DEVICE) without a CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        check(None, self.lib.dust_ctx_create(device, C.byref(h)), "dust_ctx_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dust_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self.h, self.lib.dust_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "dust_ctx_set_stream")
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        check(self.h, self.lib.dust_ctx_synchronize(self.h), "dust_ctx_synchronize")
+
+    def stats(self) -> dict:
+        s = DustStats()
+        check(self.h, self.lib.dust_get_stats(self.h, C.byref(s)), "dust_get_stats")
+        return s.as_dict()
+
+    def upload_tree(self, desc: capi.DustTreeDesc) -> "DeviceTree":
+        return DeviceTree(self, desc)
+
+    def create_scene(self, instances) -> "Scene":
+        return Scene(self, instances)
+
+
+class DeviceTree:
+    def __init__(self, ctx: Context, desc: capi.DustTreeDesc):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(ctx.h, ctx.lib.dust_tree_upload(ctx.h, C.byref(desc), C.byref(h)), "dust_tree_upload")
+        self.h = h
+
+    @property
+    def leaf_count(self) -> int:
+        n = C.c_uint64()
+        self.ctx.lib.dust_tree_leaf_count(self.h, C.byref(n))
+        return int(n.value)
+
+    @property
+    def device_bytes(self) -> int:
+        n = C.c_uint64()
+        self.ctx.lib.dust_tree_device_bytes(self.h, C.byref(n))
+        return int(n.value)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.dust_tree_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def _ptr(buf):
+    """Device or host pointer of a torch tensor / numpy array / None."""
+    if buf is None:
+        return None
+    if isinstance(buf, np.ndarray):
+        return buf.ctypes.data
+    return buf.data_ptr()
+
+
+class Scene:
+    """`instances` = iterable of (obj2world[12] row-major 3x4, DeviceTree)."""
+
+    def __init__(self, ctx: Context, instances):
+        self.ctx = ctx
+        instances = list(instances)
+        self._trees = [t for _, t in instances]          # keep alive
+        arr = (DustInstance * max(1, len(instances)))()
+        for i, (m, t) in enumerate(instances):
+            arr[i].obj2world[:] = [float(v) for v in np.asarray(m, dtype=np.float32).reshape(12)]
+            arr[i].tree = t.h
+        h = C.c_void_p()
+        check(ctx.h, ctx.lib.dust_scene_create(ctx.h, arr, len(instances), C.byref(h)), "dust_scene_create")
+        self.h = h
+        self.n_instances = len(instances)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.dust_scene_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- dust_trace ------------------------------------------------------------------------------
+    def trace(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0,
+              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None):
+        """Host-buffer call: returns dict(radiance[H,W,4], hit_instance, hit_leaf, hit_voxel, hit_t)."""
+        ctx, lib = self.ctx, self.ctx.lib
+        cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count,
+                              (DUST_TRACE_WRITE_HITS if hits else 0) | (DUST_TRACE_STATS if stats else 0))
+        res = {}
+        if shard_count == 1:
+            n_out, shape = width * height, (height, width, 4)
+        else:
+            per = C.c_uint64()
+            lib.dust_shard_layout(width, height, shard_count, None, C.byref(per))
+            n_out, shape = int(per.value), (int(per.value), 4)
+        dt = np.float32 if fmt == DUST_FMT_RGBA32F else np.float16
+        rad = out if out is not None else np.empty(shape, dtype=dt)
+        assert rad.size == n_out * 4 and rad.dtype == dt
+        fr = DustFrame(_ptr(rad), None, None, None, None, DUST_MEM_HOST, fmt)
+        if hits:
+            res["hit_instance"] = np.empty((height, width), np.uint32)
+            res["hit_leaf"] = np.empty((height, width), np.uint32)
+            res["hit_voxel"] = np.empty((height, width), np.uint8)
+            res["hit_t"] = np.empty((height, width), np.float32)
+            fr.hit_instance, fr.hit_leaf = _ptr(res["hit_instance"]), _ptr(res["hit_leaf"])
+            fr.hit_voxel, fr.hit_t = _ptr(res["hit_voxel"]), _ptr(res["hit_t"])
+        check(ctx.h, lib.dust_trace(ctx.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr)), "dust_trace")
+        res["radiance"] = rad
+        if stats:
+            res["stats"] = ctx.stats()
+        return res
+
+    def trace_device(self, camera, sky, width, height, radiance, spp=1, max_bounces=0, seed=0, frame_index=0,
+                     shard_index=0, shard_count=1, stats=False, fmt=DUST_FMT_RGBA32F, hit_buffers=None):
+        """Device-buffer call (no copies, no sync): `radiance` is a CUDA tensor the kernel writes."""
+        ctx, lib = self.ctx, self.ctx.lib
+        flags = (DUST_TRACE_STATS if stats else 0) | (DUST_TRACE_WRITE_HITS if hit_buffers else 0)
+        cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count, flags)
+        fr = DustFrame(_ptr(radiance), None, None, None, None, DUST_MEM_DEVICE, fmt)
+        if hit_buffers:
+            fr.hit_instance, fr.hit_leaf, fr.hit_voxel, fr.hit_t = (_ptr(b) for b in hit_buffers)
+        check(ctx.h, lib.dust_trace(ctx.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr)), "dust_trace")
+
+    # ---- dust_trace_rays -------------------------------------------------------------------------
+    def trace_rays(self, rays: np.ndarray, stats=False) -> np.ndarray:
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DTYPE
+        hits = np.empty(len(rays), dtype=HIT_DTYPE)
+        ctx = self.ctx
+        check(ctx.h, ctx.lib.dust_trace_rays(ctx.h, self.h, _ptr(rays), len(rays), _ptr(hits), DUST_MEM_HOST,
+                                             DUST_TRACE_STATS if stats else 0), "dust_trace_rays")
+        return hits
+
+    def trace_rays_device(self, rays, hits, n, stats=False):
+        ctx = self.ctx
+        check(ctx.h, ctx.lib.dust_trace_rays(ctx.h, self.h, _ptr(rays), n, _ptr(hits), DUST_MEM_DEVICE,
+                                             DUST_TRACE_STATS if stats else 0), "dust_trace_rays")
+
+
+def shard_layout(width, height, shard_count):
+    tiles, px = C.c_uint32(), C.c_uint64()
+    capi.load().dust_shard_layout(width, height, shard_count, C.byref(tiles), C.byref(px))
+    return int(tiles.value), int(px.value)
+
+
+def resolve_shards(ctx: Context, width, height, shard_count, gathered, out):
+    check(ctx.h, ctx.lib.dust_resolve_shards(ctx.h, width, height, shard_count, _ptr(gathered), _ptr(out)), "dust_resolve_shards")

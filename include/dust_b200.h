@@ -1,0 +1,185 @@
+/*
+ * dust_b200 — C ABI of the B200-native replacement for Dust's ray-traversal hot path.
+ *
+ * This is the drop-in boundary: the reference (dust-engine/dust @ 7ea772b) has no FFI of its own;
+ * the path is entered through Rust traits and one method,
+ *     StandardPipeline::render(&mut self, gbuffer, tlas, params, camera)
+ *                                         crates/render/src/pipeline/standard.rs:228-240
+ * fed by VoxGeometry::from_tree (crates/vox/src/geometry.rs:55-179), PaletteMaterial::parameters
+ * (crates/vox/src/material.rs:106-118) and tlas_system (crates/render/src/accel_struct/tlas.rs:79-132).
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * Rust `extern "C"` binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns an int32 status (DUST_OK = 0),
+ * never throws or aborts; out-params by pointer; caller owns host memory, the library owns
+ * device memory behind opaque handles; one DustCtx per GPU, calls on a ctx serialised by the
+ * caller (the reference has one recorder thread per frame).  There is NO CPU fallback: without a
+ * CUDA device dust_ctx_create fails with DUST_ERR_NO_DEVICE.
+ */
+#ifndef DUST_B200_H
+#define DUST_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUST_ABI_VERSION 1
+
+enum {
+    DUST_OK = 0,
+    DUST_ERR_INVALID_ARGUMENT = 1,
+    DUST_ERR_NO_DEVICE = 2,
+    DUST_ERR_CUDA = 3,
+    DUST_ERR_UNSUPPORTED = 4,     /* e.g. a hierarchy other than (4,2,2) / (4,4,2,2) */
+    DUST_ERR_OUT_OF_MEMORY = 5
+};
+
+typedef struct DustCtx DustCtx;
+typedef struct DustTree DustTree;
+typedef struct DustScene DustScene;
+
+/*
+ * A `dust_vdb::Tree<hierarchy!(..)>` exactly as it lies in host memory
+ * (crates/vdb/src/tree.rs:7-13): the inline root node and, per non-root LEVEL (0 = leaf), the
+ * chunk base pointers of `Pool` (crates/vdb/src/pool.rs:3-17; chunks of 1024 items, item `ptr`
+ * lives at chunks[ptr >> 10] + (ptr & 1023) * item_bytes).  Node byte layouts are the
+ * #[repr(C)] ones: InternalNode {child_mask: [u64; 8^f/64], child_ptrs: [u32; 8^f]}
+ * (node/internal.rs:22-32), LeafNode {occupancy: u64, active: u64, material_ptr: u32, pad}
+ * = 24 bytes (node/leaf.rs:13-25).  `materials` / `palette` are the two other buffers the
+ * reference puts in a hit-group record (crates/vox/src/material.rs:30-41).
+ */
+typedef struct DustTreeDesc {
+    uint32_t n_levels;                 /* 3 for hierarchy!(4,2,2); leaf level included */
+    uint32_t fanout_log2[4];           /* root first, as written in hierarchy!() */
+    const void *root;
+    uint64_t root_bytes;
+    const void *const *pool_chunks[3]; /* [LEVEL] -> n_chunks[LEVEL] chunk base pointers */
+    uint32_t n_chunks[3];
+    uint32_t item_bytes[3];
+    uint32_t n_items[3];               /* Pool::top — slots ever handed out */
+    const uint8_t *materials;          /* 1 palette index per voxel (loader.rs:274-288) */
+    uint64_t n_materials;
+    const uint8_t *palette;            /* 255 x RGBA8 (loader.rs:208-218) */
+} DustTreeDesc;
+
+/* One TLAS instance: tlas.rs:99-117 (object->world 3x4 row-major) + the BLAS/SBT reference */
+typedef struct DustInstance {
+    float obj2world[12];
+    const DustTree *tree;
+} DustInstance;
+
+/* CameraSettings, crates/render/src/pipeline/standard.rs:813-827 (std430, 192 bytes).
+ * Only the view columns, position, tan_half_fov, near and far are read
+ * (assets/shaders/headers/camera.glsl:1-16, primary/primary.rgen:16-19). */
+typedef struct DustCamera {
+    float view_proj[16];
+    float inverse_view_proj[16];
+    float camera_view_col0[3]; float position_x;
+    float camera_view_col1[3]; float position_y;
+    float camera_view_col2[3]; float position_z;
+    float tan_half_fov, far, near, _padding;
+} DustCamera;
+
+/* SkyModelState, crates/render/src/pipeline/sky.rs:66-85 (std430, 224 bytes) — the output of
+ * Sunlight::bake(), uploaded as the `sunlight_config` uniform (headers/layout.playout:35-51). */
+typedef struct DustSkyChannel {
+    float config[9];
+    float radiance;
+    float ld_coefficient0, ld_coefficient1;
+    float ld_coefficient2[4];
+} DustSkyChannel;
+typedef struct DustSky {
+    DustSkyChannel r, g, b;
+    float direction[4];
+    float sunlight_intensity[4];
+} DustSky;
+
+enum {
+    DUST_TRACE_WRITE_HITS = 1u,   /* fill the hit_* arrays of DustFrame (sample-0 primary ray) */
+    DUST_TRACE_STATS      = 2u    /* count rays / visited words; read back with dust_get_stats */
+};
+
+/* Replaces the push constants + launch size of the four vkCmdTraceRaysKHR dispatches
+ * (standard.rs:447-463, 477-490).  Shards: the frame is cut into 32x32 pixel tiles, tile t
+ * (row-major) belongs to shard t % shard_count and is that shard's local tile t / shard_count. */
+typedef struct DustTraceConfig {
+    uint32_t width, height;
+    uint32_t spp;
+    uint32_t max_bounces;
+    uint32_t seed, frame_index;
+    uint32_t shard_index, shard_count;   /* 0,1 = whole frame, row-major output */
+    uint32_t flags;
+} DustTraceConfig;
+
+enum { DUST_MEM_HOST = 0, DUST_MEM_DEVICE = 1 };
+enum { DUST_FMT_RGBA32F = 0, DUST_FMT_RGBA16F = 1 };
+
+/* Replaces the GBuffer images the reference writes (standard.rs:880-917).  With shard_count == 1
+ * every array is row-major width*height.  With shard_count > 1 `radiance` is the compact
+ * per-shard tile buffer (dust_shard_layout) and the hit arrays must be NULL. */
+typedef struct DustFrame {
+    void *radiance;            /* RGBA32F (ACEScg rgb, a = 1) or RGBA16F */
+    uint32_t *hit_instance;    /* 0xFFFFFFFF = miss */
+    uint32_t *hit_leaf;        /* index in Tree::iter_leaf order == gl_PrimitiveID (geometry.rs:68) */
+    uint8_t *hit_voxel;        /* x<<4 | y<<2 | z inside the leaf (hit.rint:30-32) */
+    float *hit_t;              /* gl_HitTEXT; +inf on miss (miss.rmiss:15) */
+    uint32_t memory;           /* DUST_MEM_HOST or DUST_MEM_DEVICE */
+    uint32_t radiance_format;  /* DUST_FMT_* */
+} DustFrame;
+
+typedef struct DustRay { float o[3]; float tmin; float d[3]; float tmax; } DustRay;       /* 32 B */
+typedef struct DustHit { float t; uint32_t instance, leaf, voxel; } DustHit;              /* 16 B */
+
+typedef struct DustStats {
+    uint64_t primary_rays, bounce_rays, shadow_rays;
+    uint64_t mask_words;       /* W: 64-bit mask words the traversal had to read */
+    uint64_t child_ptrs;       /* P: child links followed */
+    uint64_t hits_shaded;      /* H */
+    uint64_t kernel_launches;  /* launches of this library's kernels since ctx creation */
+} DustStats;
+
+int32_t dust_abi_version(void);
+
+/* Context = one CUDA device + one stream.  Replaces the device/queue resources of
+ * crates/rhyolite_bevy/src/lib.rs:143-191 for this path. */
+int32_t dust_ctx_create(int32_t device, DustCtx **out);
+int32_t dust_ctx_destroy(DustCtx *ctx);
+/* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = ctx's own. */
+int32_t dust_ctx_set_stream(DustCtx *ctx, void *cuda_stream);
+int32_t dust_ctx_synchronize(DustCtx *ctx);
+const char *dust_last_error_string(const DustCtx *ctx);
+
+/* Replaces VoxGeometry::from_tree + the material/palette uploads (geometry.rs:55-179,
+ * loader.rs:208-236, 274-288): the tree is re-laid-out for the GPU and uploaded once. */
+int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out);
+int32_t dust_tree_destroy(DustCtx *ctx, DustTree *tree);
+int32_t dust_tree_leaf_count(const DustTree *tree, uint64_t *out);
+int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out);
+
+/* Replaces BLAS build + tlas_system + TLASStore::accel_struct (blas.rs:125-230, tlas.rs:37-132) */
+int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t n, DustScene **out);
+int32_t dust_scene_destroy(DustCtx *ctx, DustScene *scene);
+
+/* Replaces StandardPipeline::render (standard.rs:228-810) for the primary + bounce passes. */
+int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
+                   const DustTraceConfig *config, const DustFrame *frame);
+
+/* Explicit ray batch, closest hit (BASELINE.json config 5).  `memory` = DUST_MEM_*. */
+int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *rays, uint64_t n,
+                        DustHit *hits, uint32_t memory, uint32_t flags);
+
+/* Sharded frames: sizes of the compact per-shard buffer, and the un-permute that follows the
+ * all-gather (gathered = shard_count consecutive shard buffers; out = row-major width*height).
+ * Both device pointers, RGBA32F. */
+int32_t dust_shard_layout(uint32_t width, uint32_t height, uint32_t shard_count,
+                          uint32_t *tiles_per_shard, uint64_t *pixels_per_shard);
+int32_t dust_resolve_shards(DustCtx *ctx, uint32_t width, uint32_t height, uint32_t shard_count,
+                            const void *gathered, void *out);
+
+int32_t dust_get_stats(DustCtx *ctx, DustStats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,379 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes loader for oracle/_build/liboracle.so (the plain-C CPU restatement of the reference's hot
+path).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; nothing under dust_b200/ does.  The library is (re)built on demand with
+`make -C oracle` (gcc), because the checker has to exist wherever the tests run.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_SRCS = ["oracle_vdb.c", "oracle_vox.c", "oracle_sky.c", "oracle_trace.c", "oracle_dense.c",
+         "oracle_vdb.h", "oracle_vox.h", "oracle_sky.h", "oracle_trace.h", "Makefile"]
+
+O_MISS = 0xFFFFFFFF
+
+
+def build(force=False):
+    stale = force or not os.path.exists(LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(LIB_PATH)
+        stale = any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in _SRCS)
+    if stale:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return LIB_PATH
+
+
+class OSkyChannel(C.Structure):
+    _fields_ = [("config", C.c_float * 9), ("radiance", C.c_float), ("ld_coefficient0", C.c_float),
+                ("ld_coefficient1", C.c_float), ("ld_coefficient2", C.c_float * 4)]
+
+
+class OSky(C.Structure):
+    _fields_ = [("r", OSkyChannel), ("g", OSkyChannel), ("b", OSkyChannel),
+                ("direction", C.c_float * 4), ("sunlight_intensity", C.c_float * 4)]
+
+
+class OCamera(C.Structure):
+    _fields_ = [("view_proj", C.c_float * 16), ("inverse_view_proj", C.c_float * 16),
+                ("camera_view_col0", C.c_float * 3), ("position_x", C.c_float),
+                ("camera_view_col1", C.c_float * 3), ("position_y", C.c_float),
+                ("camera_view_col2", C.c_float * 3), ("position_z", C.c_float),
+                ("tan_half_fov", C.c_float), ("far", C.c_float), ("near", C.c_float), ("_padding", C.c_float)]
+
+
+class OTraceConfig(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("width", "height", "spp", "max_bounces", "seed", "frame_index", "y0", "y1")]
+
+
+class OStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class OVoxInstance(C.Structure):
+    _fields_ = [("model_id", C.c_uint32), ("obj2world", C.c_float * 12)]
+
+
+class OVoxModelData(C.Structure):
+    _fields_ = [("tree", C.c_void_p), ("size", C.c_uint8 * 3), ("n_materials", C.c_uint64), ("materials", C.c_void_p),
+                ("n_leaves", C.c_uint32), ("nodes", C.c_void_p), ("aabbs", C.c_void_p)]
+
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("instance", "<u4"), ("leaf", "<u4"), ("voxel", "<u4")])
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
+GPU_VOX_NODE = np.dtype([("x", "<u2"), ("y", "<u2"), ("z", "<u2"), ("w", "<u2"), ("mask", "<u8"),
+                         ("material_ptr", "<u4"), ("avg_albedo", "<u4")])
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = C.CDLL(build())
+    vp, u32, u64, i32, f32, f64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_float, C.c_double
+    pu32, pf32 = C.POINTER(u32), C.POINTER(f32)
+    sig = {
+        "o_bitmask_get": (i32, [vp, u32]), "o_bitmask_set": (None, [vp, u32, i32]),
+        "o_bitmask_count_ones": (u32, [vp, u32]), "o_bitmask_iter_set_bits": (u32, [vp, u32, pu32, u32]),
+        "o_pool_init": (None, [vp, u32, u32]), "o_pool_destroy": (None, [vp]), "o_pool_alloc": (u32, [vp]),
+        "o_pool_free": (None, [vp, u32]), "o_pool_num_chunks": (u32, [vp]),
+        "o_tree_new": (vp, [u32, pu32]), "o_tree_destroy": (None, [vp]),
+        "o_tree_view": (vp, [u32, pu32, vp, vp, pu32, pu32]), "o_tree_view_free": (None, [vp]),
+        "o_tree_set_value": (i32, [vp, u32, u32, u32, i32]), "o_tree_get_value": (i32, [vp, u32, u32, u32]),
+        "o_tree_iter": (u64, [vp, pu32, u64]), "o_tree_iter_leaf": (u64, [vp, pu32, pu32, u64]),
+        "o_tree_num_leaves": (u64, [vp]), "o_tree_root": (vp, [vp]), "o_tree_node_bytes": (u32, [vp, u32]),
+        "o_tree_pool_count": (u32, [vp, u32]), "o_tree_pool_top": (u32, [vp, u32]),
+        "o_tree_pool_num_chunks": (u32, [vp, u32]), "o_tree_pool_chunk": (vp, [vp, u32, u32]),
+        "o_meta_mask": (u32, [vp]), "o_lowest_common_ancestor_level": (u32, [pu32, pu32, u32, u32]),
+        "o_accessor_init": (None, [vp, vp]), "o_accessor_get": (i32, [vp, u32, u32, u32]),
+        "o_vox_parse": (vp, [vp, u64]), "o_vox_scene_free": (None, [vp]),
+        "o_vox_instances": (u32, [vp, C.POINTER(OVoxInstance), u32]),
+        "o_vox_load_model": (C.POINTER(OVoxModelData), [vp, u32]), "o_vox_model_free": (None, [C.POINTER(OVoxModelData)]),
+        "o_vox_to_transform": (None, [C.POINTER(i32), C.c_uint8, pu32, pf32]),
+        "o_sunlight_bake": (None, [f32, pf32, pf32, C.POINTER(OSky)]),
+        "o_sky_radiance": (None, [C.POINTER(OSky), pf32, pf32]), "o_sun_radiance": (None, [C.POINTER(OSky), pf32, pf32]),
+        "o_srgb_to_linear": (f32, [f32]),
+        "o_scene_create": (vp, [u32, pf32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]), "o_scene_destroy": (None, [vp]),
+        "o_render": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
+        "o_trace_rays": (None, [vp, vp, u64, vp, C.POINTER(OStats), u32]),
+        "o_leaf_dda": (i32, [pf32, pf32, u64, f32, pf32, pu32]),
+        "o_camera_ray": (None, [C.POINTER(OCamera), u32, u32, u32, u32, f32, f32, pf32, pf32]),
+        "o_pcg": (u32, [u32]), "o_cossin_2pi": (None, [f32, pf32, pf32]),
+        "o_rotate_by_normal": (None, [pf32, pf32, pf32]), "o_world2obj": (None, [pf32, pf32]),
+        "o_dense_from_tree": (vp, [vp]), "o_dense_free": (None, [vp]),
+        "o_dense_march": (i32, [vp, C.POINTER(f64), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _u32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+class Tree:
+    """Oracle Tree (oracle_vdb.c).  value: None / False / True."""
+
+    def __init__(self, hierarchy, _borrowed=None, _owner=None):
+        self.hierarchy = tuple(int(h) for h in hierarchy)
+        self._owner = _owner
+        if _borrowed is not None:
+            self._h, self._own = _borrowed, False
+        else:
+            arr = (C.c_uint32 * len(self.hierarchy))(*self.hierarchy)
+            self._h, self._own = lib().o_tree_new(len(self.hierarchy), arr), True
+            if not self._h:
+                raise ValueError("unsupported hierarchy")
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self._h:
+            lib().o_tree_destroy(self._h)
+            self._h = None
+
+    @property
+    def levels(self):
+        return len(self.hierarchy)
+
+    def set_value(self, xyz, value):
+        v = -1 if value is None else int(bool(value))
+        if lib().o_tree_set_value(self._h, int(xyz[0]), int(xyz[1]), int(xyz[2]), v) != 0:
+            raise NotImplementedError("clearing through an InternalNode is todo!() in the reference")
+
+    def get_value(self, xyz):
+        r = lib().o_tree_get_value(self._h, int(xyz[0]), int(xyz[1]), int(xyz[2]))
+        return None if r < 0 else bool(r)
+
+    def iter(self):
+        n = lib().o_tree_iter(self._h, None, 0)
+        out = np.zeros((n, 3), np.uint32)
+        if n:
+            lib().o_tree_iter(self._h, _u32p(out), n)
+        return out
+
+    def iter_leaf(self):
+        n = lib().o_tree_num_leaves(self._h)
+        pos, ptr = np.zeros((n, 3), np.uint32), np.zeros(n, np.uint32)
+        if n:
+            lib().o_tree_iter_leaf(self._h, _u32p(pos), _u32p(ptr), n)
+        return pos, ptr
+
+    def node_bytes(self, level):
+        return lib().o_tree_node_bytes(self._h, level)
+
+    def pool_count(self, level):
+        return lib().o_tree_pool_count(self._h, level)
+
+    def pool_top(self, level):
+        return lib().o_tree_pool_top(self._h, level)
+
+    def root_bytes(self):
+        return C.string_at(lib().o_tree_root(self._h), self.node_bytes(self.levels - 1))
+
+    def pool_bytes(self, level):
+        top, nb = self.pool_top(level), self.node_bytes(level)
+        out = bytearray()
+        for c in range(lib().o_tree_pool_num_chunks(self._h, level)):
+            n = min(1024, top - c * 1024)
+            if n <= 0:
+                break
+            out += C.string_at(lib().o_tree_pool_chunk(self._h, level, c), n * nb)
+        return bytes(out)
+
+    def meta_mask(self):
+        return lib().o_meta_mask(self._h)
+
+    def accessor_get_many(self, xyz):
+        acc = C.create_string_buffer(64)
+        lib().o_accessor_init(acc, self._h)
+        out = []
+        for x, y, z in np.asarray(xyz).reshape(-1, 3):
+            r = lib().o_accessor_get(acc, int(x), int(y), int(z))
+            out.append(None if r < 0 else bool(r))
+        return out
+
+
+class TreeView(Tree):
+    """Oracle view over a tree described by a DustTreeDesc-shaped object (same bytes the product got)."""
+
+    def __init__(self, desc):
+        n = int(desc.n_levels)
+        self.hierarchy = tuple(int(desc.fanout_log2[i]) for i in range(n))
+        self._desc = desc                                   # keeps the described memory alive
+        hier = (C.c_uint32 * n)(*self.hierarchy)
+        chunks = (C.c_void_p * 3)(*[C.cast(desc.pool_chunks[i], C.c_void_p) for i in range(3)])
+        nch = (C.c_uint32 * 3)(*[int(desc.n_chunks[i]) for i in range(3)])
+        tops = (C.c_uint32 * 3)(*[int(desc.n_items[i]) for i in range(3)])
+        self._h = lib().o_tree_view(n, hier, desc.root, chunks, nch, tops)
+        self._own, self._owner = False, None
+        if not self._h:
+            raise ValueError("unsupported hierarchy")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().o_tree_view_free(self._h)
+            self._h = None
+
+
+def lowest_common_ancestor_level(a, b, mask, root_level):
+    return lib().o_lowest_common_ancestor_level((C.c_uint32 * 3)(*a), (C.c_uint32 * 3)(*b), mask, root_level)
+
+
+class VoxModel:
+    def __init__(self, ptr):
+        self._p = ptr
+        d = ptr.contents
+        self.tree = Tree((4, 2, 2), _borrowed=d.tree, _owner=self)
+        self.size = tuple(d.size)
+        self.materials = (np.frombuffer(C.string_at(d.materials, d.n_materials), np.uint8) if d.n_materials else np.zeros(0, np.uint8))
+        self.nodes = (np.frombuffer(C.string_at(d.nodes, d.n_leaves * 24), GPU_VOX_NODE) if d.n_leaves else np.zeros(0, GPU_VOX_NODE))
+        self.aabbs = (np.frombuffer(C.string_at(d.aabbs, d.n_leaves * 24), np.float32).reshape(-1, 6) if d.n_leaves else np.zeros((0, 6), np.float32))
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self.tree = None
+            lib().o_vox_model_free(self._p)
+            self._p = None
+
+
+class VoxFile:
+    def __init__(self, data: bytes):
+        self._buf = bytes(data)
+        self._h = lib().o_vox_parse(self._buf, len(self._buf))
+        if not self._h:
+            raise ValueError("oracle: cannot parse .vox")
+        n = lib().o_vox_instances(self._h, None, 0)
+        arr = (OVoxInstance * max(1, n))()
+        lib().o_vox_instances(self._h, arr, n)
+        self.instances = [(int(arr[i].model_id), np.array(arr[i].obj2world, np.float32)) for i in range(n)]
+        # OVoxScene: n_models u32, pad, models*, palette[256][4] @16
+        self.palette = np.frombuffer(C.string_at(self._h + 16, 1024), np.uint8).reshape(256, 4).copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().o_vox_scene_free(self._h)
+            self._h = None
+
+    def load_model(self, model_id) -> VoxModel:
+        p = lib().o_vox_load_model(self._h, model_id)
+        if not p:
+            raise ValueError("oracle: load_model failed")
+        return VoxModel(p)
+
+
+def to_transform(translation, rotation, size):
+    out = (C.c_float * 12)()
+    lib().o_vox_to_transform((C.c_int32 * 3)(*translation), rotation, (C.c_uint32 * 3)(*size), out)
+    return np.array(out, np.float32)
+
+
+def sunlight_bake(turbidity=1.0, albedo=(0.2, 0.2, 0.2), direction=(0.0, 0.80114365, -0.5984721)) -> OSky:
+    out = OSky()
+    lib().o_sunlight_bake(float(turbidity), (C.c_float * 3)(*albedo), (C.c_float * 3)(*direction), C.byref(out))
+    return out
+
+
+def sky_radiance(sky: OSky, d):
+    out = (C.c_float * 3)()
+    lib().o_sky_radiance(C.byref(sky), (C.c_float * 3)(*d), out)
+    return np.array(out, np.float32)
+
+
+def sun_radiance(sky: OSky, d):
+    out = (C.c_float * 3)()
+    lib().o_sun_radiance(C.byref(sky), (C.c_float * 3)(*d), out)
+    return np.array(out, np.float32)
+
+
+def as_struct(cls, other):
+    """Reinterpret a same-layout ctypes struct (e.g. dust_b200.capi.DustSky) as the oracle's type."""
+    assert C.sizeof(cls) == C.sizeof(other)
+    return cls.from_buffer_copy(bytes(other))
+
+
+class Scene:
+    """instances: list of (obj2world[12], tree_handle(void*), materials ndarray, palette ndarray[>=255,4]).
+    `tree_handle` is an OTree* — either an oracle Tree._h, or ANY memory with the same layout."""
+
+    def __init__(self, instances):
+        n = len(instances)
+        self._keep = instances
+        o2w = np.ascontiguousarray(np.stack([np.asarray(i[0], np.float32).reshape(12) for i in instances]) if n else np.zeros((0, 12), np.float32))
+        trees = (C.c_void_p * max(1, n))(*[i[1] for i in instances])
+        self._mats = [np.ascontiguousarray(i[2], np.uint8) for i in instances]
+        self._pals = [np.ascontiguousarray(i[3], np.uint8) for i in instances]
+        mats = (C.c_void_p * max(1, n))(*[m.ctypes.data for m in self._mats])
+        pals = (C.c_void_p * max(1, n))(*[p.ctypes.data for p in self._pals])
+        self._h = lib().o_scene_create(n, o2w.ctypes.data_as(C.POINTER(C.c_float)), trees, mats, pals)
+        if not self._h:
+            raise ValueError("oracle: scene_create failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().o_scene_destroy(self._h)
+            self._h = None
+
+    def render(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0, y0=0, y1=None,
+               hits=True, threads=None):
+        cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
+        sk = sky if isinstance(sky, OSky) else as_struct(OSky, sky)
+        y1 = height if y1 is None else y1
+        cfg = OTraceConfig(width, height, spp, max_bounces, seed, frame_index, y0, y1)
+        rad = np.zeros((height, width, 4), np.float32)
+        res = {"radiance": rad}
+        hp = [None] * 4
+        if hits:
+            res["hit_instance"] = np.full((height, width), O_MISS, np.uint32)
+            res["hit_leaf"] = np.full((height, width), O_MISS, np.uint32)
+            res["hit_voxel"] = np.full((height, width), 0xFF, np.uint8)
+            res["hit_t"] = np.full((height, width), np.inf, np.float32)
+            hp = [res[k].ctypes.data for k in ("hit_instance", "hit_leaf", "hit_voxel", "hit_t")]
+        st = OStats()
+        lib().o_render(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), rad.ctypes.data, hp[0], hp[1], hp[2], hp[3],
+                       C.byref(st), threads or os.cpu_count() or 1)
+        res["stats"] = st.as_dict()
+        return res
+
+    def trace_rays(self, rays: np.ndarray, threads=None):
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype.itemsize == 32
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        st = OStats()
+        lib().o_trace_rays(self._h, rays.ctypes.data, len(rays), hits.ctypes.data, C.byref(st), threads or os.cpu_count() or 1)
+        return hits, st.as_dict()
+
+
+def leaf_dda(origin, direction, grid, tmin=0.0):
+    t, v = C.c_float(), C.c_uint32()
+    ok = lib().o_leaf_dda((C.c_float * 3)(*origin), (C.c_float * 3)(*direction), int(grid), float(tmin), C.byref(t), C.byref(v))
+    return (float(t.value), int(v.value)) if ok else None
+
+
+class Dense:
+    def __init__(self, tree: Tree):
+        self._h = lib().o_dense_from_tree(tree._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().o_dense_free(self._h)
+            self._h = None
+
+    def march(self, o, d, tmin, tmax):
+        xyz, t = (C.c_int32 * 3)(), C.c_double()
+        ok = lib().o_dense_march(self._h, (C.c_double * 3)(*[float(v) for v in o]), (C.c_double * 3)(*[float(v) for v in d]),
+                                 float(tmin), float(tmax), xyz, C.byref(t))
+        return (tuple(xyz), float(t.value)) if ok else None

@@ -1,0 +1,177 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/dust_b200.h), against
+the CPU oracle on the same seeded inputs.  Bar: hit instance / leaf / voxel ids and t BIT-EXACT;
+radiance within 1e-4 relative (BASELINE.json north_star) — the tolerance covers CUDA's
+expf/powf/acosf vs glibc's in the sky model only; every ray path is reproduced exactly.
+"""
+import numpy as np
+import pytest
+
+from conftest import BuiltScene
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _cam_for(scene, host, width, height, eye_dir=(1.2, 0.9, 1.2)):
+    lo, hi = scene.bounds()
+    c = (lo + hi) / 2
+    eye = c + np.array(eye_dir) * (hi - lo).max()
+    return host.camera_look_at(eye, c, width=width, height=height)
+
+
+def _assert_hits_equal(g, o):
+    for k in ("hit_instance", "hit_leaf", "hit_voxel"):
+        bad = np.argwhere(g[k] != o[k])
+        assert len(bad) == 0, f"{k}: {len(bad)} pixels differ, first {bad[:3].tolist()}"
+    assert np.array_equal(g["hit_t"].view(np.uint32), o["hit_t"].view(np.uint32)), "hit_t not bit-exact"
+
+
+def _assert_radiance_close(g, o, rtol=RTOL):
+    a, b = g["radiance"][..., :3].astype(np.float64), o["radiance"][..., :3].astype(np.float64)
+    # relative to the pixel's own magnitude (luminance floor 1e-3 of the frame mean avoids 0/0 in black pixels)
+    scale = np.maximum(np.abs(b).max(axis=-1, keepdims=True), 1e-3 * np.abs(b).mean())
+    err = np.abs(a - b) / scale
+    assert err.max() <= rtol, f"radiance max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+@pytest.fixture(scope="module")
+def teapot(oracle, ctx):
+    from dust_b200 import scenes
+    return BuiltScene(scenes.teapot_like(), oracle, ctx)
+
+
+@pytest.fixture(scope="module")
+def castle_small(oracle, ctx):
+    from dust_b200 import scenes
+    return BuiltScene(scenes.castle_like(tiles=2, tile=64, height=128, props=12), oracle, ctx)
+
+
+def test_teapot_primary_hits_bit_exact(teapot, host):
+    """BASELINE config 1 geometry (teapot stand-in, 256x256, primary only, 1 spp) on the GPU."""
+    W = H = 256
+    cam, sky = _cam_for(teapot, host, W, H), host.sunlight_bake()
+    g = teapot.loaded.scene.trace(cam, sky, W, H, spp=1, max_bounces=0, hits=True)
+    o = teapot.oscene.render(cam, sky, W, H, spp=1, max_bounces=0)
+    assert (o["hit_instance"] != 0xFFFFFFFF).mean() > 0.05
+    _assert_hits_equal(g, o)
+    _assert_radiance_close(g, o)
+
+
+@pytest.mark.parametrize("spp,bounces", [(1, 1), (4, 1), (2, 2)])
+def test_teapot_bounces_radiance(teapot, host, spp, bounces):
+    W = H = 128
+    cam, sky = _cam_for(teapot, host, W, H), host.sunlight_bake()
+    g = teapot.loaded.scene.trace(cam, sky, W, H, spp=spp, max_bounces=bounces, seed=7, frame_index=3, hits=True)
+    o = teapot.oscene.render(cam, sky, W, H, spp=spp, max_bounces=bounces, seed=7, frame_index=3)
+    _assert_hits_equal(g, o)
+    _assert_radiance_close(g, o)
+
+
+def test_castle_small_instances_bit_exact(castle_small, host):
+    """Many instances with all 24 rotations + mirrors; the castle.rs camera and zenith sun."""
+    from dust_b200 import scenes
+    W, H = 320, 180
+    cam = host.camera_look_at(width=W, height=H, **{k: v for k, v in scenes.CASTLE_CAMERA.items()})
+    sky = host.sunlight_bake(direction=host.castle_sun_direction(0.0))
+    g = castle_small.loaded.scene.trace(cam, sky, W, H, spp=1, max_bounces=0, hits=True)
+    o = castle_small.oscene.render(cam, sky, W, H, spp=1, max_bounces=0)
+    assert (o["hit_instance"] != 0xFFFFFFFF).mean() > 0.2
+    assert len(np.unique(o["hit_instance"])) > 3
+    _assert_hits_equal(g, o)
+    _assert_radiance_close(g, o)
+
+
+def test_castle_small_gi(castle_small, host):
+    W, H = 160, 96
+    cam = _cam_for(castle_small, host, W, H, eye_dir=(0.7, 0.5, 0.9))
+    sky = host.sunlight_bake()
+    g = castle_small.loaded.scene.trace(cam, sky, W, H, spp=2, max_bounces=2, seed=11, hits=True, stats=True)
+    o = castle_small.oscene.render(cam, sky, W, H, spp=2, max_bounces=2, seed=11)
+    _assert_hits_equal(g, o)
+    _assert_radiance_close(g, o)
+    # ray counts are order-independent and must agree exactly
+    for k in ("primary_rays", "bounce_rays", "shadow_rays", "hits_shaded"):
+        assert g["stats"][k] == o["stats"][k], k
+
+
+def test_single_instance_visit_counters_match_oracle(teapot, host):
+    """With one instance the traversal order is fully specified, so W and P match exactly."""
+    W = H = 96
+    cam, sky = _cam_for(teapot, host, W, H), host.sunlight_bake()
+    g = teapot.loaded.scene.trace(cam, sky, W, H, spp=1, max_bounces=1, seed=3, stats=True)
+    o = teapot.oscene.render(cam, sky, W, H, spp=1, max_bounces=1, seed=3)
+    for k in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded"):
+        assert g["stats"][k] == o["stats"][k], (k, g["stats"][k], o["stats"][k])
+
+
+def test_fp16_output_and_device_buffers(teapot, host, ctx):
+    import torch
+    from dust_b200.capi import DUST_FMT_RGBA16F
+    W = H = 64
+    cam, sky = _cam_for(teapot, host, W, H), host.sunlight_bake()
+    ref = teapot.loaded.scene.trace(cam, sky, W, H, spp=1, max_bounces=1)["radiance"]
+    h16 = teapot.loaded.scene.trace(cam, sky, W, H, spp=1, max_bounces=1, fmt=DUST_FMT_RGBA16F)["radiance"]
+    assert np.array_equal(h16, ref.astype(np.float16))
+    dev = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    ctx.use_torch_stream()
+    teapot.loaded.scene.trace_device(cam, sky, W, H, dev, spp=1, max_bounces=1)
+    torch.cuda.synchronize()
+    ctx.set_stream(None)
+    assert np.array_equal(dev.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_frame_equals_whole_frame(castle_small, host, ctx, shards):
+    """Tile-sharded render + resolve == single-GPU frame, bit for bit (ragged 200x120 frame)."""
+    import torch
+    from dust_b200.pipeline import resolve_shards, shard_layout
+    W, H = 200, 120
+    cam = _cam_for(castle_small, host, W, H, eye_dir=(0.6, 0.8, 0.7))
+    sky = host.sunlight_bake()
+    whole = castle_small.loaded.scene.trace(cam, sky, W, H, spp=2, max_bounces=1, seed=5)["radiance"]
+    _, per = shard_layout(W, H, shards)
+    gathered = torch.zeros((shards, per, 4), dtype=torch.float32, device="cuda")
+    for s in range(shards):
+        castle_small.loaded.scene.trace_device(cam, sky, W, H, gathered[s], spp=2, max_bounces=1, seed=5,
+                                               shard_index=s, shard_count=shards)
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    resolve_shards(ctx, W, H, shards, gathered, out)
+    ctx.synchronize()
+    assert np.array_equal(out.cpu().numpy(), whole)
+
+
+def test_ray_batch_small_domain(oracle, host, ctx):
+    """BASELINE config 5 in miniature: hierarchy!(4,4,2,2), sphere-union leaf fill, random rays."""
+    from dust_b200 import scenes
+    from dust_b200.pipeline import Scene
+    dom = host.SynthDomain(seed=5, fill=0.02, domain_leaves=96)
+    assert dom.num_leaves > 1000
+    desc = dom.describe()
+    dtree = ctx.upload_tree(desc)
+    assert dtree.leaf_count == dom.num_leaves
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    scene = Scene(ctx, [(ident, dtree)])
+    rays = scenes.ray_batch(200_000, dom.extent, seed=5)
+    g = scene.trace_rays(rays)
+    otree = oracle.TreeView(desc)
+    oscene = oracle.Scene([(ident, otree._h, dom.materials, dom.palette)])
+    o, _ = oscene.trace_rays(rays)
+    assert (o["instance"] != 0xFFFFFFFF).mean() > 0.1
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+
+
+def test_empty_scene_and_errors(host, ctx):
+    from dust_b200.capi import DustError
+    from dust_b200.pipeline import Scene
+    W = H = 16
+    cam = host.camera_look_at((0, 0, 10), (0, 0, 0), width=W, height=H)
+    sky = host.sunlight_bake()
+    empty = Scene(ctx, [])
+    r = empty.trace(cam, sky, W, H, hits=True)
+    assert (r["hit_instance"] == 0xFFFFFFFF).all() and np.isinf(r["hit_t"]).all()
+    assert np.isfinite(r["radiance"]).all()
+    with pytest.raises(DustError):
+        empty.trace(cam, sky, 0, 16)
+    with pytest.raises(DustError):
+        empty.trace(cam, sky, W, H, shard_index=2, shard_count=2)
