@@ -102,7 +102,7 @@ SYMBOLS = {
     "dust_abi_version": (C.c_int32, []),
     "dust_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "dust_ctx_destroy": (C.c_int32, [C.c_void_p]),
-    "dust_ctx_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "dust_ctx_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
     "dust_ctx_synchronize": (C.c_int32, [C.c_void_p]),
     "dust_last_error_string": (C.c_char_p, [C.c_void_p]),
     "dust_tree_upload": (C.c_int32, [C.c_void_p, C.POINTER(DustTreeDesc), C.POINTER(C.c_void_p)]),

@@ -289,10 +289,10 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     return DUST_OK;
 }
 
-int32_t dust_ctx_set_stream(DustCtx *ctx, void *cuda_stream)
+int32_t dust_ctx_set_stream(DustCtx *ctx, void *cuda_stream, int32_t external)
 {
     if (!ctx) return DUST_ERR_INVALID_ARGUMENT;
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = external ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return DUST_OK;
 }
 

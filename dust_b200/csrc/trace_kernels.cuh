@@ -218,12 +218,15 @@ __device__ __forceinline__ bool trace_instance(const DInstance &in, f3 ow, f3 dw
     if (fabsf(d.y) < DUST_DIR_EPS) d.y = copysignf(DUST_DIR_EPS, d.y);
     if (fabsf(d.z) < DUST_DIR_EPS) d.z = copysignf(DUST_DIR_EPS, d.z);
     const float ix_ = 1.0f / d.x, iy_ = 1.0f / d.y, iz_ = 1.0f / d.z;
-    const float nbx = -(ix_ * o.x), nby = -(iy_ * o.y), nbz = -(iz_ * o.z);
     constexpr int Ei = NL == 3 ? 256 : 4096;
     constexpr float E = (float)Ei;
-    float t1x = __fmaf_rn(E, ix_, nbx), t1y = __fmaf_rn(E, iy_, nby), t1z = __fmaf_rn(E, iz_, nbz);
-    float t_enter = fmaxf(fmaxf(fminf(nbx, t1x), fminf(nby, t1y)), fmaxf(fminf(nbz, t1z), tmin));
-    float t_exit = fminf(fminf(fmaxf(nbx, t1x), fmaxf(nby, t1y)), fminf(fmaxf(nbz, t1z), tmax));
+    // plane times are (plane - o) * inv: difference first, plane*inv - o*inv would cancel (|o/d| >> t)
+    const float t0x = (0.0f - o.x) * ix_, t0y = (0.0f - o.y) * iy_, t0z = (0.0f - o.z) * iz_;
+    const float t1x = (E - o.x) * ix_, t1y = (E - o.y) * iy_, t1z = (E - o.z) * iz_;
+    float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+    // walk a hair past tmax (acceptance stays exact): see oracle_trace.c / DESIGN.md "Traversal semantics"
+    const float tmax_pad = tmax + (fabsf(tmax) * 3.814697265625e-06f + 9.5367431640625e-07f);
+    float t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
     if (!(t_enter <= t_exit)) return false;
     int ix = (int)floorf(__fmaf_rn(d.x, t_enter, o.x));
     int iy = (int)floorf(__fmaf_rn(d.y, t_enter, o.y));
@@ -283,11 +286,11 @@ __device__ __forceinline__ bool trace_instance(const DInstance &in, f3 ow, f3 dw
                 return true;
             }
         }
-        float tx = __fmaf_rn((float)(px_ ? cx + L : cx), ix_, nbx);
-        float ty = __fmaf_rn((float)(py_ ? cy + L : cy), iy_, nby);
-        float tz = __fmaf_rn((float)(pz_ ? cz + L : cz), iz_, nbz);
+        float tx = ((float)(px_ ? cx + L : cx) - o.x) * ix_;
+        float ty = ((float)(py_ ? cy + L : cy) - o.y) * iy_;
+        float tz = ((float)(pz_ ? cz + L : cz) - o.z) * iz_;
         float t_next = fminf(fminf(tx, ty), tz);
-        if (!(t_next < t_exit)) return false;
+        if (!(t_next <= t_exit)) return false;   // inclusive, see oracle_trace.c / DESIGN.md
         if (tx <= t_next) { ix = px_ ? cx + L : cx - 1; if (ix < 0 || ix >= Ei) return false; }
         else { int ip = (int)floorf(__fmaf_rn(d.x, t_next, o.x)); ix = min(max(ip, cx), cx + L - 1); }
         if (ty <= t_next) { iy = py_ ? cy + L : cy - 1; if (iy < 0 || iy >= Ei) return false; }
@@ -334,7 +337,10 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, f3 o, f3 d, fl
     best.hit = false; best.instance = 0xFFFFFFFFu;
     float cur = tmax;
     if (sc.n_inst == 0) return;
-    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    // box tests only: a zero component gets a huge FINITE inverse so (lo - o) * inv is never 0 * inf
+    f3 inv = mk3(fabsf(d.x) < 1e-30f ? copysignf(1e30f, d.x) : 1.0f / d.x,
+                 fabsf(d.y) < 1e-30f ? copysignf(1e30f, d.y) : 1.0f / d.y,
+                 fabsf(d.z) < 1e-30f ? copysignf(1e30f, d.z) : 1.0f / d.z);
     int stack[DUST_BVH_STACK];
     int sp = 0;
     int node = 0;

@@ -37,7 +37,9 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream_ptr):
-        check(self.h, self.lib.dust_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "dust_ctx_set_stream")
+        """cuda_stream_ptr: a cudaStream_t handle as int (0 = legacy default stream); None = the ctx's own stream."""
+        ext = cuda_stream_ptr is not None
+        check(self.h, self.lib.dust_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0), int(ext)), "dust_ctx_set_stream")
 
     def use_torch_stream(self):
         import torch

@@ -145,8 +145,10 @@ int32_t dust_abi_version(void);
  * crates/rhyolite_bevy/src/lib.rs:143-191 for this path. */
 int32_t dust_ctx_create(int32_t device, DustCtx **out);
 int32_t dust_ctx_destroy(DustCtx *ctx);
-/* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = ctx's own. */
-int32_t dust_ctx_set_stream(DustCtx *ctx, void *cuda_stream);
+/* external != 0: run on the caller's cudaStream_t `cuda_stream` (e.g. torch's current stream; the
+ * legacy default stream is the NULL handle, hence the explicit flag).  external == 0: back to the
+ * context's own stream. */
+int32_t dust_ctx_set_stream(DustCtx *ctx, void *cuda_stream, int32_t external);
 int32_t dust_ctx_synchronize(DustCtx *ctx);
 const char *dust_last_error_string(const DustCtx *ctx);
 

@@ -26,6 +26,10 @@ struct OScene {
     uint32_t n_orders;
     uint32_t **orders;
     const OTree **order_trees;
+    /* optional early-out: padded world box of every instance's [0,E]^3 object box.  Purely a
+     * speed-up of the linear instance loop (o_scene_set_cull; tests check on == off). */
+    int cull;
+    float *boxes;     /* n * 6: lo xyz, hi xyz */
 };
 
 /* ---------------------------------------------------------------- helpers */
@@ -138,14 +142,65 @@ OScene *o_scene_create(uint32_t n, const float *obj2world, const OTree *const *t
         }
         in->leaf_order = s->orders[j];
     }
+    s->cull = 1;
+    s->boxes = (float *)calloc(n ? n : 1, 6 * sizeof(float));
+    for (uint32_t k = 0; k < n; k++) {
+        const OInstance *in = &s->inst[k];
+        /* object-space bounds of the occupied leaves (a leaf spans 4 voxels) */
+        uint64_t nl = o_tree_num_leaves(in->tree);
+        uint32_t *pos = (uint32_t *)malloc(sizeof(uint32_t) * 3 * (nl ? nl : 1));
+        o_tree_iter_leaf(in->tree, pos, NULL, nl);
+        double omin[3] = { 0, 0, 0 }, omax[3] = { 0, 0, 0 };
+        for (uint64_t l = 0; l < nl; l++)
+            for (int a = 0; a < 3; a++) {
+                double v = (double)pos[3 * l + a];
+                if (l == 0 || v < omin[a]) omin[a] = v;
+                if (l == 0 || v + 4.0 > omax[a]) omax[a] = v + 4.0;
+            }
+        free(pos);
+        double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY }, big = 0.0;
+        for (int c = 0; c < 8; c++) {
+            double p[3] = { (c & 1) ? omax[0] : omin[0], (c & 2) ? omax[1] : omin[1], (c & 4) ? omax[2] : omin[2] };
+            for (int a = 0; a < 3; a++) {
+                const float *M = in->obj2world + 4 * a;
+                double w = (double)M[0] * p[0] + (double)M[1] * p[1] + (double)M[2] * p[2] + (double)M[3];
+                if (w < lo[a]) lo[a] = w;
+                if (w > hi[a]) hi[a] = w;
+                if (fabs(w) > big) big = fabs(w);
+            }
+        }
+        double pad = 0.05 + 1e-4 * big;
+        for (int a = 0; a < 3; a++) { s->boxes[6 * k + a] = (float)(lo[a] - pad); s->boxes[6 * k + 3 + a] = (float)(hi[a] + pad); }
+    }
     return s;
+}
+
+void o_scene_set_cull(OScene *s, int enabled) { s->cull = enabled; }
+
+/* 1/d for the box tests only; a zero component becomes a huge FINITE value so that (b - o) * inv is
+ * never 0 * inf */
+static void cull_inv(const float d[3], float inv[3])
+{
+    for (int a = 0; a < 3; a++) inv[a] = fabsf(d[a]) < 1e-30f ? copysignf(1e30f, d[a]) : 1.0f / d[a];
+}
+
+/* conservative: returns 0 only when the ray certainly misses the padded box within [tmin, tmax] */
+static int box_may_hit(const float *b, const float o[3], const float inv[3], float tmin, float tmax)
+{
+    float t0 = tmin, t1 = tmax;
+    for (int a = 0; a < 3; a++) {
+        float ta = (b[a] - o[a]) * inv[a], tb = (b[3 + a] - o[a]) * inv[a];
+        t0 = fmaxf(t0, fminf(ta, tb));     /* inv[] is finite (cull_inv), so no 0 * inf = NaN here */
+        t1 = fminf(t1, fmaxf(ta, tb));
+    }
+    return t0 <= t1;
 }
 
 void o_scene_destroy(OScene *s)
 {
     if (!s) return;
     for (uint32_t j = 0; j < s->n_orders; j++) free(s->orders[j]);
-    free(s->orders); free((void *)s->order_trees); free(s->inst); free(s);
+    free(s->orders); free((void *)s->order_trees); free(s->inst); free(s->boxes); free(s);
 }
 
 /* --------------------------------------------------------------- LEAF STEP */
@@ -222,7 +277,8 @@ typedef struct InstHit {
  * Per iteration: descend from the root with the InternalNode::get index arithmetic
  * (crates/vdb/src/node/internal.rs:77-95) until a clear child_mask bit (empty cell of edge L)
  * or a leaf (L = 4, LEAF STEP); then leave the cell through its exit planes
- * t_a = fma(plane_a, 1/d_a, -o_a/d_a); axes whose t_a equals the minimum step one cell
+ * t_a = (plane_a - o_a) * (1/d_a)  (the difference first: plane*inv - o*inv would cancel
+ * catastrophically, |o/d| >> t); axes whose t_a equals the minimum step one cell
  * (ties step together, like hit.rint:102-104), the others are re-derived from the ray at that t
  * and clamped into the cell's own range.
  */
@@ -231,26 +287,30 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
 {
     const OTree *t = in->tree;
     const float *M = in->w2o;
-    float o[3], d[3], inv[3], nb[3];
+    float o[3], d[3], inv[3];
     for (int a = 0; a < 3; a++) {
         /* gl_ObjectRayOriginEXT / gl_ObjectRayDirectionEXT (hit.rint:140-141) */
         o[a] = ((M[4 * a] * ow[0] + M[4 * a + 1] * ow[1]) + M[4 * a + 2] * ow[2]) + M[4 * a + 3];
         d[a] = (M[4 * a] * dw[0] + M[4 * a + 1] * dw[1]) + M[4 * a + 2] * dw[2];
         if (fabsf(d[a]) < O_DIR_EPS) d[a] = copysignf(O_DIR_EPS, d[a]);        /* deviation (1) */
         inv[a] = 1.0f / d[a];
-        nb[a] = -(inv[a] * o[a]);
     }
     uint32_t root_level = t->n_levels - 1;
     int32_t Ei = (int32_t)1 << t->extent_log2[root_level];
     float E = (float)Ei;
     float lo[3], hi[3];
     for (int a = 0; a < 3; a++) {
-        float t0 = nb[a];
-        float t1 = fmaf(E, inv[a], nb[a]);
+        float t0 = (0.0f - o[a]) * inv[a];
+        float t1 = (E - o[a]) * inv[a];
         lo[a] = fminf(t0, t1); hi[a] = fmaxf(t0, t1);
     }
     float t_enter = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], tmin));
-    float t_exit = fminf(fminf(hi[0], hi[1]), fminf(hi[2], tmax));
+    /* The cell walk stops a hair AFTER tmax (2^-18 relative + 2^-20): plane times and leaf
+     * hit times (hit.rint's divisions) round differently, so a hit at t == tmax can sit in a cell the
+     * walk enters at tmax + 1 ulp.  Acceptance itself stays exact (tmin <= t <= tmax); the pad only
+     * makes the result independent of how far tmax was already shrunk by other instances. */
+    float tmax_pad = tmax + (fabsf(tmax) * 3.814697265625e-06f + 9.5367431640625e-07f);
+    float t_exit = fminf(fminf(hi[0], hi[1]), fminf(hi[2], tmax_pad));
     if (!(t_enter <= t_exit)) return 0;
     int32_t iv[3];
     for (int a = 0; a < 3; a++) {
@@ -289,10 +349,12 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
         float tx[3];
         for (int a = 0; a < 3; a++) {
             int32_t plane = d[a] > 0.0f ? cmin[a] + L : cmin[a];
-            tx[a] = fmaf((float)plane, inv[a], nb[a]);
+            tx[a] = ((float)plane - o[a]) * inv[a];
         }
         float t_next = fminf(fminf(tx[0], tx[1]), tx[2]);
-        if (!(t_next < t_exit)) return 0;
+        /* inclusive: a cell entered exactly at tmax may still hold a hit at t == tmax (accepted by
+         * reportIntersectionEXT); keeps the closest-hit result independent of instance order */
+        if (!(t_next <= t_exit)) return 0;
         for (int a = 0; a < 3; a++) {
             if (tx[a] <= t_next) {
                 iv[a] = d[a] > 0.0f ? cmin[a] + L : cmin[a] - 1;
@@ -311,27 +373,52 @@ typedef struct SceneHit {
     InstHit ih;
 } SceneHit;
 
+/* debug recorder (o_debug_pixel): every ray a pixel's paths trace, with the oracle's answer */
+static __thread ORay *g_rec_rays;
+static __thread OHitRec *g_rec_hits;
+static __thread uint32_t g_rec_n, g_rec_cap;
+
+static void record_ray(const OScene *s, const float o[3], const float d[3], float tmin, float tmax, int any,
+                       int hit, uint32_t inst, const InstHit *ih)
+{
+    if (!g_rec_rays || g_rec_n >= g_rec_cap) return;
+    ORay *r = &g_rec_rays[g_rec_n];
+    OHitRec *h = &g_rec_hits[g_rec_n++];
+    memcpy(r->o, o, 12); memcpy(r->d, d, 12); r->tmin = tmin; r->tmax = tmax;
+    h->voxel = any ? 0x80000000u : 0u;                        /* bit 31 = any-hit (shadow) ray */
+    if (hit) { h->t = ih->t; h->instance = inst; h->leaf = s->inst[inst].leaf_order[ih->leaf_ptr]; h->voxel |= ih->voxel; }
+    else { h->t = INFINITY; h->instance = O_MISS; h->leaf = O_MISS; h->voxel |= 0xFFu; }
+}
+
 /* Closest hit over all instances: lexicographic minimum of (t, instance index). */
 static void trace_closest(const OScene *s, const float o[3], const float d[3], float tmin, float tmax,
                           SceneHit *best, OStats *st)
 {
     best->hit = 0; best->instance = O_MISS;
     float cur = tmax;
+    float inv[3];
+    cull_inv(d, inv);
     for (uint32_t k = 0; k < s->n; k++) {
         InstHit ih;
+        if (s->cull && !box_may_hit(s->boxes + 6 * k, o, inv, tmin, cur)) continue;
         if (trace_instance(&s->inst[k], o, d, tmin, cur, &ih, st)) {
             if (!best->hit || ih.t < best->ih.t) { best->hit = 1; best->instance = k; best->ih = ih; cur = ih.t; }
         }
     }
+    record_ray(s, o, d, tmin, tmax, 0, best->hit, best->instance, &best->ih);
 }
 
 /* gl_RayFlagsTerminateOnFirstHitEXT (ambient_occlusion.rgen:37-38): any accepted hit */
 static int trace_any(const OScene *s, const float o[3], const float d[3], float tmin, float tmax, OStats *st)
 {
+    float inv[3];
+    cull_inv(d, inv);
     for (uint32_t k = 0; k < s->n; k++) {
         InstHit ih;
-        if (trace_instance(&s->inst[k], o, d, tmin, tmax, &ih, st)) return 1;
+        if (s->cull && !box_may_hit(s->boxes + 6 * k, o, inv, tmin, tmax)) continue;
+        if (trace_instance(&s->inst[k], o, d, tmin, tmax, &ih, st)) { record_ray(s, o, d, tmin, tmax, 1, 1, k, &ih); return 1; }
     }
+    record_ray(s, o, d, tmin, tmax, 1, 0, O_MISS, NULL);
     return 0;
 }
 
@@ -502,8 +589,13 @@ static void *render_worker(void *arg)
 {
     Job *j = (Job *)arg;
     const OTraceConfig *cfg = j->F->cfg;
-    for (uint32_t y = cfg->y0 + j->tid; y < cfg->y1; y += j->nthreads)
-        for (uint32_t x = 0; x < cfg->width; x++) shade_pixel(j->F, x, y, &j->st);
+    /* 32-pixel spans of the row range, dealt round-robin: even a single row keeps every thread busy */
+    const uint64_t total = (uint64_t)(cfg->y1 - cfg->y0) * cfg->width, span = 32;
+    for (uint64_t base = (uint64_t)j->tid * span; base < total; base += (uint64_t)j->nthreads * span) {
+        uint64_t end = base + span < total ? base + span : total;
+        for (uint64_t i = base; i < end; i++)
+            shade_pixel(j->F, (uint32_t)(i % cfg->width), cfg->y0 + (uint32_t)(i / cfg->width), &j->st);
+    }
     return NULL;
 }
 
@@ -559,6 +651,25 @@ void o_render(const OScene *s, const OCamera *cam, const OSky *sky, const OTrace
     for (uint32_t i = 0; i < n_threads; i++) { jobs[i].F = &F; jobs[i].tid = i; jobs[i].nthreads = n_threads; }
     run_jobs(jobs, n_threads, render_worker, stats);
     free(jobs);
+}
+
+/* Debug aid: shade ONE pixel (all samples) and record every ray its paths trace, with the oracle's
+ * answer (voxel bit 31 set = any-hit shadow ray).  Returns the number of rays recorded. */
+uint32_t o_debug_pixel(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
+                       uint32_t px, uint32_t py, ORay *rays, OHitRec *hits, uint32_t cap, float rgba[4])
+{
+    float *rad = (float *)calloc((size_t)cfg->width * cfg->height, 4 * sizeof(float));
+    Frame F = { s, cam, sky, cfg, rad, NULL, NULL, NULL, NULL, { 0, 0, 0 }, 0.0f };
+    normalize3(sky->direction, F.sun_dir);
+    F.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
+    OStats st;
+    memset(&st, 0, sizeof st);
+    g_rec_rays = rays; g_rec_hits = hits; g_rec_n = 0; g_rec_cap = cap;
+    shade_pixel(&F, px, py, &st);
+    g_rec_rays = NULL; g_rec_hits = NULL;
+    memcpy(rgba, rad + 4 * ((size_t)py * cfg->width + px), 4 * sizeof(float));
+    free(rad);
+    return g_rec_n;
 }
 
 void o_trace_rays(const OScene *s, const ORay *rays, uint64_t n, OHitRec *hits, OStats *stats, uint32_t n_threads)

@@ -72,6 +72,8 @@ typedef struct OHitRec { float t; uint32_t instance, leaf, voxel; } OHitRec;    
 OScene *o_scene_create(uint32_t n, const float *obj2world /* n*12 */, const OTree *const *trees,
                        const uint8_t *const *materials, const uint8_t *const *palettes /* 255*4 RGBA */);
 void    o_scene_destroy(OScene *s);
+/* 1 (default): skip instances whose padded world box the ray cannot touch; 0: test every instance */
+void    o_scene_set_cull(OScene *s, int enabled);
 
 /* Full path: fills radiance (float4 per pixel, row-major W*H) and, when non-NULL, the sample-0
  * primary hit record arrays.  Only rows [y0,y1) are touched. */
@@ -81,6 +83,10 @@ void o_render(const OScene *s, const OCamera *cam, const OSky *sky, const OTrace
 
 /* Explicit ray batch, closest hit (BASELINE config 5) */
 void o_trace_rays(const OScene *s, const ORay *rays, uint64_t n, OHitRec *hits, OStats *stats, uint32_t n_threads);
+
+/* debug aid: every ray of one pixel's paths + the oracle's answers (voxel bit 31 = any-hit ray) */
+uint32_t o_debug_pixel(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
+                       uint32_t px, uint32_t py, ORay *rays, OHitRec *hits, uint32_t cap, float rgba[4]);
 
 /* building blocks exposed for unit tests */
 int   o_leaf_dda(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t, uint32_t *voxel);

@@ -106,8 +106,10 @@ def lib() -> C.CDLL:
         "o_sky_radiance": (None, [C.POINTER(OSky), pf32, pf32]), "o_sun_radiance": (None, [C.POINTER(OSky), pf32, pf32]),
         "o_srgb_to_linear": (f32, [f32]),
         "o_scene_create": (vp, [u32, pf32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]), "o_scene_destroy": (None, [vp]),
+        "o_scene_set_cull": (None, [vp, i32]),
         "o_render": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
         "o_trace_rays": (None, [vp, vp, u64, vp, C.POINTER(OStats), u32]),
+        "o_debug_pixel": (u32, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), u32, u32, vp, vp, u32, pf32]),
         "o_leaf_dda": (i32, [pf32, pf32, u64, f32, pf32, pu32]),
         "o_camera_ray": (None, [C.POINTER(OCamera), u32, u32, u32, u32, f32, f32, pf32, pf32]),
         "o_pcg": (u32, [u32]), "o_cossin_2pi": (None, [f32, pf32, pf32]),
@@ -327,6 +329,9 @@ class Scene:
             lib().o_scene_destroy(self._h)
             self._h = None
 
+    def set_cull(self, enabled: bool):
+        lib().o_scene_set_cull(self._h, int(bool(enabled)))
+
     def render(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0, y0=0, y1=None,
                hits=True, threads=None):
         cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
@@ -347,6 +352,16 @@ class Scene:
                        C.byref(st), threads or os.cpu_count() or 1)
         res["stats"] = st.as_dict()
         return res
+
+    def debug_pixel(self, camera, sky, width, height, px, py, spp=1, max_bounces=0, seed=0, frame_index=0, cap=256):
+        """All rays of one pixel's paths and the oracle's answers (voxel bit 31 = any-hit shadow ray)."""
+        cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
+        sk = sky if isinstance(sky, OSky) else as_struct(OSky, sky)
+        cfg = OTraceConfig(width, height, spp, max_bounces, seed, frame_index, 0, height)
+        rays, hits = np.zeros(cap, RAY_DTYPE), np.zeros(cap, HIT_DTYPE)
+        rgba = (C.c_float * 4)()
+        n = lib().o_debug_pixel(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), px, py, rays.ctypes.data, hits.ctypes.data, cap, rgba)
+        return rays[:n], hits[:n], np.array(rgba, np.float32)
 
     def trace_rays(self, rays: np.ndarray, threads=None):
         rays = np.ascontiguousarray(rays)
