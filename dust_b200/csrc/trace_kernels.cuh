@@ -224,7 +224,7 @@ __device__ __forceinline__ bool trace_instance(const DInstance &in, f3 ow, f3 dw
     const float t0x = (0.0f - o.x) * ix_, t0y = (0.0f - o.y) * iy_, t0z = (0.0f - o.z) * iz_;
     const float t1x = (E - o.x) * ix_, t1y = (E - o.y) * iy_, t1z = (E - o.z) * iz_;
     float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-    // walk a hair past tmax (acceptance stays exact): see oracle_trace.c / DESIGN.md "Traversal semantics"
+    // walk a hair past tmax (acceptance stays exact): DESIGN.md "Traversal semantics"
     const float tmax_pad = tmax + (fabsf(tmax) * 3.814697265625e-06f + 9.5367431640625e-07f);
     float t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
     if (!(t_enter <= t_exit)) return false;
@@ -290,7 +290,7 @@ __device__ __forceinline__ bool trace_instance(const DInstance &in, f3 ow, f3 dw
         float ty = ((float)(py_ ? cy + L : cy) - o.y) * iy_;
         float tz = ((float)(pz_ ? cz + L : cz) - o.z) * iz_;
         float t_next = fminf(fminf(tx, ty), tz);
-        if (!(t_next <= t_exit)) return false;   // inclusive, see oracle_trace.c / DESIGN.md
+        if (!(t_next <= t_exit)) return false;   // inclusive, DESIGN.md "Traversal semantics"
         if (tx <= t_next) { ix = px_ ? cx + L : cx - 1; if (ix < 0 || ix >= Ei) return false; }
         else { int ip = (int)floorf(__fmaf_rn(d.x, t_next, o.x)); ix = min(max(ip, cx), cx + L - 1); }
         if (ty <= t_next) { iy = py_ ? cy + L : cy - 1; if (iy < 0 || iy >= Ei) return false; }

@@ -1,0 +1,101 @@
+#!/usr/bin/env python3
+"""Writes the golden fixtures tests/golden/*.npz.
+
+Provenance (be precise about what these pin): the reference (dust-engine/dust @ 7ea772b) holds NO
+golden vector, fixture or test for traversal, hit ids, t or radiance and cannot be
+built or run in this environment, so these fixtures are outputs of the repo's own CPU oracle
+(oracle/), frozen at the commit that added them.  They are "parity unpinned" with respect to the
+reference; what they pin is (a) the oracle against silent drift and (b) the CUDA path against a
+committed, machine-independent answer (the -m gpu tests compare against them too).  The only
+reference-pinned vectors are the crates/vdb doc-test KATs in tests/test_vdb_kat.py.
+
+Scenes are tiny and generated in code (no asset needed).  Run from the repo root:
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _scene_two_models():
+    """Two small models, three instances (one rotated, one mirrored), deterministic content."""
+    from dust_b200 import scenes
+    rng = np.random.default_rng(42)
+    X, Y, Z = np.meshgrid(np.arange(24), np.arange(20), np.arange(16), indexing="ij")
+    blob = ((X - 12) ** 2 / 100 + (Y - 10) ** 2 / 64 + (Z - 8) ** 2 / 36 < 1) & ~((X - 12) ** 2 + (Y - 10) ** 2 < 9)
+    a = np.stack([*np.nonzero(blob), rng.integers(0, 255, int(blob.sum()))], axis=1)
+    slab = (Z[:16, :16, :6] < 2) | ((X[:16, :16, :6] + Y[:16, :16, :6]) % 5 == 0)
+    b = np.stack([*np.nonzero(slab), rng.integers(0, 255, int(slab.sum()))], axis=1)
+    rots = scenes.all_rotation_bytes(False)
+    inst = [(0, (0, 0, 8), 4), (1, (6, 4, -3), rots[9]), (0, (-20, 14, 12), rots[30])]
+    return scenes.write_vox([((24, 20, 16), a), ((16, 16, 6), b)], inst, scenes.default_palette(1))
+
+
+def _built(oracle):
+    from conftest import BuiltScene
+    return BuiltScene(_scene_two_models(), oracle)
+
+
+def _camera(s, w, h):
+    lo, hi = s.bounds()
+    c = (lo + hi) / 2
+    return s.host.camera_look_at(c + np.array((0.9, 0.7, 1.1)) * (hi - lo).max(), c, width=w, height=h)
+
+
+def case_primary(oracle):
+    s = _built(oracle)
+    r = s.oscene.render(_camera(s, 48, 40), s.host.sunlight_bake(), 48, 40, spp=1, max_bounces=0, seed=9)
+    return {k: r[k] for k in ("radiance", "hit_instance", "hit_leaf", "hit_voxel", "hit_t")}
+
+
+def case_gi(oracle):
+    s = _built(oracle)
+    r = s.oscene.render(_camera(s, 32, 24), s.host.sunlight_bake(turbidity=2.5, direction=(0.3, 0.7, 0.648)), 32, 24,
+                        spp=3, max_bounces=2, seed=21, frame_index=5)
+    return {k: r[k] for k in ("radiance", "hit_instance", "hit_leaf", "hit_voxel", "hit_t")}
+
+
+def case_sky(oracle):
+    out = {}
+    for i, (turb, alb, d) in enumerate([(1.0, (0.2, 0.2, 0.2), (0.0, 0.80114365, -0.5984721)),
+                                        (3.7, (0.1, 0.5, 0.9), (0.5, 0.5, 0.70710678)),
+                                        (10.0, (1.0, 1.0, 1.0), (0.0, 1.0, 0.0))]):
+        sky = oracle.sunlight_bake(turb, alb, d)
+        out[f"bake{i}"] = np.frombuffer(bytes(sky), np.float32).copy()
+    return out
+
+
+CASES = {"two_models_primary": case_primary, "two_models_gi": case_gi, "sky_bake": case_sky}
+
+
+class _Npz(dict):
+    @property
+    def files(self):
+        return list(self.keys())
+
+
+def load_all():
+    out = {}
+    for name in CASES:
+        with np.load(os.path.join(HERE, name + ".npz")) as z:
+            out[name] = _Npz({k: z[k] for k in z.files})
+    return out
+
+
+def main():
+    from oracle import pyoracle
+    for name, fn in CASES.items():
+        data = fn(pyoracle)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, {k: v.shape for k, v in data.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -183,3 +183,24 @@ def test_empty_scene_and_errors(host, ctx):
         empty.trace(cam, sky, 0, 16)
     with pytest.raises(DustError):
         empty.trace(cam, sky, W, H, shard_index=2, shard_count=2)
+
+
+def test_cuda_matches_committed_golden_fixtures(oracle, host, ctx):
+    """The CUDA path against tests/golden/*.npz (frozen oracle outputs): ids and t bit-exact, radiance 1e-4."""
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_golden
+    from dust_b200.loader import load_vox
+    want = make_golden.load_all()
+    loaded = load_vox(ctx, make_golden._scene_two_models())
+    s = BuiltScene(make_golden._scene_two_models(), oracle)
+    g = loaded.scene.trace(make_golden._camera(s, 48, 40), host.sunlight_bake(), 48, 40, spp=1, max_bounces=0, seed=9, hits=True)
+    _assert_hits_equal(g, want["two_models_primary"])
+    _assert_radiance_close(g, want["two_models_primary"])
+    g = loaded.scene.trace(make_golden._camera(s, 32, 24), host.sunlight_bake(turbidity=2.5, direction=(0.3, 0.7, 0.648)), 32, 24,
+                           spp=3, max_bounces=2, seed=21, frame_index=5, hits=True)
+    _assert_hits_equal(g, want["two_models_gi"])
+    _assert_radiance_close(g, want["two_models_gi"])
