@@ -37,8 +37,10 @@ struct alignas(16) DInstance {
     const uint4 *leaves;
     const uint8_t *materials;
     const float4 *palette_lin;     // 256 x SRGBToLinear(rgb/255), w unused
+    int32_t bmin[3], bmax[3];      // occupied bounds [bmin, bmax) in object voxels (multiples of 4): the walk is clipped to it
+    uint32_t _pad[2];
 };
-static_assert(sizeof(DInstance) == 128, "DInstance layout");
+static_assert(sizeof(DInstance) == 160, "DInstance layout");
 
 // Binary BVH over instance world boxes (replaces the TLAS).  left < 0 => leaf, instance = ~left.
 struct alignas(16) DBvhNode {

@@ -1,7 +1,9 @@
 // C ABI of libdust_b200.so (include/dust_b200.h): context, one-time tree re-layout + upload,
 // instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
 // launches sm_100a kernels or fails.
-#include "trace_kernels.cuh"
+#include "trace_persistent.cuh"
+
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -22,6 +24,9 @@ struct DustCtx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     DCounters *d_counters = nullptr;
+    unsigned int *d_work = nullptr;   // work-item counter of the persistent kernel
+    int sms = 148;
+    int kernel_variant = 2;           // 2 = persistent (default), 1 = one-thread-per-pixel (DUST_KERNEL=v1)
     DustStats stats{};
 };
 
@@ -41,7 +46,7 @@ struct DustTree {
 struct DustScene {
     DInstance *d_inst = nullptr;
     DBvhNode *d_bvh = nullptr;
-    uint32_t n_inst = 0, n_bvh = 0, max_levels = 3;
+    uint32_t n_inst = 0, n_bvh = 0, max_levels = 3, min_levels = 3;
 };
 
 namespace {
@@ -268,10 +273,13 @@ int32_t dust_ctx_create(int32_t device, DustCtx **out)
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_work, sizeof(unsigned int)) != cudaSuccess) {
         delete ctx;
         return DUST_ERR_CUDA;
     }
+    cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char *k = std::getenv("DUST_KERNEL")) ctx->kernel_variant = (k[0] == 'v' && k[1] == '1') ? 1 : 2;
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return DUST_OK;
@@ -284,6 +292,7 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DUST_OK;
@@ -397,7 +406,7 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     *out = nullptr;
     std::vector<DInstance> inst(n);
     std::vector<Box> boxes(n);
-    uint32_t max_levels = 3;
+    uint32_t max_levels = 3, min_levels = 4;
     for (uint32_t k = 0; k < n; k++) {
         const DustTree *t = instances[k].tree;
         if (!t) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "instance without a tree");
@@ -407,7 +416,10 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
         d.n_levels = t->n_levels;
         d.n16 = t->n16; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin;
+        for (int a = 0; a < 3; a++) { d.bmin[a] = t->bmin[a]; d.bmax[a] = t->bmax[a]; }
+        d._pad[0] = d._pad[1] = 0;
         max_levels = std::max(max_levels, t->n_levels);
+        min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove
         // a hit the exact per-instance traversal would report (DESIGN.md "Instance BVH")
         Box b;
@@ -435,7 +447,7 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     }
     DustScene *s = new (std::nothrow) DustScene();
     if (!s) return DUST_ERR_OUT_OF_MEMORY;
-    s->n_inst = n; s->n_bvh = (uint32_t)nodes.size(); s->max_levels = max_levels;
+    s->n_inst = n; s->n_bvh = (uint32_t)nodes.size(); s->max_levels = max_levels; s->min_levels = std::min(min_levels, max_levels);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (n) {
         cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
@@ -543,9 +555,30 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     if (cfg.shard_count > 1 && tiles_per_shard * cfg.shard_count != p.tiles_x * p.tiles_y)
         CU_TRY(ctx, cudaMemsetAsync(p.radiance32 ? (void *)p.radiance32 : (void *)p.radiance16, 0, out_pixels * px_bytes, ctx->stream));
 
-    const uint32_t grid = tiles_per_shard * 8u;
-    if (stats) frame_kernel<true><<<grid, 128, 0, ctx->stream>>>(p);
-    else frame_kernel<false><<<grid, 128, 0, ctx->stream>>>(p);
+    const bool uniform_levels = scene->n_inst == 0 || scene->min_levels == scene->max_levels;
+    if (ctx->kernel_variant == 2 && uniform_levels) {
+        // persistent kernel: one resident wave of CTAs, work items (pixels) claimed with a global counter
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+        const uint32_t n_items = tiles_per_shard * 1024u;
+        const bool four = scene->n_inst && scene->max_levels == 4;
+        int per_sm = 0;
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_PT_THREADS, 0);
+            if (e != cudaSuccess) return e;
+            const uint32_t want = (n_items + DUST_PT_THREADS - 1) / DUST_PT_THREADS;
+            const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
+            kernel<<<grid, DUST_PT_THREADS, 0, ctx->stream>>>(p, ctx->d_work, n_items);
+            return cudaGetLastError();
+        };
+        cudaError_t e;
+        if (four) e = stats ? launch(frame_kernel_persistent<4, true>) : launch(frame_kernel_persistent<4, false>);
+        else e = stats ? launch(frame_kernel_persistent<3, true>) : launch(frame_kernel_persistent<3, false>);
+        CU_TRY(ctx, e);
+    } else {
+        const uint32_t grid = tiles_per_shard * 8u;
+        if (stats) frame_kernel<true><<<grid, 128, 0, ctx->stream>>>(p);
+        else frame_kernel<false><<<grid, 128, 0, ctx->stream>>>(p);
+    }
     CU_TRY(ctx, cudaGetLastError());
     count_launch(ctx);
 

@@ -143,7 +143,9 @@ __device__ __forceinline__ f3 sun_radiance(const DustSky &sky, float ar2, f3 dir
 
 // assets/shaders/primary/hit.rint:43-131 (scale = 1).  origin is leaf-local.  Returns true with
 // (t, voxelId) when the DDA reaches a set bit; the caller applies the [tmin, tmax] acceptance.
-__device__ __forceinline__ bool leaf_dda(f3 origin, f3 dir, uint64_t grid, float ray_tmin, float &t_out, uint32_t &voxel)
+// `inv` must be exactly (1/dir.x, 1/dir.y, 1/dir.z) (t_coef, hit.rint:87): callers that walk many leaves
+// with one ray compute it once.
+__device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint64_t grid, float ray_tmin, float &t_out, uint32_t &voxel)
 {
     // intersectAABB vs [0,4]^3, hit.rint:20-28 (true divisions)
     float ax = (0.0f - origin.x) / dir.x, bx = (4.0f - origin.x) / dir.x;
@@ -159,7 +161,7 @@ __device__ __forceinline__ bool leaf_dda(f3 origin, f3 dir, uint64_t grid, float
     int pz = (int)floorf(origin.z + dir.z * hitDistance);
     px = min(max(px, 0), 3); py = min(max(py, 0), 3); pz = min(max(pz, 0), 3);
     float sx = signf(dir.x), sy = signf(dir.y), sz = signf(dir.z);      // :79
-    float cx = 1.0f / dir.x, cy = 1.0f / dir.y, cz = 1.0f / dir.z;      // :87
+    float cx = inv.x, cy = inv.y, cz = inv.z;                           // :87
     float bx_ = cx * origin.x, by_ = cy * origin.y, bz_ = cz * origin.z;   // :88
     float mx = ((float)px + fmaxf(sx, 0.0f)) * cx - bx_;                // :90
     float my = ((float)py + fmaxf(sy, 0.0f)) * cy - by_;
@@ -180,6 +182,11 @@ __device__ __forceinline__ bool leaf_dda(f3 origin, f3 dir, uint64_t grid, float
     t_out = hitDistance / 1.0f;                                         // :115
     voxel = hit;
     return true;
+}
+
+__device__ __forceinline__ bool leaf_dda(f3 origin, f3 dir, uint64_t grid, float ray_tmin, float &t_out, uint32_t &voxel)
+{
+    return leaf_dda_inv(origin, dir, mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z), grid, ray_tmin, t_out, voxel);
 }
 
 // ----------------------------------------------------------------------------- instance traversal
@@ -218,85 +225,112 @@ __device__ __forceinline__ bool trace_instance(const DInstance &in, f3 ow, f3 dw
     if (fabsf(d.y) < DUST_DIR_EPS) d.y = copysignf(DUST_DIR_EPS, d.y);
     if (fabsf(d.z) < DUST_DIR_EPS) d.z = copysignf(DUST_DIR_EPS, d.z);
     const float ix_ = 1.0f / d.x, iy_ = 1.0f / d.y, iz_ = 1.0f / d.z;
-    constexpr int Ei = NL == 3 ? 256 : 4096;
-    constexpr float E = (float)Ei;
+    // clip against the occupied bounds [bmin, bmax) of the tree, not the whole [0, extent)^3
+    const int bx0 = in.bmin[0], by0 = in.bmin[1], bz0 = in.bmin[2], bx1 = in.bmax[0], by1 = in.bmax[1], bz1 = in.bmax[2];
     // plane times are (plane - o) * inv: difference first, plane*inv - o*inv would cancel (|o/d| >> t)
-    const float t0x = (0.0f - o.x) * ix_, t0y = (0.0f - o.y) * iy_, t0z = (0.0f - o.z) * iz_;
-    const float t1x = (E - o.x) * ix_, t1y = (E - o.y) * iy_, t1z = (E - o.z) * iz_;
+    const float t0x = ((float)bx0 - o.x) * ix_, t0y = ((float)by0 - o.y) * iy_, t0z = ((float)bz0 - o.z) * iz_;
+    const float t1x = ((float)bx1 - o.x) * ix_, t1y = ((float)by1 - o.y) * iy_, t1z = ((float)bz1 - o.z) * iz_;
     float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
     // walk a hair past tmax (acceptance stays exact): DESIGN.md "Traversal semantics"
     const float tmax_pad = tmax + (fabsf(tmax) * 3.814697265625e-06f + 9.5367431640625e-07f);
     float t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
-    if (!(t_enter <= t_exit)) return false;
+    if (!(t_enter <= t_exit) || bx1 <= bx0) return false;
     int ix = (int)floorf(__fmaf_rn(d.x, t_enter, o.x));
     int iy = (int)floorf(__fmaf_rn(d.y, t_enter, o.y));
     int iz = (int)floorf(__fmaf_rn(d.z, t_enter, o.z));
-    ix = min(max(ix, 0), Ei - 1); iy = min(max(iy, 0), Ei - 1); iz = min(max(iz, 0), Ei - 1);
+    ix = min(max(ix, bx0), bx1 - 1); iy = min(max(iy, by0), by1 - 1); iz = min(max(iz, bz0), bz1 - 1);
     const bool px_ = d.x > 0.0f, py_ = d.y > 0.0f, pz_ = d.z > 0.0f;
+    const f3 inv = mk3(ix_, iy_, iz_);
 
+    // leave the cell of edge L holding (ix,iy,iz); returns false when the walk ends
+    auto leave_cell = [&](int L) -> bool {
+        const int cx = ix & ~(L - 1), cy = iy & ~(L - 1), cz = iz & ~(L - 1);
+        const float tx = ((float)(px_ ? cx + L : cx) - o.x) * ix_;
+        const float ty = ((float)(py_ ? cy + L : cy) - o.y) * iy_;
+        const float tz = ((float)(pz_ ? cz + L : cz) - o.z) * iz_;
+        const float t_next = fminf(fminf(tx, ty), tz);
+        bool ok = (t_next <= t_exit);            // inclusive, DESIGN.md "Traversal semantics"
+        int nx, ny, nz;
+        if (tx <= t_next) { nx = px_ ? cx + L : cx - 1; ok &= (nx >= bx0 && nx < bx1); }
+        else { const int ip = (int)floorf(__fmaf_rn(d.x, t_next, o.x)); nx = min(max(ip, cx), cx + L - 1); }
+        if (ty <= t_next) { ny = py_ ? cy + L : cy - 1; ok &= (ny >= by0 && ny < by1); }
+        else { const int ip = (int)floorf(__fmaf_rn(d.y, t_next, o.y)); ny = min(max(ip, cy), cy + L - 1); }
+        if (tz <= t_next) { nz = pz_ ? cz + L : cz - 1; ok &= (nz >= bz0 && nz < bz1); }
+        else { const int ip = (int)floorf(__fmaf_rn(d.z, t_next, o.z)); nz = min(max(ip, cz), cz + L - 1); }
+        ix = nx; iy = ny; iz = nz;
+        return ok;
+    };
+
+    // "while-while": every lane first walks empty cells until it stands on an occupied leaf (cheap
+    // steps, lanes in lockstep), THEN the lanes that found one run the expensive leaf step together.
+    uint32_t mid_key = 0, mid_lo = 0, mid_hi = 0, mid_base = 0;     // the 4^3 node of the current 16-cell
     for (;;) {
-        int L;
-        bool at_leaf = false;
         uint32_t leaf_i = 0;
-        uint4 leaf = make_uint4(0, 0, 0, 0);
-        const DNode16 *n16 = in.n16;
-        bool alive = true;
-        if (NL == 4) {
-            uint32_t tidx = ((uint32_t)(ix >> 8) << 8) | ((uint32_t)(iy >> 8) << 4) | (uint32_t)(iz >> 8);
-            uint64_t m = __ldg(&n16->mask[tidx >> 6]);
-            if (STATS) st.mask_words++;
-            uint32_t b = tidx & 63u;
-            if (!((m >> b) & 1ull)) { L = 256; alive = false; }
-            else {
-                if (STATS) st.child_ptrs++;
-                n16 = in.n16 + (__ldg(&n16->child[tidx >> 6]) + __popcll(m & ((1ull << b) - 1ull)));
-            }
-        }
-        if (alive) {
-            uint32_t ridx = ((uint32_t)((ix >> 4) & 15) << 8) | ((uint32_t)((iy >> 4) & 15) << 4) | (uint32_t)((iz >> 4) & 15);
-            uint64_t m = __ldg(&n16->mask[ridx >> 6]);
-            if (STATS) st.mask_words++;
-            uint32_t b = ridx & 63u;
-            if (!((m >> b) & 1ull)) { L = 16; }
-            else {
-                if (STATS) { st.child_ptrs++; st.mask_words++; }
-                uint32_t mid_i = __ldg(&n16->child[ridx >> 6]) + __popcll(m & ((1ull << b) - 1ull));
-                uint4 mid = __ldg(&in.mids[mid_i]);
-                uint64_t mm = u64_of(mid.x, mid.y);
-                uint32_t midx = ((uint32_t)((ix >> 2) & 3) << 4) | ((uint32_t)((iy >> 2) & 3) << 2) | (uint32_t)((iz >> 2) & 3);
-                L = 4;
-                if ((mm >> midx) & 1ull) {
-                    if (STATS) { st.child_ptrs++; st.mask_words++; }
-                    leaf_i = mid.z + __popcll(mm & ((1ull << midx) - 1ull));
-                    leaf = __ldg(&in.leaves[leaf_i]);
-                    at_leaf = true;
+        bool walking = true;
+        for (;;) {
+            int L;
+            bool at_leaf = false;
+            const DNode16 *n16 = in.n16;
+            bool alive = true;
+            uint32_t key = 1;
+            if (NL == 4) {
+                const uint32_t tidx = ((uint32_t)(ix >> 8) << 8) | ((uint32_t)(iy >> 8) << 4) | (uint32_t)(iz >> 8);
+                const uint64_t m = __ldg(&n16->mask[tidx >> 6]);
+                if (STATS) st.mask_words++;
+                const uint32_t b = tidx & 63u;
+                if (!((m >> b) & 1ull)) { L = 256; alive = false; }
+                else {
+                    if (STATS) st.child_ptrs++;
+                    n16 = in.n16 + (__ldg(&n16->child[tidx >> 6]) + __popcll(m & ((1ull << b) - 1ull)));
+                    key += tidx << 12;
                 }
             }
-        }
-        const int cx = ix & ~(L - 1), cy = iy & ~(L - 1), cz = iz & ~(L - 1);
-        if (at_leaf) {
-            uint64_t grid = u64_of(leaf.x, leaf.y);
-            f3 lo = mk3(o.x - (float)cx, o.y - (float)cy, o.z - (float)cz);   // hit.rint:140
-            float th; uint32_t vox;
-            if (leaf_dda(lo, d, grid, tmin, th, vox) && tmin <= th && th <= tmax) {
-                out.t = th; out.leaf = leaf_i; out.voxel = vox;
-                out.lx = cx; out.ly = cy; out.lz = cz;
-                out.o = o; out.d = d;
-                out.material_ptr = leaf.z; out.mask = grid;
-                return true;
+            if (alive) {
+                const uint32_t ridx = ((uint32_t)((ix >> 4) & 15) << 8) | ((uint32_t)((iy >> 4) & 15) << 4) | (uint32_t)((iz >> 4) & 15);
+                key += ridx;
+                if (STATS) st.mask_words++;
+                bool have_mid = mid_key == key;
+                L = 16;
+                if (!have_mid) {
+                    const uint64_t m = __ldg(&n16->mask[ridx >> 6]);
+                    const uint32_t b = ridx & 63u;
+                    if ((m >> b) & 1ull) {
+                        const uint32_t mid_i = __ldg(&n16->child[ridx >> 6]) + __popcll(m & ((1ull << b) - 1ull));
+                        const uint4 mid = __ldg(&in.mids[mid_i]);
+                        mid_key = key; mid_lo = mid.x; mid_hi = mid.y; mid_base = mid.z;
+                        have_mid = true;
+                    }
+                }
+                if (have_mid) {
+                    if (STATS) { st.child_ptrs++; st.mask_words++; }
+                    const uint64_t mm = u64_of(mid_lo, mid_hi);
+                    const uint32_t midx = ((uint32_t)((ix >> 2) & 3) << 4) | ((uint32_t)((iy >> 2) & 3) << 2) | (uint32_t)((iz >> 2) & 3);
+                    L = 4;
+                    if ((mm >> midx) & 1ull) {
+                        if (STATS) { st.child_ptrs++; st.mask_words++; }
+                        leaf_i = mid_base + __popcll(mm & ((1ull << midx) - 1ull));
+                        at_leaf = true;
+                    }
+                }
             }
+            if (at_leaf) break;
+            if (!leave_cell(L)) { walking = false; break; }
         }
-        float tx = ((float)(px_ ? cx + L : cx) - o.x) * ix_;
-        float ty = ((float)(py_ ? cy + L : cy) - o.y) * iy_;
-        float tz = ((float)(pz_ ? cz + L : cz) - o.z) * iz_;
-        float t_next = fminf(fminf(tx, ty), tz);
-        if (!(t_next <= t_exit)) return false;   // inclusive, DESIGN.md "Traversal semantics"
-        if (tx <= t_next) { ix = px_ ? cx + L : cx - 1; if (ix < 0 || ix >= Ei) return false; }
-        else { int ip = (int)floorf(__fmaf_rn(d.x, t_next, o.x)); ix = min(max(ip, cx), cx + L - 1); }
-        if (ty <= t_next) { iy = py_ ? cy + L : cy - 1; if (iy < 0 || iy >= Ei) return false; }
-        else { int ip = (int)floorf(__fmaf_rn(d.y, t_next, o.y)); iy = min(max(ip, cy), cy + L - 1); }
-        if (tz <= t_next) { iz = pz_ ? cz + L : cz - 1; if (iz < 0 || iz >= Ei) return false; }
-        else { int ip = (int)floorf(__fmaf_rn(d.z, t_next, o.z)); iz = min(max(ip, cz), cz + L - 1); }
+        if (!walking) return false;
+        // leaf step: one 128-bit load (occupancy + material_ptr), then hit.rint's DDA
+        const uint4 leaf = __ldg(&in.leaves[leaf_i]);
+        const int cx = ix & ~3, cy = iy & ~3, cz = iz & ~3;
+        const uint64_t grid = u64_of(leaf.x, leaf.y);
+        const f3 lo = mk3(o.x - (float)cx, o.y - (float)cy, o.z - (float)cz);   // hit.rint:140
+        float th; uint32_t vox;
+        if (leaf_dda_inv(lo, d, inv, grid, tmin, th, vox) && tmin <= th && th <= tmax) {
+            out.t = th; out.leaf = leaf_i; out.voxel = vox;
+            out.lx = cx; out.ly = cy; out.lz = cz;
+            out.o = o; out.d = d;
+            out.material_ptr = leaf.z; out.mask = grid;
+            return true;
+        }
+        if (!leave_cell(4)) return false;
     }
 }
 
@@ -328,6 +362,7 @@ __device__ __forceinline__ float box_entry(const DBvhNode &n, f3 o, f3 inv, floa
 }
 
 #define DUST_BVH_STACK 24
+#define DUST_BVH_CAND 16
 
 // Closest hit = lexicographic minimum of (t, instance) over all instances.  The BVH only culls
 // (boxes are padded, see build_bvh), so the result equals the oracle's linear instance loop.
@@ -348,10 +383,46 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, f3 o, f3 d, fl
         DBvhNode root = sc.bvh[0];
         if (box_entry(root, o, inv, tmin, cur) == CUDART_INF_F) return;
     }
-    for (;;) {
-        const DBvhNode n = sc.bvh[node];
-        if (n.left < 0) {
-            uint32_t k = (uint32_t)~n.left;
+    // Two phases instead of walking an instance the moment the BVH reaches it: (1) cull — collect the
+    // instances whose padded box the ray touches, sorted by box entry; (2) walk them front to back.
+    // All lanes of a warp are then inside the (long) tree walk at the same time instead of taking
+    // turns, which is what kept the walk at ~3.5 active lanes (profiles/).  The result does not depend
+    // on the visiting order (lexicographic min of (t, instance)), only the pruning does.
+    float ct[DUST_BVH_CAND];
+    int ci[DUST_BVH_CAND];
+    bool more = true;
+    while (more) {
+        int nc = 0;
+        for (;;) {                                                   // ---- phase 1: cull
+            const DBvhNode n = sc.bvh[node];
+            bool descend = false;
+            if (n.left < 0) {
+                const float te = box_entry(n, o, inv, tmin, cur);
+                if (te != CUDART_INF_F) {
+                    int k = nc++;                                    // insertion sort by (entry t, instance)
+                    const int id = ~n.left;
+                    while (k > 0 && (ct[k - 1] > te || (ct[k - 1] == te && ci[k - 1] > id))) { ct[k] = ct[k - 1]; ci[k] = ci[k - 1]; --k; }
+                    ct[k] = te; ci[k] = id;
+                }
+            } else {
+                float tl = box_entry(sc.bvh[n.left], o, inv, tmin, cur);
+                float tr = box_entry(sc.bvh[n.right], o, inv, tmin, cur);
+                int near_ = n.left, far_ = n.right;
+                if (tr < tl) { near_ = n.right; far_ = n.left; const float s = tl; tl = tr; tr = s; }
+                if (tl != CUDART_INF_F) {
+                    if (tr != CUDART_INF_F && sp < DUST_BVH_STACK) stack[sp++] = far_;
+                    node = near_;
+                    descend = true;
+                }
+            }
+            if (descend) continue;
+            if (sp == 0) { more = false; break; }
+            node = stack[--sp];
+            if (nc == DUST_BVH_CAND) break;                          // list full: walk these, then resume the cull
+        }
+        for (int j = 0; j < nc; ++j) {                               // ---- phase 2: walk, front to back
+            if (ct[j] > cur) break;                                  // sorted: nothing further can beat the best hit
+            const uint32_t k = (uint32_t)ci[j];
             InstHit ih;
             if (trace_instance_any_levels<STATS>(sc.inst[k], o, d, tmin, cur, ih, st)) {
                 if (ANY) { best.hit = true; best.instance = k; return; }
@@ -359,24 +430,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, f3 o, f3 d, fl
                     best.hit = true; best.instance = k; best.ih = ih; cur = ih.t;
                 }
             }
-        } else {
-            float tl = box_entry(sc.bvh[n.left], o, inv, tmin, cur);
-            float tr = box_entry(sc.bvh[n.right], o, inv, tmin, cur);
-            int near_ = n.left, far_ = n.right;
-            if (tr < tl) { near_ = n.right; far_ = n.left; float s = tl; tl = tr; tr = s; }
-            if (tl != CUDART_INF_F) {
-                if (tr != CUDART_INF_F && sp < DUST_BVH_STACK) stack[sp++] = far_;
-                node = near_;
-                continue;
-            }
         }
-        // pop; boxes are re-tested against the shrunken `cur` when they are expanded
-        bool found = false;
-        while (sp > 0) {
-            int cand = stack[--sp];
-            if (box_entry(sc.bvh[cand], o, inv, tmin, cur) != CUDART_INF_F) { node = cand; found = true; break; }
-        }
-        if (!found) return;
     }
 }
 

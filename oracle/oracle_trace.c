@@ -18,6 +18,9 @@ typedef struct OInstance {
     const uint8_t *materials;
     const uint8_t *palette;        /* RGBA8 * 255 */
     const uint32_t *leaf_order;    /* pool pointer -> index in Tree::iter_leaf order (= gl_PrimitiveID) */
+    /* occupied bounds of the tree in object voxels: [bmin, bmax) spans every leaf (multiples of 4).
+     * The cell walk is clipped to this box instead of the full [0, extent)^3. */
+    int32_t bmin[3], bmax[3];
 } OInstance;
 
 struct OScene {
@@ -145,7 +148,7 @@ OScene *o_scene_create(uint32_t n, const float *obj2world, const OTree *const *t
     s->cull = 1;
     s->boxes = (float *)calloc(n ? n : 1, 6 * sizeof(float));
     for (uint32_t k = 0; k < n; k++) {
-        const OInstance *in = &s->inst[k];
+        OInstance *in = &s->inst[k];
         /* object-space bounds of the occupied leaves (a leaf spans 4 voxels) */
         uint64_t nl = o_tree_num_leaves(in->tree);
         uint32_t *pos = (uint32_t *)malloc(sizeof(uint32_t) * 3 * (nl ? nl : 1));
@@ -158,6 +161,7 @@ OScene *o_scene_create(uint32_t n, const float *obj2world, const OTree *const *t
                 if (l == 0 || v + 4.0 > omax[a]) omax[a] = v + 4.0;
             }
         free(pos);
+        for (int a = 0; a < 3; a++) { in->bmin[a] = (int32_t)omin[a]; in->bmax[a] = (int32_t)omax[a]; }   /* empty tree: [0,0) */
         double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY }, big = 0.0;
         for (int c = 0; c < 8; c++) {
             double p[3] = { (c & 1) ? omax[0] : omin[0], (c & 2) ? omax[1] : omin[1], (c & 4) ? omax[2] : omin[2] };
@@ -296,12 +300,13 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
         inv[a] = 1.0f / d[a];
     }
     uint32_t root_level = t->n_levels - 1;
-    int32_t Ei = (int32_t)1 << t->extent_log2[root_level];
-    float E = (float)Ei;
+    /* clip against the tree's occupied bounds [bmin, bmax) rather than the whole [0, extent)^3:
+     * everything outside holds no leaf, so the walk may start at, and stop on leaving, that box */
+    const int32_t *bmin = in->bmin, *bmax = in->bmax;
     float lo[3], hi[3];
     for (int a = 0; a < 3; a++) {
-        float t0 = (0.0f - o[a]) * inv[a];
-        float t1 = (E - o[a]) * inv[a];
+        float t0 = ((float)bmin[a] - o[a]) * inv[a];
+        float t1 = ((float)bmax[a] - o[a]) * inv[a];
         lo[a] = fminf(t0, t1); hi[a] = fmaxf(t0, t1);
     }
     float t_enter = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], tmin));
@@ -311,11 +316,11 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
      * makes the result independent of how far tmax was already shrunk by other instances. */
     float tmax_pad = tmax + (fabsf(tmax) * 3.814697265625e-06f + 9.5367431640625e-07f);
     float t_exit = fminf(fminf(hi[0], hi[1]), fminf(hi[2], tmax_pad));
-    if (!(t_enter <= t_exit)) return 0;
+    if (!(t_enter <= t_exit) || bmax[0] <= bmin[0]) return 0;
     int32_t iv[3];
     for (int a = 0; a < 3; a++) {
         int32_t ip = (int32_t)floorf(fmaf(d[a], t_enter, o[a]));
-        iv[a] = ip < 0 ? 0 : (ip > Ei - 1 ? Ei - 1 : ip);
+        iv[a] = ip < bmin[a] ? bmin[a] : (ip > bmax[a] - 1 ? bmax[a] - 1 : ip);
     }
     for (;;) {
         const uint8_t *node = t->root;
@@ -358,7 +363,7 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
         for (int a = 0; a < 3; a++) {
             if (tx[a] <= t_next) {
                 iv[a] = d[a] > 0.0f ? cmin[a] + L : cmin[a] - 1;
-                if (iv[a] < 0 || iv[a] >= Ei) return 0;
+                if (iv[a] < bmin[a] || iv[a] >= bmax[a]) return 0;
             } else {
                 int32_t ip = (int32_t)floorf(fmaf(d[a], t_next, o[a]));
                 iv[a] = ip < cmin[a] ? cmin[a] : (ip > cmin[a] + L - 1 ? cmin[a] + L - 1 : ip);
