@@ -12,7 +12,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libdust_b200.so")
+LIB_PATH = os.environ.get("DUST_B200_LIB") or os.path.join(LIB_DIR, "libdust_b200.so")   # override: tuning builds only
 
 DUST_OK = 0
 ERR_NAMES = {

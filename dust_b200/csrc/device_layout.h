@@ -9,11 +9,14 @@
 //     Tree::iter_leaf order (crates/vdb/src/node/internal.rs:306-332).  A child's slot is then
 //     base + popcount(mask & below(i)): no pointer table, and a leaf's slot IS the reference's
 //     gl_PrimitiveID (crates/vox/src/geometry.rs:68), so hit ids need no translation.
-//   * 16^3 node  : 64 mask words + 64 per-word child bases            = 768 B  (was 16 896 B)
-//   * 4^3  node  : {mask lo, mask hi, child base, -}                   = 16 B   (was 264 B)
-//   * leaf       : {occupancy lo, occupancy hi, material_ptr, -}       = 16 B   (one 128-bit load)
+//   * EVERY node word, at every level, is one uint4 = {mask lo, mask hi, base, 0}: one 128-bit
+//     load answers "is the bit set" and "where is the child".
+//       16^3 node : 64 words (word w = bits 64w..64w+63 of child_mask, base = slot of the first
+//                   child of that word)                                = 1024 B  (was 16 896 B)
+//       4^3 node  : 1 word, base = slot of its first leaf               = 16 B    (was 264 B)
+//       leaf      : 1 word, mask = occupancy, base = material_ptr       = 16 B    (was 24 B)
 //
-// Everything a ray touches above the leaves of a 256^3 model is < 100 KB and stays in L1/L2.
+// Everything a ray touches above the leaves of a 256^3 model is ~100 KB and stays in L1/L2.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -21,39 +24,44 @@
 namespace dust {
 
 struct alignas(16) DNode16 {
-    uint64_t mask[64];     // child_mask of an InternalNode<_, {4,4,4}>, bit = x<<8 | y<<4 | z
-    uint32_t child[64];    // child[w] = slot of the first child whose bit lives in mask[w]
+    uint4 word[64];        // child_mask of an InternalNode<_, {4,4,4}>, bit = x<<8 | y<<4 | z
 };
-static_assert(sizeof(DNode16) == 768, "DNode16 layout");
-
-// 4^3 internal node and leaf are both uint4:  .x/.y = 64-bit mask, .z = child base / material_ptr
+static_assert(sizeof(DNode16) == 1024, "DNode16 layout");
 
 struct alignas(16) DInstance {
-    float w2o[12];                 // world -> object, row-major 3x4
-    float o2w[9];                  // linear part of object -> world (normals)
-    uint32_t n_levels;             // 3: (4,2,2)   4: (4,4,2,2)
+    float w2o[12];                 // world -> object, row-major 3x4                       (3 x 128 bit)
+    // occupied bounds in LEAF units (voxel / 4), per axis: lo | (size << 16); the walk is clipped to it
+    uint32_t bounds[3];
+    uint32_t n_levels;             // 3: (4,2,2)   4: (4,4,2,2)                            (128 bit with bounds)
     const DNode16 *n16;            // [0] = root; for 4 levels [1..] = the 16^3 nodes below it
-    const uint4 *mids;             // 4^3 internal nodes
+    const uint4 *mids;             // 4^3 internal nodes                                   (128 bit with n16)
     const uint4 *leaves;
     const uint8_t *materials;
     const float4 *palette_lin;     // 256 x SRGBToLinear(rgb/255), w unused
-    int32_t bmin[3], bmax[3];      // occupied bounds [bmin, bmax) in object voxels (multiples of 4): the walk is clipped to it
-    uint32_t _pad[2];
+    uint64_t _pad0;
+    float o2w[9];                  // linear part of object -> world (normals)
+    uint32_t _pad1[3];
 };
 static_assert(sizeof(DInstance) == 160, "DInstance layout");
 
-// Binary BVH over instance world boxes (replaces the TLAS).  left < 0 => leaf, instance = ~left.
+// Binary BVH over instance world boxes (replaces the TLAS).  A node holds the padded boxes of BOTH
+// children, so one node fetch (4 x 128 bit) decides both.  child >= 0: inner node index;
+// child < 0: instance ~child.
 struct alignas(16) DBvhNode {
-    float lo[3]; int32_t left;
-    float hi[3]; int32_t right;
+    float lo0[3]; int32_t child0;
+    float hi0[3]; int32_t child1;
+    float lo1[3]; int32_t _p0;
+    float hi1[3]; int32_t _p1;
 };
+static_assert(sizeof(DBvhNode) == 64, "DBvhNode layout");
 
 struct DSceneView {
     const DInstance *inst;
-    const DBvhNode *bvh;
+    const DBvhNode *bvh;           // n_inst - 1 inner nodes (none for 0 / 1 instances)
+    float root_lo[3], root_hi[3];  // padded world box of the whole scene
+    int32_t root_ref;              // >= 0 inner node, < 0 instance ~root_ref
     uint32_t n_inst;
-    uint32_t n_bvh;
-    uint32_t max_levels;           // max n_levels over instances (kernel specialisation)
+    uint32_t id_bits;              // low bits of a candidate key that hold the instance index
 };
 
 struct DCounters {                 // DUST_TRACE_STATS

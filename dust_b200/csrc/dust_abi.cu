@@ -1,7 +1,7 @@
 // C ABI of libdust_b200.so (include/dust_b200.h): context, one-time tree re-layout + upload,
 // instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
 // launches sm_100a kernels or fails.
-#include "trace_persistent.cuh"
+#include "kernels.cuh"
 
 #include <cstdlib>
 
@@ -24,9 +24,7 @@ struct DustCtx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     DCounters *d_counters = nullptr;
-    unsigned int *d_work = nullptr;   // work-item counter of the persistent kernel
     int sms = 148;
-    int kernel_variant = 2;           // 2 = persistent (default), 1 = one-thread-per-pixel (DUST_KERNEL=v1)
     DustStats stats{};
 };
 
@@ -46,6 +44,7 @@ struct DustTree {
 struct DustScene {
     DInstance *d_inst = nullptr;
     DBvhNode *d_bvh = nullptr;
+    DSceneView view{};               // device pointers + root box, passed to the kernels by value
     uint32_t n_inst = 0, n_bvh = 0, max_levels = 3, min_levels = 3;
 };
 
@@ -124,8 +123,7 @@ void emit_n16_over_mids(const HostTree &ht, const uint8_t *node, int32_t ox, int
     const uint64_t *mask = n16_mask(node);
     const uint32_t *ptrs = n16_ptrs(node);
     for (uint32_t w = 0; w < 64; w++) {
-        out.mask[w] = mask[w];
-        out.child[w] = (uint32_t)r.mids.size();
+        out.word[w] = make_uint4((uint32_t)mask[w], (uint32_t)(mask[w] >> 32), (uint32_t)r.mids.size(), 0);
         for (uint64_t m = mask[w]; m; m &= m - 1) {
             const uint32_t idx = w * 64u + (uint32_t)__builtin_ctzll(m);
             const uint8_t *mid = ht.item(1, ptrs[idx]);
@@ -165,8 +163,7 @@ void relayout(const HostTree &ht, Relayout &r)
     r.n16.resize(1 + (size_t)n_children);
     uint32_t next = 1;
     for (uint32_t w = 0; w < 64; w++) {
-        r.n16[0].mask[w] = mask[w];
-        r.n16[0].child[w] = next;
+        r.n16[0].word[w] = make_uint4((uint32_t)mask[w], (uint32_t)(mask[w] >> 32), next, 0);
         for (uint64_t m = mask[w]; m; m &= m - 1) {
             const uint32_t idx = w * 64u + (uint32_t)__builtin_ctzll(m);
             const uint8_t *child = ht.item(2, ptrs[idx]);
@@ -208,26 +205,30 @@ void world2obj(const float m[12], float w[12])
 
 struct Box { float lo[3], hi[3]; };
 
-int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const std::vector<Box> &boxes, uint32_t begin, uint32_t end)
+Box box_union(const Box &a, const Box &b)
 {
-    const int me = (int)nodes.size();
-    nodes.emplace_back();
-    Box b = boxes[ids[begin]];
-    float clo[3], chi[3];
-    for (int a = 0; a < 3; a++) clo[a] = chi[a] = 0.5f * (b.lo[a] + b.hi[a]);
-    for (uint32_t k = begin + 1; k < end; k++) {
+    Box r;
+    for (int k = 0; k < 3; k++) { r.lo[k] = std::min(a.lo[k], b.lo[k]); r.hi[k] = std::max(a.hi[k], b.hi[k]); }
+    return r;
+}
+
+// Median split over box centres.  Returns the reference of the subtree (>= 0: index into `nodes`,
+// < 0: ~instance) and its box; inner nodes store the boxes of both children.
+int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const std::vector<Box> &boxes, uint32_t begin, uint32_t end,
+              Box &out_box, int depth, int &max_depth)
+{
+    max_depth = std::max(max_depth, depth);
+    if (end - begin == 1) {
+        out_box = boxes[ids[begin]];
+        return ~(int)ids[begin];
+    }
+    float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (uint32_t k = begin; k < end; k++) {
         const Box &x = boxes[ids[k]];
         for (int a = 0; a < 3; a++) {
-            b.lo[a] = std::min(b.lo[a], x.lo[a]); b.hi[a] = std::max(b.hi[a], x.hi[a]);
             const float c = 0.5f * (x.lo[a] + x.hi[a]);
             clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
         }
-    }
-    for (int a = 0; a < 3; a++) { nodes[me].lo[a] = b.lo[a]; nodes[me].hi[a] = b.hi[a]; }
-    if (end - begin == 1) {
-        nodes[me].left = ~(int32_t)ids[begin];
-        nodes[me].right = 0;
-        return me;
     }
     int axis = 0;
     if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
@@ -237,11 +238,40 @@ int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const st
         const float cx = boxes[x].lo[axis] + boxes[x].hi[axis], cy = boxes[y].lo[axis] + boxes[y].hi[axis];
         return cx < cy || (cx == cy && x < y);
     });
-    const int l = build_bvh(nodes, ids, boxes, begin, mid);
-    const int r = build_bvh(nodes, ids, boxes, mid, end);
-    nodes[me].left = l;
-    nodes[me].right = r;
+    const int me = (int)nodes.size();
+    nodes.emplace_back();
+    Box bl, br;
+    const int l = build_bvh(nodes, ids, boxes, begin, mid, bl, depth + 1, max_depth);
+    const int r = build_bvh(nodes, ids, boxes, mid, end, br, depth + 1, max_depth);
+    DBvhNode &n = nodes[me];
+    for (int a = 0; a < 3; a++) { n.lo0[a] = bl.lo[a]; n.hi0[a] = bl.hi[a]; n.lo1[a] = br.lo[a]; n.hi1[a] = br.hi[a]; }
+    n.child0 = l; n.child1 = r; n._p0 = 0; n._p1 = 0;
+    out_box = box_union(bl, br);
     return me;
+}
+
+// sun_radiance (assets/shaders/headers/sky.glsl:80-113) on the host, for the uniform-only NEE term
+void sun_radiance_host(const DustSky &sky, float ar2, const float dir[3], float out[3])
+{
+    out[0] = out[1] = out[2] = 0.0f;
+    const float cos_gamma = (dir[0] * sky.direction[0] + dir[1] * sky.direction[1]) + dir[2] * sky.direction[2];
+    if (cos_gamma < 0.0f || dir[1] < 0.0f) return;
+    const float singamma = 1.0f - (cos_gamma * cos_gamma);
+    const float sc2 = 1.0f - ar2 * singamma * singamma;
+    if (sc2 <= 0.0f) return;
+    const float sc = sqrtf(sc2);
+    const DustSkyChannel *ch = &sky.r;
+    float xyz[3];
+    for (int i = 0; i < 3; i++) {
+        float dk = ch[i].ld_coefficient0;
+        dk += ch[i].ld_coefficient1 * sc;
+        float cur = sc;
+        for (int k = 0; k < 4; k++) { cur *= sc; dk += ch[i].ld_coefficient2[k] * cur; }
+        xyz[i] = sky.sunlight_intensity[i] * dk;
+    }
+    // XYZ2ACEScg, headers/color.glsl:24-31 (GLSL mat3 columns)
+    static const float m[9] = { 1.6410228f, -0.66366285f, 0.011721907f, -0.32480323f, 1.6153315f, -0.0082844375f, -0.23642465f, 0.016756356f, 0.9883947f };
+    for (int r = 0; r < 3; r++) out[r] = (m[r] * xyz[0] + m[3 + r] * xyz[1]) + m[6 + r] * xyz[2];
 }
 
 void count_launch(DustCtx *ctx) { ctx->stats.kernel_launches++; }
@@ -273,13 +303,11 @@ int32_t dust_ctx_create(int32_t device, DustCtx **out)
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_work, sizeof(unsigned int)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess) {
         delete ctx;
         return DUST_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
-    if (const char *k = std::getenv("DUST_KERNEL")) ctx->kernel_variant = (k[0] == 'v' && k[1] == '1') ? 1 : 2;
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return DUST_OK;
@@ -292,7 +320,6 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DUST_OK;
@@ -416,8 +443,9 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
         d.n_levels = t->n_levels;
         d.n16 = t->n16; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin;
-        for (int a = 0; a < 3; a++) { d.bmin[a] = t->bmin[a]; d.bmax[a] = t->bmax[a]; }
-        d._pad[0] = d._pad[1] = 0;
+        // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
+        for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
+        d._pad0 = 0; d._pad1[0] = d._pad1[1] = d._pad1[2] = 0;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove
@@ -438,12 +466,16 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         for (int a = 0; a < 3; a++) { b.lo[a] -= pad; b.hi[a] += pad; }
         boxes[k] = b;
     }
+    if (n > (1u << 20)) return fail(ctx, DUST_ERR_UNSUPPORTED, "more than 2^20 instances");
     std::vector<DBvhNode> nodes;
+    Box root_box{};
+    int root_ref = -1, depth = 0;
     if (n) {
         std::vector<uint32_t> ids(n);
         for (uint32_t k = 0; k < n; k++) ids[k] = k;
-        nodes.reserve(2 * (size_t)n);
-        build_bvh(nodes, ids, boxes, 0, n);
+        nodes.reserve((size_t)n);
+        root_ref = build_bvh(nodes, ids, boxes, 0, n, root_box, 0, depth);
+        if (depth > DUST_MAX_BVH_DEPTH) return fail(ctx, DUST_ERR_UNSUPPORTED, "instance BVH deeper than the traversal stack");
     }
     DustScene *s = new (std::nothrow) DustScene();
     if (!s) return DUST_ERR_OUT_OF_MEMORY;
@@ -451,9 +483,9 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (n) {
         cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * nodes.size());
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * std::max<size_t>(nodes.size(), 1));
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && !nodes.empty()) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             if (s->d_inst) cudaFree(s->d_inst);
@@ -462,6 +494,11 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
             return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e));
         }
     }
+    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh;
+    for (int a = 0; a < 3; a++) { s->view.root_lo[a] = root_box.lo[a]; s->view.root_hi[a] = root_box.hi[a]; }
+    s->view.root_ref = root_ref; s->view.n_inst = n;
+    s->view.id_bits = 8;                                   // candidate key = entry t (high bits) | instance (low id_bits)
+    while ((1u << s->view.id_bits) < n) s->view.id_bits++;
     *out = s;
     return DUST_OK;
 }
@@ -509,17 +546,22 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
 
     FrameParams p;
     memset(&p, 0, sizeof p);
-    p.scene.inst = scene->d_inst; p.scene.bvh = scene->d_bvh; p.scene.n_inst = scene->n_inst; p.scene.n_bvh = scene->n_bvh;
-    p.scene.max_levels = scene->max_levels;
+    p.scene = scene->view;
     p.cam = *camera; p.sky = *sky; p.cfg = cfg;
     {
         // uniform-only terms hoisted out of the shaders (ambient_occlusion.rgen:45, nee.rmiss:18-19, sky.glsl:88-89)
         const float *d = sky->direction;
         const float l = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
         p.sun_dir[0] = d[0] / l; p.sun_dir[1] = d[1] / l; p.sun_dir[2] = d[2] / l;
-        p.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
-        const float s = sinf(sky->sunlight_intensity[3]);
-        p.sun_ar2 = 1.0f / (s * s);
+        const float sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
+        const float sn = sinf(sky->sunlight_intensity[3]);
+        p.sun_ar2 = 1.0f / (sn * sn);
+        // nee.rmiss:18-21: sun_radiance(normalize(sun_dir)) * (1 - cos(solar radius)) does not depend on the hit
+        const float sl = sqrtf((p.sun_dir[0] * p.sun_dir[0] + p.sun_dir[1] * p.sun_dir[1]) + p.sun_dir[2] * p.sun_dir[2]);
+        const float sdn[3] = { p.sun_dir[0] / sl, p.sun_dir[1] / sl, p.sun_dir[2] / sl };
+        float su[3];
+        sun_radiance_host(*sky, p.sun_ar2, sdn, su);
+        for (int a = 0; a < 3; a++) p.sun_nee[a] = su[a] * sun_cone;
     }
     p.tiles_x = (cfg.width + 31) / 32; p.tiles_y = (cfg.height + 31) / 32; p.n_local_tiles = tiles_per_shard;
 
@@ -555,30 +597,16 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     if (cfg.shard_count > 1 && tiles_per_shard * cfg.shard_count != p.tiles_x * p.tiles_y)
         CU_TRY(ctx, cudaMemsetAsync(p.radiance32 ? (void *)p.radiance32 : (void *)p.radiance16, 0, out_pixels * px_bytes, ctx->stream));
 
-    const bool uniform_levels = scene->n_inst == 0 || scene->min_levels == scene->max_levels;
-    if (ctx->kernel_variant == 2 && uniform_levels) {
-        // persistent kernel: one resident wave of CTAs, work items (pixels) claimed with a global counter
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
-        const uint32_t n_items = tiles_per_shard * 1024u;
-        const bool four = scene->n_inst && scene->max_levels == 4;
-        int per_sm = 0;
-        auto launch = [&](auto kernel) -> cudaError_t {
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_PT_THREADS, 0);
-            if (e != cudaSuccess) return e;
-            const uint32_t want = (n_items + DUST_PT_THREADS - 1) / DUST_PT_THREADS;
-            const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
-            kernel<<<grid, DUST_PT_THREADS, 0, ctx->stream>>>(p, ctx->d_work, n_items);
-            return cudaGetLastError();
-        };
-        cudaError_t e;
-        if (four) e = stats ? launch(frame_kernel_persistent<4, true>) : launch(frame_kernel_persistent<4, false>);
-        else e = stats ? launch(frame_kernel_persistent<3, true>) : launch(frame_kernel_persistent<3, false>);
-        CU_TRY(ctx, e);
-    } else {
-        const uint32_t grid = tiles_per_shard * 8u;
-        if (stats) frame_kernel<true><<<grid, 128, 0, ctx->stream>>>(p);
-        else frame_kernel<false><<<grid, 128, 0, ctx->stream>>>(p);
-    }
+    // 2^slot_log2 threads per pixel, one sample each per round (frame_kernel's thread mapping)
+    p.slot_log2 = cfg.spp >= 3 ? 2u : (cfg.spp == 2 ? 1u : 0u);
+    const uint64_t n_threads = ((uint64_t)tiles_per_shard * 1024u) << p.slot_log2;
+    if (n_threads / DUST_THREADS > 0x7FFFFFFFull) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "frame too large");
+    const uint32_t grid = (uint32_t)(n_threads / DUST_THREADS);
+    const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
+    auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
+    if (nl == 3) { if (stats) launch(frame_kernel<3, true>); else launch(frame_kernel<3, false>); }
+    else if (nl == 4) { if (stats) launch(frame_kernel<4, true>); else launch(frame_kernel<4, false>); }
+    else { if (stats) launch(frame_kernel<0, true>); else launch(frame_kernel<0, false>); }
     CU_TRY(ctx, cudaGetLastError());
     count_launch(ctx);
 
@@ -604,8 +632,7 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     RayParams p;
     memset(&p, 0, sizeof p);
-    p.scene.inst = scene->d_inst; p.scene.bvh = scene->d_bvh; p.scene.n_inst = scene->n_inst; p.scene.n_bvh = scene->n_bvh;
-    p.scene.max_levels = scene->max_levels;
+    p.scene = scene->view;
     p.n = n;
     p.counters = ctx->d_counters;
     uint8_t *scratch = nullptr;
@@ -624,10 +651,13 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     if (stats) CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DCounters), ctx->stream));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const uint64_t want = (n + 127) / 128;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 16u);
-    if (stats) rays_kernel<true><<<grid, 128, 0, ctx->stream>>>(p);
-    else rays_kernel<false><<<grid, 128, 0, ctx->stream>>>(p);
+    const uint64_t want = (n + DUST_THREADS - 1) / DUST_THREADS;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 64u);
+    const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
+    auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
+    if (nl == 3) { if (stats) launch(rays_kernel<3, true>); else launch(rays_kernel<3, false>); }
+    else if (nl == 4) { if (stats) launch(rays_kernel<4, true>); else launch(rays_kernel<4, false>); }
+    else { if (stats) launch(rays_kernel<0, true>); else launch(rays_kernel<0, false>); }
     CU_TRY(ctx, cudaGetLastError());
     count_launch(ctx);
     if (memory == DUST_MEM_HOST) {

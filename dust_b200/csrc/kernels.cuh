@@ -1,0 +1,288 @@
+// sm_100a device code, part 3: the kernels.
+//   frame_kernel    per-pixel primary ray + sun next-event estimation + diffuse GI bounces + radiance
+//                   (replaces the vkCmdTraceRaysKHR passes of StandardPipeline::render,
+//                   crates/render/src/pipeline/standard.rs:477-490, 564-577, 627-640)
+//   rays_kernel     explicit ray batch, closest hit (BASELINE.json config 5)
+//   resolve_kernel  un-permute gathered shard buffers to a row-major frame
+// Reference sources restated in frame_kernel:
+//   camera ray   assets/shaders/headers/camera.glsl:1-16, primary/primary.rgen:9-21
+//   shading      primary/hit.rchit:16-95, primary/miss.rmiss:7-17,
+//                final_gather/{ambient_occlusion.rgen, nee.rmiss, final_gather.rgen, .rmiss, .rchit}
+//   final value  assets/shaders/tone_map.comp:192-203
+#pragma once
+#include "trace_core.cuh"
+
+namespace dust {
+
+#ifndef DUST_MIN_BLOCKS
+#define DUST_MIN_BLOCKS 5
+#endif
+
+struct FrameParams {
+    DSceneView scene;
+    DustCamera cam;
+    DustSky sky;
+    float sun_dir[3];          // normalize(sky.direction.xyz)                          (ambient_occlusion.rgen:45)
+    float sun_ar2;             // 1 / sin^2(solar radius)                               (sky.glsl:88-89, uniform-only)
+    float sun_nee[3];          // sun_radiance(sun_dir) * (1 - cos(solar radius))        (nee.rmiss:18-21, uniform-only)
+    DustTraceConfig cfg;
+    uint32_t tiles_x, tiles_y, n_local_tiles;
+    uint32_t slot_log2;        // 2^slot_log2 threads share a pixel, each takes every 2^slot_log2-th sample
+    float4 *radiance32;
+    __half *radiance16;
+    uint32_t *hit_instance, *hit_leaf;
+    uint8_t *hit_voxel;
+    float *hit_t;
+    DCounters *counters;
+};
+
+enum : int { RAY_NONE = 0, RAY_PRIMARY = 1, RAY_SHADOW = 2, RAY_BOUNCE = 3 };
+
+// headers/camera.glsl:1-16
+__device__ __forceinline__ void camera_ray(const DustCamera &cam, uint32_t width, uint32_t height, uint32_t px, uint32_t py,
+                                           float jx, float jy, f3 &o, f3 &d)
+{
+    float ndc_x = ((float)px + jx) / (float)width;
+    float ndc_y = ((float)py + jy) / (float)height;
+    float cx = 2.0f * ndc_x - 1.0f;
+    float cy = 2.0f * ndc_y - 1.0f;
+    cy = cy * -1.0f;
+    cx = cx * ((float)width / (float)height);
+    cx = cx * cam.tan_half_fov;
+    cy = cy * cam.tan_half_fov;
+    d.x = (cam.camera_view_col0[0] * cx + cam.camera_view_col1[0] * cy) + cam.camera_view_col2[0] * -1.0f;
+    d.y = (cam.camera_view_col0[1] * cx + cam.camera_view_col1[1] * cy) + cam.camera_view_col2[1] * -1.0f;
+    d.z = (cam.camera_view_col0[2] * cx + cam.camera_view_col1[2] * cy) + cam.camera_view_col2[2] * -1.0f;
+    o = mk3(cam.position_x, cam.position_y, cam.position_z);
+}
+
+// hit.rchit:16-76 for hit `h` of world ray (ro, rd): world normal -> sn, offset hit point
+// (ambient_occlusion.rgen:23) -> ro, returns SRGBToLinear(albedo)
+template <bool STATS>
+__device__ __forceinline__ f3 surface_at(const DSceneView &sc, const Hit &h, f3 &ro, const f3 rd, f3 &sn, Counters &st)
+{
+    const DInstance &in = sc.inst[h.inst];
+    f3 o, d;
+    object_ray(in, ro, rd, o, d);
+    const uint32_t vox = h.voxel;
+    const int lx = (int)(h.pos & 1023u) << 2, ly = (int)((h.pos >> 10) & 1023u) << 2, lz = (int)(h.pos >> 20) << 2;
+    const float t = h.t;
+    const float vx = (t * d.x + o.x) - (((float)lx + (float)((vox >> 4) & 3u)) + 0.5f);
+    const float vy = (t * d.y + o.y) - (((float)ly + (float)((vox >> 2) & 3u)) + 0.5f);
+    const float vz = (t * d.z + o.z) - (((float)lz + (float)(vox & 3u)) + 0.5f);
+    const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
+    const float mx = fmaxf(ax, fmaxf(ay, az));                                     // normal.glsl:39-43
+    const f3 n_obj = mk3(signf(vx) * (ax >= mx ? 1.0f : 0.0f), signf(vy) * (ay >= mx ? 1.0f : 0.0f), signf(vz) * (az >= mx ? 1.0f : 0.0f));
+    const float *W = in.o2w;
+    sn = mk3((W[0] * n_obj.x + W[1] * n_obj.y) + W[2] * n_obj.z,
+             (W[3] * n_obj.x + W[4] * n_obj.y) + W[5] * n_obj.z,
+             (W[6] * n_obj.x + W[7] * n_obj.y) + W[8] * n_obj.z);
+    const uint4 leaf = __ldg(&in.leaves[h.leaf]);
+    const uint32_t off = rank64(leaf.x, leaf.y, vox);                              // hit.rchit:60-61
+    const uint8_t pi = __ldg(&in.materials[leaf.z + off]);                         // :71
+    const float4 c = __ldg(&in.palette_lin[pi]);                                   // :72-74 + SRGBToLinear
+    ro = mk3((t * rd.x + ro.x) + sn.x * 0.01f, (t * rd.y + ro.y) + sn.y * 0.01f, (t * rd.z + ro.z) + sn.z * 0.01f);
+    if (STATS) st.hits_shaded++;
+    return mk3(c.x, c.y, c.z);
+}
+
+__device__ __forceinline__ void flush_counters(DCounters *g, const Counters &st)
+{
+    // warp-aggregate, one atomic per counter per warp
+    uint32_t v[6] = { st.primary_rays, st.bounce_rays, st.shadow_rays, st.mask_words, st.child_ptrs, st.hits_shaded };
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(g);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        unsigned long long s = v[i];
+        for (int ofs = 16; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&dst[i], s);
+    }
+}
+
+__device__ __forceinline__ uint32_t even_bits(uint32_t v)      // bits 0,2,4,6,8 -> 0..4
+{
+    v &= 0x155u;
+    v = (v | (v >> 1)) & 0x133u;
+    v = (v | (v >> 2)) & 0x10Fu;
+    v = (v | (v >> 4)) & 0x01Fu;
+    return v;
+}
+
+// Thread mapping: 2^slot_log2 consecutive threads share a pixel (one sample each per round); pixels
+// follow a Morton curve inside 32x32 tiles, so a warp covers a compact patch (4x2 pixels x 4 samples
+// at 4 spp, 8x4 pixels at 1 spp).  32x32 tiles are the sharding unit: tile t -> shard t % shard_count.
+// Every thread runs ONE loop around ONE call of trace_scene: the path's next ray (primary, sun
+// shadow, bounce) is generated after the previous one is consumed.
+template <int NL, bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) frame_kernel(const __grid_constant__ FrameParams p)
+{
+    __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
+    uint32_t *sm = s_scratch + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const DustTraceConfig &cfg = p.cfg;
+    const uint32_t item = blockIdx.x * DUST_THREADS + threadIdx.x;
+    const uint32_t S = 1u << p.slot_log2, slot = item & (S - 1u), pix = item >> p.slot_log2;
+    const uint32_t lt = pix >> 10, q = pix & 1023u;
+    const uint32_t lx = even_bits(q), ly = even_bits(q >> 1);
+    const uint32_t t = lt * cfg.shard_count + cfg.shard_index;
+    const uint32_t tile_x = t % p.tiles_x, tile_y = t / p.tiles_x;
+    const uint32_t px = tile_x * 32u + lx, py = tile_y * 32u + ly;
+    const bool have_pixel = lt < p.n_local_tiles && tile_y < p.tiles_y && px < cfg.width && py < cfg.height;
+    const uint32_t pixel_index = py * cfg.width + px;
+    const uint32_t s0 = pcg(pixel_index ^ pcg(cfg.seed + 0x9E3779B9u * cfg.frame_index));
+    const f3 sun_dir = mk3(p.sun_dir[0], p.sun_dir[1], p.sun_dir[2]);
+    Counters st = { 0, 0, 0, 0, 0, 0 };
+    f3 acc = mk3(0.0f, 0.0f, 0.0f);
+
+#pragma unroll 1
+    for (uint32_t smp0 = 0; smp0 < cfg.spp; smp0 += S) {
+        const uint32_t smp = smp0 + slot;
+        int kind = (have_pixel && smp < cfg.spp) ? RAY_PRIMARY : RAY_NONE;
+        const uint32_t s1 = pcg(s0 + smp);
+        f3 ro, rd, sn = mk3(0.0f, 0.0f, 0.0f);
+        {
+            float jx = 0.5f, jy = 0.5f;
+            if (smp > 0) { jx = u01(pcg(s1 + 0u)); jy = u01(pcg(s1 + 1u)); }
+            camera_ray(p.cam, cfg.width, cfg.height, px, py, jx, jy, ro, rd);          // primary.rgen:9-21
+        }
+        float tmin = p.cam.near, tmax = p.cam.far;
+        f3 L = mk3(0.0f, 0.0f, 0.0f), T = mk3(1.0f, 1.0f, 1.0f);                      // linear sRGB primaries
+        uint32_t v = 0;
+
+#pragma unroll 1
+        while (__any_sync(full, kind != RAY_NONE)) {
+            Hit h;
+            trace_scene<NL, STATS>(p.scene, ro, rd, tmin, tmax, kind == RAY_SHADOW, kind != RAY_NONE, sm, h, st);
+
+            bool to_vertex = false, to_bounce = false, need_sky = false;
+            if (kind == RAY_SHADOW) {
+                if (!h.hit) {                                                          // nee.rmiss:11-22
+                    const float ndl = dot3(sn, sun_dir);
+                    const f3 ts = acescg2srgb(mk3(p.sun_nee[0] * ndl, p.sun_nee[1] * ndl, p.sun_nee[2] * ndl));
+                    L.x += T.x * ts.x; L.y += T.y * ts.y; L.z += T.z * ts.z;
+                }
+                to_bounce = true;
+            } else if (kind != RAY_NONE) {
+                if (STATS) { if (kind == RAY_PRIMARY) st.primary_rays++; else st.bounce_rays++; }
+                if (kind == RAY_PRIMARY && smp == 0 && (cfg.flags & DUST_TRACE_WRITE_HITS) && p.hit_instance) {
+                    p.hit_instance[pixel_index] = h.hit ? h.inst : 0xFFFFFFFFu; p.hit_leaf[pixel_index] = h.hit ? h.leaf : 0xFFFFFFFFu;
+                    p.hit_voxel[pixel_index] = h.hit ? (uint8_t)h.voxel : (uint8_t)0xFF; p.hit_t[pixel_index] = h.hit ? h.t : CUDART_INF_F;
+                }
+                if (h.hit) {
+                    const f3 a = surface_at<STATS>(p.scene, h, ro, rd, sn, st);
+                    if (kind == RAY_PRIMARY) { T = a; v = 0; }                         // tone_map.comp:195-203
+                    else { T.x = T.x * a.x; T.y = T.y * a.y; T.z = T.z * a.z; v += 1; }   // final_gather.rchit:76-80
+                    to_vertex = true;
+                } else need_sky = true;
+            }
+            if (need_sky) {
+                const f3 dn = normalize3(rd);
+                f3 sk, su;
+                sky_eval(p.sky, p.sun_ar2, dn.x, dn.y, dn.z, kind == RAY_PRIMARY, sk.x, sk.y, sk.z, su.x, su.y, su.z);
+                if (kind == RAY_PRIMARY) {                                             // miss.rmiss:8-14
+                    L = acescg2srgb(mk3((sk.x + su.x) / 3.14f, (sk.y + su.y) / 3.14f, (sk.z + su.z) / 3.14f));
+                } else {                                                               // final_gather.rmiss:13-17
+                    const f3 ts = acescg2srgb(sk);
+                    L.x += T.x * ts.x; L.y += T.y * ts.y; L.z += T.z * ts.z;
+                }
+                kind = RAY_NONE;
+            }
+            if (to_vertex) {
+                if (dot3(mk3(p.sky.direction[0], p.sky.direction[1], p.sky.direction[2]), sn) > 0.0f) {   // ambient_occlusion.rgen:33-50
+                    if (STATS) st.shadow_rays++;
+                    rd = sun_dir; tmin = 0.1f; tmax = 10000.0f;
+                    kind = RAY_SHADOW;
+                } else to_bounce = true;
+            }
+            if (to_bounce) {
+                if (v == cfg.max_bounces) kind = RAY_NONE;
+                else {
+                    const float u1 = u01(pcg(s1 + 2u + 2u * v)), u2 = u01(pcg(s1 + 3u + 2u * v));   // final_gather.rgen:32-34
+                    const float r = sqrtf(u1), cz = sqrtf(1.0f - u1);
+                    float c, sn_;
+                    cossin_2pi(u2, c, sn_);
+                    rd = normalize3(rotate_by_normal(sn, mk3(r * c, r * sn_, cz)));
+                    tmin = 0.1f; tmax = p.cam.far;
+                    kind = RAY_BOUNCE;
+                }
+            }
+        }
+
+        // pixel = mean over samples, accumulated in sample order (like the oracle's loop) by every thread of the pixel
+        const f3 Lc = srgb2acescg(L);
+        const unsigned base = (threadIdx.x & 31u) & ~(S - 1u);
+        for (uint32_t s = 0; s < S; s++) {
+            const float x = __shfl_sync(full, Lc.x, base + s), y = __shfl_sync(full, Lc.y, base + s), z = __shfl_sync(full, Lc.z, base + s);
+            if (smp0 + s < cfg.spp) { acc.x += x; acc.y += y; acc.z += z; }
+        }
+    }
+
+    if (have_pixel && slot == 0) {
+        const uint32_t out_index = cfg.shard_count > 1 ? lt * 1024u + ly * 32u + lx : pixel_index;
+        const float n = (float)cfg.spp;
+        const float4 outv = make_float4(acc.x / n, acc.y / n, acc.z / n, 1.0f);
+        if (p.radiance32) p.radiance32[out_index] = outv;
+        if (p.radiance16) {
+            __half2 a = __floats2half2_rn(outv.x, outv.y), b = __floats2half2_rn(outv.z, outv.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&a); pk.y = *reinterpret_cast<uint32_t *>(&b);
+            reinterpret_cast<uint2 *>(p.radiance16)[out_index] = pk;
+        }
+    }
+    if (STATS) flush_counters(p.counters, st);
+}
+
+// ------------------------------------------------------------------------------------- ray batches
+
+struct RayParams {
+    DSceneView scene;
+    const DustRay *rays;
+    DustHit *hits;
+    unsigned long long n;
+    DCounters *counters;
+};
+
+template <int NL, bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) rays_kernel(const __grid_constant__ RayParams p)
+{
+    __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
+    uint32_t *sm = s_scratch + threadIdx.x;
+    Counters st = { 0, 0, 0, 0, 0, 0 };
+    const unsigned long long stride = (unsigned long long)gridDim.x * DUST_THREADS;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * DUST_THREADS; base < p.n; base += stride) {
+        const unsigned long long i = base + threadIdx.x;
+        const bool live = i < p.n;
+        // 32-byte ray = two coalesced 128-bit loads
+        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        if (live) {
+            a = __ldg(reinterpret_cast<const float4 *>(p.rays) + 2 * i);
+            b = __ldg(reinterpret_cast<const float4 *>(p.rays) + 2 * i + 1);
+        }
+        Hit h;
+        trace_scene<NL, STATS>(p.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, false, live, sm, h, st);
+        if (live) {
+            if (STATS) st.primary_rays++;
+            uint4 o;
+            if (h.hit) { o.x = __float_as_uint(h.t); o.y = h.inst; o.z = h.leaf; o.w = h.voxel; }
+            else { o.x = __float_as_uint(CUDART_INF_F); o.y = o.z = o.w = 0xFFFFFFFFu; }
+            reinterpret_cast<uint4 *>(p.hits)[i] = o;
+        }
+    }
+    if (STATS) flush_counters(p.counters, st);
+}
+
+// un-permute gathered shard buffers to a row-major frame (runs after the all-gather)
+__global__ void __launch_bounds__(256) resolve_kernel(const float4 *__restrict__ gathered, float4 *__restrict__ out,
+                                                      uint32_t width, uint32_t height, uint32_t shard_count,
+                                                      uint32_t tiles_x, uint32_t tiles_per_shard)
+{
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= width || y >= height) return;
+    const uint32_t t = (y >> 5) * tiles_x + (x >> 5);
+    const uint32_t shard = t % shard_count, lt = t / shard_count;
+    const size_t src = ((size_t)shard * tiles_per_shard + lt) * 1024u + (y & 31u) * 32u + (x & 31u);
+    out[(size_t)y * width + x] = __ldg(&gathered[src]);
+}
+
+}  // namespace dust
