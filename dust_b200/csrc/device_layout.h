@@ -66,6 +66,7 @@ struct DSceneView {
 
 struct DCounters {                 // DUST_TRACE_STATS
     unsigned long long primary_rays, bounce_rays, shadow_rays, mask_words, child_ptrs, hits_shaded;
+    unsigned long long dbg[16];    // scheduling diagnostics (trace_core.cuh Counters::dbg)
 };
 
 }  // namespace dust

@@ -283,6 +283,11 @@ int32_t fetch_counters(DustCtx *ctx)
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.primary_rays = h.primary_rays; ctx->stats.bounce_rays = h.bounce_rays; ctx->stats.shadow_rays = h.shadow_rays;
     ctx->stats.mask_words = h.mask_words; ctx->stats.child_ptrs = h.child_ptrs; ctx->stats.hits_shaded = h.hits_shaded;
+    if (std::getenv("DUST_DEBUG_STATS")) {
+        fprintf(stderr, "[dust dbg] rays p/b/s %llu %llu %llu |", h.primary_rays, h.bounce_rays, h.shadow_rays);
+        for (int i = 0; i < 16; i++) fprintf(stderr, " %llu", h.dbg[i]);
+        fprintf(stderr, "\n");
+    }
     return DUST_OK;
 }
 

@@ -89,10 +89,12 @@ __device__ __forceinline__ f3 surface_at(const DSceneView &sc, const Hit &h, f3 
 __device__ __forceinline__ void flush_counters(DCounters *g, const Counters &st)
 {
     // warp-aggregate, one atomic per counter per warp
-    uint32_t v[6] = { st.primary_rays, st.bounce_rays, st.shadow_rays, st.mask_words, st.child_ptrs, st.hits_shaded };
+    uint32_t v[22] = { st.primary_rays, st.bounce_rays, st.shadow_rays, st.mask_words, st.child_ptrs, st.hits_shaded };
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[6 + i] = st.dbg[i];
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(g);
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < 22; i++) {
         unsigned long long s = v[i];
         for (int ofs = 16; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
         if ((threadIdx.x & 31) == 0 && s) atomicAdd(&dst[i], s);
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) frame_kernel(co
     const uint32_t pixel_index = py * cfg.width + px;
     const uint32_t s0 = pcg(pixel_index ^ pcg(cfg.seed + 0x9E3779B9u * cfg.frame_index));
     const f3 sun_dir = mk3(p.sun_dir[0], p.sun_dir[1], p.sun_dir[2]);
-    Counters st = { 0, 0, 0, 0, 0, 0 };
+    Counters st = {};
     f3 acc = mk3(0.0f, 0.0f, 0.0f);
 
 #pragma unroll 1
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) rays_kernel(con
 {
     __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
     uint32_t *sm = s_scratch + threadIdx.x;
-    Counters st = { 0, 0, 0, 0, 0, 0 };
+    Counters st = {};
     const unsigned long long stride = (unsigned long long)gridDim.x * DUST_THREADS;
     for (unsigned long long base = (unsigned long long)blockIdx.x * DUST_THREADS; base < p.n; base += stride) {
         const unsigned long long i = base + threadIdx.x;

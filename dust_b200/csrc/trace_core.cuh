@@ -22,6 +22,11 @@ namespace dust {
 
 struct Counters {
     uint32_t primary_rays, bounce_rays, shadow_rays, mask_words, child_ptrs, hits_shaded;
+    // scheduling diagnostics of the STATS instantiation (DUST_DEBUG_STATS=1 prints them; not part of the ABI):
+    //  0..2 trips that ran WALK / LEAF / NEXT   3..5 lanes served by them   6 lanes idle (ray finished) summed over trips
+    //  7 cells left with edge 1   8 edge 4   9 edge 64 (leaf units)   10 leaf steps   11 leaf DDA iterations
+    //  12 instances entered   13 BVH nodes expanded   14 candidates   15 trace_scene calls (per warp)
+    uint32_t dbg[16];
 };
 
 #define DUST_DIR_EPS 9.094947017729282e-13f   // 2^-40
@@ -84,6 +89,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     best.hit = false; best.inst = 0xFFFFFFFFu; best.t = tmax;
     float cur = tmax;                                                 // current tmax: shrinks to the best hit
     const uint32_t id_mask = (1u << sc.id_bits) - 1u;
+    if (STATS && (threadIdx.x & 31u) == 0) st.dbg[15]++;
 
     // ---- ray set-up for the cull: a zero component gets a huge FINITE inverse so (lo - o) * inv is never 0 * inf
     const f3 winv = mk3(fabsf(rd.x) < 1e-30f ? copysignf(1e30f, rd.x) : 1.0f / rd.x,
@@ -121,6 +127,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
         while (pend >= 0 && nc + 3 <= sp) {
             const float4 *n = reinterpret_cast<const float4 *>(sc.bvh + pend);
             const float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), e = __ldg(n + 3);
+            if (STATS) st.dbg[13]++;
             float t0 = box_entry(a.x, a.y, a.z, b.x, b.y, b.z, ro, winv, tmin, cur);
             float t1 = box_entry(c.x, c.y, c.z, e.x, e.y, e.z, ro, winv, tmin, cur);
             int c0 = __float_as_int(a.w), c1 = __float_as_int(b.w);
@@ -136,6 +143,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
                 } else {                                              // instance: insertion sort by key
                     const uint32_t key = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~ch;
                     int k = nc++;
+                    if (STATS) st.dbg[14]++;
                     while (k > 0) {
                         const uint32_t prev = sm[(k - 1) * DUST_THREADS];
                         if (prev <= key) break;
@@ -161,10 +169,16 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
             int op = M_WALK, cnt = n_walk;
             if (n_next > cnt) { op = M_NEXT; cnt = n_next; }
             if (n_leaf > cnt) { op = M_LEAF; }
+            if (STATS && (threadIdx.x & 31u) == 0) {
+                st.dbg[op == M_WALK ? 0 : (op == M_LEAF ? 1 : 2)]++;
+                st.dbg[op == M_WALK ? 3 : (op == M_LEAF ? 4 : 5)] += op == M_WALK ? n_walk : (op == M_LEAF ? n_leaf : n_next);
+                st.dbg[6] += 32 - n_walk - n_leaf - n_next;
+            }
 
             if (op == M_WALK) {
                 if (mode == M_WALK) {
                     if (L4) {
+                        if (STATS) st.dbg[L4 == 1 ? 7 : (L4 == 4 ? 8 : 9)]++;
                         // leave the cell of edge L4 that contains (jx,jy,jz): oracle trace_instance, "t_next"
                         const int cx = jx & ~(L4 - 1), cy = jy & ~(L4 - 1), cz = jz & ~(L4 - 1);
                         const bool px_ = d.x > 0.0f, py_ = d.y > 0.0f, pz_ = d.z > 0.0f;
@@ -239,9 +253,10 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
                 if (mode == M_LEAF) {
                     // leaf step: one 128-bit load (occupancy + material_ptr), then hit.rint's DDA
                     const uint4 leaf = __ldg(&leaves[leaf_i]);
+                    if (STATS) st.dbg[10]++;
                     const f3 lo = mk3(o.x - (float)(jx << 2), o.y - (float)(jy << 2), o.z - (float)(jz << 2));   // hit.rint:140
                     float th; uint32_t vox;
-                    if (leaf_dda_inv(lo, d, inv, leaf.x, leaf.y, tmin, th, vox) && tmin <= th && th <= cur) {   // reportIntersectionEXT
+                    if (leaf_dda_inv<STATS>(lo, d, inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]) && tmin <= th && th <= cur) {   // reportIntersectionEXT
                         if (any) { best.hit = true; best.inst = inst; mode = M_DONE; pend = -1; sp = DUST_SCRATCH_WORDS; }
                         else {
                             if (!best.hit || th < cur || inst < best.inst) {          // (t, instance) lexicographic
@@ -262,6 +277,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
                             // enter instance: world -> object ray, reciprocals, clip against the occupied bounds
                             mode = M_NEXT;
                             inst = key & id_mask;
+                            if (STATS) st.dbg[12]++;
                             const DInstance &in = sc.inst[inst];
                             object_ray(in, ro, rd, o, d);
                             inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);

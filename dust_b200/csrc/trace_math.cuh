@@ -163,8 +163,9 @@ __device__ __noinline__ void sky_eval(const DustSky &sky, float ar2, float dx, f
 // leaves with one ray compute it once.  dir has no zero component (deviation (1)), so step = sign(dir)
 // is +-1 and is carried as a predicate; the 0/1 `comp` factors of hit.rint:102-110 are carried as
 // predicates too: x + d * 1.0f == x + d and x + d * 0.0f == x + 0.0f for finite d, bit for bit.
+template <bool COUNT>
 __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t grid_lo, uint32_t grid_hi, float ray_tmin,
-                                             float &t_out, uint32_t &voxel)
+                                             float &t_out, uint32_t &voxel, uint32_t &iterations)
 {
     // intersectAABB vs [0,4]^3, hit.rint:20-28 (true divisions)
     float ax = (0.0f - origin.x) / dir.x, bx = (4.0f - origin.x) / dir.x;
@@ -191,6 +192,7 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
     int hit = (px << 4) | (py << 2) | pz;                               // :99
 #pragma unroll 1
     while (!bit64(grid_lo, grid_hi, (uint32_t)hit)) {                   // :101
+        if (COUNT) iterations++;
         const bool kx = (mz >= mx) && (my >= mx);                       // :102
         const bool ky = (mx >= my) && (mz >= my);
         const bool kz = (my >= mz) && (mx >= mz);
