@@ -21,6 +21,9 @@ ERR_NAMES = {
 }
 DUST_TRACE_WRITE_HITS = 1
 DUST_TRACE_STATS = 2
+DUST_TRACE_PIPELINE_MEGAKERNEL = 4
+DUST_TRACE_PIPELINE_WAVEFRONT = 8
+PIPELINE_FLAGS = {None: 0, "auto": 0, "megakernel": 4, "wavefront": 8}
 DUST_MEM_HOST, DUST_MEM_DEVICE = 0, 1
 DUST_FMT_RGBA32F, DUST_FMT_RGBA16F = 0, 1
 

@@ -1,7 +1,8 @@
 // C ABI of libdust_b200.so (include/dust_b200.h): context, one-time tree re-layout + upload,
 // instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
 // launches sm_100a kernels or fails.
-#include "kernels.cuh"
+#include "sched.cuh"
+#include "wavefront.cuh"
 
 #include <cstdlib>
 
@@ -24,7 +25,13 @@ struct DustCtx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     DCounters *d_counters = nullptr;
+    unsigned long long *d_work = nullptr;   // work-item counter of the persistent kernels
+    // wavefront pipeline: path state + ray queues (grown on demand), queue / bin counters (fixed size)
+    void *wf_scratch = nullptr;
+    size_t wf_scratch_bytes = 0;
+    uint32_t *d_wf_counters = nullptr;
     int sms = 148;
+    int kernel_variant = 2;           // 2 = one thread per sample / ray (default); 3 = persistent fully operation-scheduled lanes (DUST_KERNEL=v3, A/B only)
     DustStats stats{};
 };
 
@@ -291,6 +298,113 @@ int32_t fetch_counters(DustCtx *ctx)
     return DUST_OK;
 }
 
+// ---- wavefront pipeline (wavefront.cuh) ---------------------------------------------------------
+
+constexpr uint32_t kWfMaxDepths = 65;                                  // max_bounces <= 64
+// per depth: 4 queue counters, 2 x WF_BINS bin totals / cursors, 2 overflow counters, 2 x 64-bit work counters
+constexpr size_t kWfCounterWords = (size_t)kWfMaxDepths * (4 + 2 * WF_BINS + 2 + 4);
+
+int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_shard, int nl, bool stats)
+{
+    const DustTraceConfig &cfg = fp.cfg;
+    if (cfg.max_bounces + 1 > kWfMaxDepths) return fail(ctx, DUST_ERR_UNSUPPORTED, "wavefront pipeline: more than 64 bounces");
+    const uint32_t n_slots = tiles_per_shard * 1024u;
+    uint64_t max_paths = 16u << 20;
+    if (const char *e = std::getenv("DUST_WF_MAX_PATHS")) max_paths = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));   // tests: force several batches
+    const uint32_t batch_spp = (uint32_t)std::min<uint64_t>(cfg.spp, std::max<uint64_t>(1, max_paths / n_slots));
+    const uint64_t n_paths = (uint64_t)n_slots * batch_spp;
+    if (n_paths >= (1ull << 31)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "frame too large for one wavefront batch");
+
+    // carve the scratch: [ps0 ps1 ps2 | qc qs qg (a, b, path) | hits | acc | vis | bin]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_ps0 = take(n_paths * 16), o_ps1 = take(n_paths * 16), o_ps2 = take(n_paths * 16);
+    size_t o_q[3][3];
+    for (int q = 0; q < 3; q++) { o_q[q][0] = take(n_paths * 16); o_q[q][1] = take(n_paths * 16); o_q[q][2] = take(n_paths * 4); }
+    const size_t o_hits = take(n_paths * 16), o_acc = take((size_t)n_slots * 16), o_vis = take(n_paths), o_bin = take(n_paths);
+    const size_t o_cand = take(n_paths * 32), o_ovf = take(n_paths * 4);
+    if (off > ctx->wf_scratch_bytes) {
+        if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
+        CU_TRY(ctx, cudaMalloc(&ctx->wf_scratch, off));
+        ctx->wf_scratch_bytes = off;
+    }
+    if (!ctx->d_wf_counters) CU_TRY(ctx, cudaMalloc(&ctx->d_wf_counters, kWfCounterWords * sizeof(uint32_t)));
+    uint8_t *base = static_cast<uint8_t *>(ctx->wf_scratch);
+
+    WfParams p;
+    memset(&p, 0, sizeof p);
+    p.f = fp;
+    p.n_slots = n_slots;
+    p.ps0 = reinterpret_cast<float4 *>(base + o_ps0); p.ps1 = reinterpret_cast<float4 *>(base + o_ps1); p.ps2 = reinterpret_cast<float4 *>(base + o_ps2);
+    WfQueue *qs[3] = { &p.qc, &p.qs, &p.qg };
+    for (int q = 0; q < 3; q++) {
+        qs[q]->a = reinterpret_cast<float4 *>(base + o_q[q][0]); qs[q]->b = reinterpret_cast<float4 *>(base + o_q[q][1]);
+        qs[q]->path = reinterpret_cast<uint32_t *>(base + o_q[q][2]);
+    }
+    p.hits = reinterpret_cast<uint4 *>(base + o_hits); p.acc = reinterpret_cast<float4 *>(base + o_acc);
+    p.vis = base + o_vis; p.bin = base + o_bin;
+    p.cand = reinterpret_cast<uint4 *>(base + o_cand); p.overflow = reinterpret_cast<uint32_t *>(base + o_ovf);
+    p.counts = ctx->d_wf_counters; p.bins = ctx->d_wf_counters + 4 * kWfMaxDepths;
+    uint32_t *ovf_counts = p.bins + 2 * WF_BINS * kWfMaxDepths;                                  // [2 * depth + (shadow ? 1 : 0)]
+    unsigned long long *work = reinterpret_cast<unsigned long long *>(ovf_counts + 2 * kWfMaxDepths);   // 8-byte aligned: all counts above are even
+    // queues of incoherent rays (bounce rays and the shadow rays behind them) are pre-culled and traced by persistent lanes
+    uint32_t pt_depth = 1;
+    if (const char *e = std::getenv("DUST_WF_PT_DEPTH")) pt_depth = (uint32_t)atoi(e);           // tuning / A-B only
+    int pt_blocks = 0;
+
+    auto trace = [&](const WfQueue &q, const uint32_t *count, const uint32_t *list, uint32_t grid) {
+        if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
+        else if (nl == 4) { if (stats) wf_trace<4, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<4, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
+        else { if (stats) wf_trace<0, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<0, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
+        count_launch(ctx);
+    };
+    cudaError_t pt_err = cudaSuccess;
+    auto trace_pt = [&](const WfQueue &q, const uint32_t *count, uint32_t slot, uint32_t grid) {
+        if (stats) wf_cull<true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, ovf_counts + slot);
+        else wf_cull<false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, ovf_counts + slot);
+        count_launch(ctx);
+        auto launch = [&](auto kernel) {
+            if (!pt_blocks) pt_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pt_blocks, kernel, DUST_THREADS, 0);
+            const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(pt_blocks, 1)));
+            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, work + slot);
+        };
+        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
+        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
+        else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
+        count_launch(ctx);
+        trace(q, ovf_counts + slot, p.overflow, grid);                 // rays whose candidate list overflowed (normally none: CTAs exit at once)
+    };
+
+    for (uint32_t first = 0; first < cfg.spp; first += batch_spp) {
+        p.batch_first = first;
+        p.batch_spp = std::min(batch_spp, cfg.spp - first);
+        p.n_paths = n_slots * p.batch_spp;
+        p.last_batch = first + p.batch_spp >= cfg.spp;
+        const uint32_t grid128 = (p.n_paths + DUST_THREADS - 1) / DUST_THREADS, grid256 = (p.n_paths + 255) / 256;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_wf_counters, 0, kWfCounterWords * sizeof(uint32_t), ctx->stream));
+        wf_gen_primary<<<grid256, 256, 0, ctx->stream>>>(p);
+        count_launch(ctx);
+        for (uint32_t depth = 0; depth <= cfg.max_bounces; depth++) {
+            p.depth = depth;
+            // queue sizes live on the device: launch for the largest possible queue, surplus CTAs exit at once
+            const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : p.counts + 3;
+            if (depth >= pt_depth) trace_pt(p.qc, n_closest, 2 * depth, grid128); else trace(p.qc, n_closest, nullptr, grid128);
+            if (stats) wf_shade<true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_shade<false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p);
+            count_launch(ctx);
+            if (depth >= pt_depth) trace_pt(p.qs, p.counts + 4 * depth + 1, 2 * depth + 1, grid128); else trace(p.qs, p.counts + 4 * depth + 1, nullptr, grid128);
+            if (depth < cfg.max_bounces) {
+                wf_scatter<<<(p.n_paths + WF_SCATTER_CHUNK - 1) / WF_SCATTER_CHUNK, WF_SCATTER_THREADS, 0, ctx->stream>>>(p);
+                count_launch(ctx);
+            }
+        }
+        wf_resolve<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(p);
+        count_launch(ctx);
+        CU_TRY(ctx, pt_err);
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    return DUST_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -308,11 +422,13 @@ int32_t dust_ctx_create(int32_t device, DustCtx **out)
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_work, sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return DUST_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char *k = std::getenv("DUST_KERNEL")) ctx->kernel_variant = (k[0] == 'v' && k[1] == '3') ? 3 : 2;   // A/B only
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return DUST_OK;
@@ -325,6 +441,9 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
+    if (ctx->d_wf_counters) cudaFree(ctx->d_wf_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DUST_OK;
@@ -608,12 +727,40 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     if (n_threads / DUST_THREADS > 0x7FFFFFFFull) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "frame too large");
     const uint32_t grid = (uint32_t)(n_threads / DUST_THREADS);
     const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
-    auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
-    if (nl == 3) { if (stats) launch(frame_kernel<3, true>); else launch(frame_kernel<3, false>); }
-    else if (nl == 4) { if (stats) launch(frame_kernel<4, true>); else launch(frame_kernel<4, false>); }
-    else { if (stats) launch(frame_kernel<0, true>); else launch(frame_kernel<0, false>); }
+    // Pipeline: frames with bounces re-order their rays between path vertices (wavefront.cuh); coherent
+    // frames (primary + sun only) and small frames stay in the single-launch megakernel.
+    bool wavefront = cfg.max_bounces >= 1 && (uint64_t)tiles_per_shard * 1024u * cfg.spp >= (1u << 18);
+    if (cfg.flags & DUST_TRACE_PIPELINE_WAVEFRONT) wavefront = true;
+    if (cfg.flags & DUST_TRACE_PIPELINE_MEGAKERNEL) wavefront = false;
+    if (wavefront) {
+        const int32_t rc = trace_wavefront(ctx, p, tiles_per_shard, nl, stats);
+        if (rc != DUST_OK) return rc;
+    } else if (ctx->kernel_variant == 3) {
+        // persistent lanes: one resident wave of CTAs, pixels claimed from a global counter
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
+        const uint32_t n_items = tiles_per_shard * 1024u;
+        cudaError_t le = cudaSuccess;
+        auto launch = [&](auto kernel) {
+            int per_sm = 0;
+            le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
+            if (le != cudaSuccess) return;
+            const uint32_t want = (n_items + DUST_THREADS - 1) / DUST_THREADS;
+            const uint32_t pgrid = std::min<uint32_t>(want, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
+            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, ctx->d_work, n_items);
+        };
+        if (nl == 3) { if (stats) launch(frame_kernel_pt<3, true>); else launch(frame_kernel_pt<3, false>); }
+        else if (nl == 4) { if (stats) launch(frame_kernel_pt<4, true>); else launch(frame_kernel_pt<4, false>); }
+        else { if (stats) launch(frame_kernel_pt<0, true>); else launch(frame_kernel_pt<0, false>); }
+        CU_TRY(ctx, le);
+        count_launch(ctx);
+    } else {
+        auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
+        if (nl == 3) { if (stats) launch(frame_kernel<3, true>); else launch(frame_kernel<3, false>); }
+        else if (nl == 4) { if (stats) launch(frame_kernel<4, true>); else launch(frame_kernel<4, false>); }
+        else { if (stats) launch(frame_kernel<0, true>); else launch(frame_kernel<0, false>); }
+        count_launch(ctx);
+    }
     CU_TRY(ctx, cudaGetLastError());
-    count_launch(ctx);
 
     if (frame->memory == DUST_MEM_HOST) {
         CU_TRY(ctx, cudaMemcpyAsync(frame->radiance, scratch, out_pixels * px_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -659,10 +806,26 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     const uint64_t want = (n + DUST_THREADS - 1) / DUST_THREADS;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 64u);
     const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
-    auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
-    if (nl == 3) { if (stats) launch(rays_kernel<3, true>); else launch(rays_kernel<3, false>); }
-    else if (nl == 4) { if (stats) launch(rays_kernel<4, true>); else launch(rays_kernel<4, false>); }
-    else { if (stats) launch(rays_kernel<0, true>); else launch(rays_kernel<0, false>); }
+    if (ctx->kernel_variant == 3) {
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
+        cudaError_t le = cudaSuccess;
+        auto launch = [&](auto kernel) {
+            int per_sm = 0;
+            le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
+            if (le != cudaSuccess) return;
+            const uint32_t pgrid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * std::max(per_sm, 1));
+            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, ctx->d_work);
+        };
+        if (nl == 3) { if (stats) launch(rays_kernel_pt<3, true>); else launch(rays_kernel_pt<3, false>); }
+        else if (nl == 4) { if (stats) launch(rays_kernel_pt<4, true>); else launch(rays_kernel_pt<4, false>); }
+        else { if (stats) launch(rays_kernel_pt<0, true>); else launch(rays_kernel_pt<0, false>); }
+        CU_TRY(ctx, le);
+    } else {
+        auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
+        if (nl == 3) { if (stats) launch(rays_kernel<3, true>); else launch(rays_kernel<3, false>); }
+        else if (nl == 4) { if (stats) launch(rays_kernel<4, true>); else launch(rays_kernel<4, false>); }
+        else { if (stats) launch(rays_kernel<0, true>); else launch(rays_kernel<0, false>); }
+    }
     CU_TRY(ctx, cudaGetLastError());
     count_launch(ctx);
     if (memory == DUST_MEM_HOST) {

@@ -1,0 +1,637 @@
+// sm_100a device code, part 4: the wavefront pipeline of dust_trace (frames with GI bounces).
+//
+// frame_kernel (kernels.cuh) keeps a path in one thread from camera ray to pixel.  That is ideal for
+// coherent rays (primary-only frames: 27 of 32 lanes busy per traversal step), but diffuse bounce rays
+// of neighbouring pixels point in unrelated directions: on the castle frame the warp then runs with 13
+// busy lanes and 17 lanes waiting for the slowest ray (profiles/r01_history.md); forcing one bounce
+// direction per warp — an experiment, not a valid render — halves the frame time.  The wavefront
+// pipeline gets that coherence legitimately by RE-ORDERING rays between path vertices:
+//
+//   wf_gen_primary   camera rays of every (pixel, sample) path of the batch          -> closest queue
+//   per depth v = 0 .. max_bounces:
+//     wf_trace       closest hit of every ray of the queue                           -> hit records
+//     wf_shade       apply the previous vertex's sun visibility, consume the hit (sky on a miss,
+//                    surface on a hit), emit the sun-shadow ray -> shadow queue and the cosine-weighted
+//                    bounce ray -> staging queue with a direction bin (octahedral 8x8)
+//     wf_trace       any hit of every shadow ray                                     -> visibility byte per path
+//     wf_scatter     counting sort of the staging queue by direction bin (stable per 2048-ray chunk, i.e.
+//                    Morton pixel order inside a bin)                                -> next closest queue
+//   wf_resolve       last visibility, sRGB -> ACEScg, mean over samples in sample order -> frame
+//
+// Rays of one warp of the bounce pass then start within a few voxels of each other and point into the
+// same 1/64 of the sphere.  Every ray is traced by the same trace_scene as in the megakernel and every
+// float of a path is accumulated in the same order, so results are bit-identical to frame_kernel;
+// queue order (atomics) varies from run to run but no result depends on it.
+// Path state and queues live in HBM: ~175 B per path per batch, ~0.3 KB of traffic per ray.
+#pragma once
+#include "kernels.cuh"
+
+namespace dust {
+
+#define WF_BINS 64
+#define WF_SCATTER_THREADS 256
+#define WF_SCATTER_CHUNK 2048
+
+struct WfQueue {
+    float4 *a;          // origin.xyz, tmin
+    float4 *b;          // direction.xyz, tmax
+    uint32_t *path;     // path index; bit 31: any-hit (shadow) ray
+};
+
+struct WfParams {
+    FrameParams f;
+    uint32_t n_slots;                 // pixel slots of this shard (tiles * 1024, Morton order inside a tile)
+    uint32_t n_paths;                 // n_slots * batch_spp
+    uint32_t batch_spp, batch_first;  // samples per pixel in this batch, index of its first sample
+    uint32_t depth;                   // vertex index of the closest queue being traced / shaded
+    uint32_t last_batch;
+    float4 *ps0, *ps1, *ps2;          // path state: (T, s1) (L, flags) (pending sun term, -)
+    WfQueue qc, qs, qg;               // closest queue, shadow queue, staging (unsorted bounce rays)
+    uint4 *hits;                      // per closest-queue slot: t, instance | voxel << 20, leaf, leaf origin
+    uint8_t *vis;                     // per path: 1 = its pending shadow ray was occluded
+    uint8_t *bin;                     // per staging slot
+    uint4 *cand;                      // per queue slot: 2 x uint4 = up to WF_CANDS sorted candidate keys (wf_cull)
+    uint32_t *overflow;               // queue slots whose candidate list did not fit: traced by wf_trace with the full cull
+    uint32_t *counts;                 // per depth: [4v+1] shadow rays, [4v+2] bounce rays (= next closest queue); [3] = n_paths
+    uint32_t *bins;                   // per depth: WF_BINS totals, then WF_BINS cursors
+    float4 *acc;                      // per pixel slot, carried across batches
+};
+
+#define WF_CANDS 8                    // pre-culled candidates per ray; rays touching more instances take the slow path
+#define WF_PEND 1u                    // ps1.w flag: a sun term is pending on vis[path]
+
+__device__ __forceinline__ uint32_t wf_in_count(const WfParams &p)
+{
+    return p.depth == 0 ? p.n_paths : p.counts[4 * (p.depth - 1) + 2];
+}
+
+// pixel of slot (Morton inside 32x32 tiles; tile t = lt * shard_count + shard_index)
+__device__ __forceinline__ bool wf_pixel(const FrameParams &f, uint32_t slot, uint32_t &px, uint32_t &py, uint32_t &out_index)
+{
+    const uint32_t lt = slot >> 10, q = slot & 1023u;
+    const uint32_t lx = even_bits(q), ly = even_bits(q >> 1);
+    const uint32_t t = lt * f.cfg.shard_count + f.cfg.shard_index;
+    const uint32_t tile_x = t % f.tiles_x, tile_y = t / f.tiles_x;
+    px = tile_x * 32u + lx; py = tile_y * 32u + ly;
+    out_index = f.cfg.shard_count > 1 ? lt * 1024u + ly * 32u + lx : py * f.cfg.width + px;
+    return tile_y < f.tiles_y && px < f.cfg.width && py < f.cfg.height;
+}
+
+__global__ void __launch_bounds__(256) wf_gen_primary(const __grid_constant__ WfParams p)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= p.n_paths) return;
+    const DustTraceConfig &cfg = p.f.cfg;
+    const uint32_t slot = i / p.batch_spp, smp = p.batch_first + (i - slot * p.batch_spp);
+    uint32_t px, py, oi;
+    float4 a = make_float4(0.0f, 0.0f, 0.0f, 1.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);     // tmax < tmin: traces nothing
+    uint32_t s1 = 0;
+    if (wf_pixel(p.f, slot, px, py, oi)) {
+        const uint32_t s0 = pcg((py * cfg.width + px) ^ pcg(cfg.seed + 0x9E3779B9u * cfg.frame_index));
+        s1 = pcg(s0 + smp);
+        float jx = 0.5f, jy = 0.5f;
+        if (smp > 0) { jx = u01(pcg(s1 + 0u)); jy = u01(pcg(s1 + 1u)); }
+        f3 ro, rd;
+        camera_ray(p.f.cam, cfg.width, cfg.height, px, py, jx, jy, ro, rd);                   // primary.rgen:9-21
+        a = make_float4(ro.x, ro.y, ro.z, p.f.cam.near);
+        b = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
+    }
+    p.qc.a[i] = a; p.qc.b[i] = b; p.qc.path[i] = i;
+    p.ps0[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(s1));
+    if (i == 0) p.counts[3] = p.n_paths;                               // size of the depth-0 closest queue, for kernels that read it from memory
+}
+
+// One thread per ray of a queue; the same trace_scene as the megakernel.
+// `list` != NULL: trace only the queue slots list[0 .. *count) (the rays wf_cull could not pre-cull).
+template <int NL, bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count,
+                                                                          const uint32_t *list)
+{
+    __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
+    const uint32_t n = count ? *count : p.n_paths;
+    if (blockIdx.x * DUST_THREADS >= n) return;
+    const uint32_t k = blockIdx.x * DUST_THREADS + threadIdx.x;
+    const bool live = k < n;
+    const uint32_t i = live && list ? __ldg(&list[k]) : k;
+    float4 a = make_float4(0.0f, 0.0f, 0.0f, 1.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    uint32_t pw = 0;
+    if (live) { a = __ldg(&q.a[i]); b = __ldg(&q.b[i]); pw = __ldg(&q.path[i]); }
+    Counters st = {};
+    Hit h;
+    trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st);
+    if (live) {
+        if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = h.hit ? 1 : 0;
+        else p.hits[i] = h.hit ? make_uint4(__float_as_uint(h.t), h.inst | (h.voxel << 20), h.leaf, h.pos)
+                               : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    }
+    if (STATS) flush_counters(p.f.counters, st);
+}
+
+
+// ---------------------------------------------------------------- incoherent rays: pre-cull + persistent lanes
+//
+// wf_trace gives every ray a thread; a warp lasts as long as its longest ray.  For sorted bounce rays
+// that still leaves 13 of 32 lanes idle (profiles/r01_history.md): neighbouring rays of one direction
+// bin start a few voxels apart and meet different fates.  For those queues the work is split:
+//   wf_cull      one thread per ray, all lanes busy: walk the instance BVH, store the sorted candidate
+//                keys of the ray (<= WF_CANDS; rays that touch more go to an overflow list for wf_trace)
+//   wf_trace_pt  persistent lanes over the queue: NEXT / WALK / LEAF voted as in trace_scene, and a lane
+//                whose ray is finished writes its result and claims the next ray of the queue (one
+//                warp-aggregated atomic) inside the NEXT operation — no lane waits for another lane's ray.
+
+template <bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, uint32_t *overflow_count)
+{
+    __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
+    const unsigned full = 0xffffffffu;
+    const uint32_t n = *count;
+    if (blockIdx.x * DUST_THREADS >= n) return;
+    const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const DSceneView &sc = p.f.scene;
+    uint32_t *sm = s_scratch + threadIdx.x;
+    const uint32_t id_mask = (1u << sc.id_bits) - 1u;
+    bool over = false;
+    if (i < n) {
+        const float4 a = __ldg(&q.a[i]), b = __ldg(&q.b[i]);
+        const f3 ro = mk3(a.x, a.y, a.z), rd = mk3(b.x, b.y, b.z);
+        const float tmin = a.w, tmax = b.w;
+        const f3 winv = mk3(fabsf(rd.x) < 1e-30f ? copysignf(1e30f, rd.x) : 1.0f / rd.x,
+                            fabsf(rd.y) < 1e-30f ? copysignf(1e30f, rd.y) : 1.0f / rd.y,
+                            fabsf(rd.z) < 1e-30f ? copysignf(1e30f, rd.z) : 1.0f / rd.z);
+        int sp = DUST_SCRATCH_WORDS, pend = -1, nc = 0;
+        if (sc.n_inst) {
+            const float te = box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], ro, winv, tmin, tmax);
+            if (te != CUDART_INF_F) {
+                if (sc.root_ref >= 0) pend = sc.root_ref;
+                else { sm[0] = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~sc.root_ref; nc = 1; }
+            }
+        }
+        while (pend >= 0 && nc + 3 <= sp) {                           // same expansion as trace_scene phase 1
+            const float4 *nd = reinterpret_cast<const float4 *>(sc.bvh + pend);
+            const float4 na = __ldg(nd), nb = __ldg(nd + 1), ncx = __ldg(nd + 2), ne = __ldg(nd + 3);
+            float t0 = box_entry(na.x, na.y, na.z, nb.x, nb.y, nb.z, ro, winv, tmin, tmax);
+            float t1 = box_entry(ncx.x, ncx.y, ncx.z, ne.x, ne.y, ne.z, ro, winv, tmin, tmax);
+            int c0 = __float_as_int(na.w), c1 = __float_as_int(nb.w);
+            if (t1 < t0) { const float tf = t0; t0 = t1; t1 = tf; const int ci = c0; c0 = c1; c1 = ci; }
+            int next = -1;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const float te = s ? t1 : t0;
+                const int ch = s ? c1 : c0;
+                if (te == CUDART_INF_F) continue;
+                if (ch >= 0) {
+                    if (next < 0) next = ch; else sm[--sp * DUST_THREADS] = (uint32_t)ch;
+                } else {
+                    const uint32_t key = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~ch;
+                    int k = nc++;
+                    while (k > 0) {
+                        const uint32_t prev = sm[(k - 1) * DUST_THREADS];
+                        if (prev <= key) break;
+                        sm[k * DUST_THREADS] = prev; --k;
+                    }
+                    sm[k * DUST_THREADS] = key;
+                }
+            }
+            if (next < 0 && sp < DUST_SCRATCH_WORDS) next = (int)sm[sp++ * DUST_THREADS];
+            pend = next;
+        }
+        over = pend >= 0 || nc > WF_CANDS;                            // list incomplete or too long: slow path
+        uint32_t c[WF_CANDS];
+#pragma unroll
+        for (int k = 0; k < WF_CANDS; k++) c[k] = (!over && k < nc) ? sm[k * DUST_THREADS] : 0xFFFFFFFFu;
+        p.cand[2 * (size_t)i] = make_uint4(c[0], c[1], c[2], c[3]);
+        p.cand[2 * (size_t)i + 1] = make_uint4(c[4], c[5], c[6], c[7]);
+        if (over) p.cand[2 * (size_t)i].x = 0xFFFFFFFEu;               // marker: not pre-culled
+    }
+    const unsigned m = __ballot_sync(full, over);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(overflow_count, (uint32_t)__popc(m));
+        base = __shfl_sync(full, base, __ffs(m) - 1);
+        if (over) p.overflow[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+    }
+}
+
+#ifndef DUST_PT_MIN_BLOCKS2
+#define DUST_PT_MIN_BLOCKS2 6
+#endif
+
+enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
+
+template <int NL, bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work)
+{
+    __shared__ uint32_t s_cand[WF_CANDS * DUST_THREADS];
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const DSceneView &sc = p.f.scene;
+    uint32_t *sm = s_cand + threadIdx.x;
+    const uint32_t id_mask = (1u << sc.id_bits) - 1u;
+    const uint32_t n = *count;
+    Counters st = {};
+
+    // the ray in flight and its best hit
+    bool have_ray = false, hit = false;
+    uint32_t ri = 0, pw = 0;
+    f3 ro = mk3(0.0f, 0.0f, 0.0f), rd = mk3(1.0f, 1.0f, 1.0f);
+    float tmin = 0.0f, cur = 0.0f;
+    uint32_t b_inst = 0xFFFFFFFFu, b_leaf = 0, b_pos = 0, b_vox = 0;
+    int mode = W_NEXT, j = 0;                                          // j == WF_CANDS or key 0xFFFFFFFF: list exhausted
+    bool exhausted = true;
+    // instance walk
+    uint32_t inst = 0, leaf_i = 0;
+    f3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(1.0f, 1.0f, 1.0f), inv = mk3(1.0f, 1.0f, 1.0f);
+    int jx = 0, jy = 0, jz = 0, L4 = 0;
+    float t_exit = 0.0f;
+    uint32_t bnd0 = 0, bnd1 = 0, bnd2 = 0;
+    const DNode16 *n16 = nullptr;
+    const uint4 *mids = nullptr, *leaves = nullptr;
+    uint32_t mid_lo = 0, mid_hi = 0, mid_base = 0;
+    bool have_mid = false, four = NL == 4;
+
+#pragma unroll 1
+    for (;;) {
+        const uint32_t packed = __reduce_add_sync(full, mode < W_DEAD ? (1u << (8 * mode)) : 0u);
+        if (packed == 0u) break;
+        const uint32_t n_next = packed & 255u, n_walk = (packed >> 8) & 255u, n_leaf = packed >> 16;
+        int op = W_WALK;
+        uint32_t cnt = n_walk;
+        if (n_next > cnt) { op = W_NEXT; cnt = n_next; }
+        if (n_leaf > cnt) { op = W_LEAF; cnt = n_leaf; }
+        if (STATS && lane == 0) {
+            st.dbg[op == W_WALK ? 0 : (op == W_LEAF ? 1 : 2)]++;
+            st.dbg[op == W_WALK ? 3 : (op == W_LEAF ? 4 : 5)] += cnt;
+            st.dbg[6] += 32u - (n_next + n_walk + n_leaf);
+        }
+
+        if (op == W_WALK) {
+            if (mode == W_WALK) {
+                if (L4) {
+                    if (STATS) st.dbg[L4 == 1 ? 7 : (L4 == 4 ? 8 : 9)]++;
+                    const int cx = jx & ~(L4 - 1), cy = jy & ~(L4 - 1), cz = jz & ~(L4 - 1);
+                    const bool px_ = d.x > 0.0f, py_ = d.y > 0.0f, pz_ = d.z > 0.0f;
+                    const float tx = ((float)((px_ ? cx + L4 : cx) << 2) - o.x) * inv.x;
+                    const float ty = ((float)((py_ ? cy + L4 : cy) << 2) - o.y) * inv.y;
+                    const float tz = ((float)((pz_ ? cz + L4 : cz) << 2) - o.z) * inv.z;
+                    const float t_next = fminf(fminf(tx, ty), tz);
+                    bool out = !(t_next <= t_exit);                   // inclusive, DESIGN.md "Traversal semantics"
+                    int nx = jx, ny = jy, nz = jz;
+                    if (tx <= t_next) { nx = px_ ? cx + L4 : cx - 1; out |= (uint32_t)(nx - (int)(bnd0 & 0xFFFFu)) >= (bnd0 >> 16); }
+                    else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.x, t_next, o.x)) >> 2; nx = min(max(ip, cx), cx + L4 - 1); }
+                    if (ty <= t_next) { ny = py_ ? cy + L4 : cy - 1; out |= (uint32_t)(ny - (int)(bnd1 & 0xFFFFu)) >= (bnd1 >> 16); }
+                    else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.y, t_next, o.y)) >> 2; ny = min(max(ip, cy), cy + L4 - 1); }
+                    if (tz <= t_next) { nz = pz_ ? cz + L4 : cz - 1; out |= (uint32_t)(nz - (int)(bnd2 & 0xFFFFu)) >= (bnd2 >> 16); }
+                    else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.z, t_next, o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
+                    have_mid = have_mid && (((uint32_t)((nx ^ jx) | (ny ^ jy) | (nz ^ jz)) >> 2) == 0u);
+                    jx = nx; jy = ny; jz = nz;
+                    L4 = 0;
+                    if (out) mode = W_NEXT;
+                }
+                if (mode == W_WALK) {
+                    if (!have_mid) {
+                        const DNode16 *node = n16;
+                        bool alive = true;
+                        if (NL == 4 || (NL == 0 && four)) {
+                            const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
+                            const uint4 w = __ldg(&node->word[tidx >> 6]);
+                            if (STATS) st.mask_words++;
+                            const uint32_t b = tidx & 63u;
+                            if (!bit64(w.x, w.y, b)) { L4 = 64; alive = false; }
+                            else {
+                                if (STATS) st.child_ptrs++;
+                                node = n16 + (w.z + rank64(w.x, w.y, b));
+                            }
+                        }
+                        if (alive) {
+                            const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
+                            if (STATS) st.mask_words++;
+                            const uint4 w = __ldg(&node->word[ridx >> 6]);
+                            const uint32_t b = ridx & 63u;
+                            L4 = 4;
+                            if (bit64(w.x, w.y, b)) {
+                                const uint4 mid = __ldg(&mids[w.z + rank64(w.x, w.y, b)]);
+                                mid_lo = mid.x; mid_hi = mid.y; mid_base = mid.z;
+                                have_mid = true;
+                            }
+                        }
+                    } else if (STATS) {
+                        if (NL == 4 || (NL == 0 && four)) { st.mask_words++; st.child_ptrs++; }
+                        st.mask_words++;
+                    }
+                    if (have_mid) {
+                        if (STATS) { st.child_ptrs++; st.mask_words++; }
+                        const uint32_t midx = ((uint32_t)(jx & 3) << 4) | ((uint32_t)(jy & 3) << 2) | (uint32_t)(jz & 3);
+                        L4 = 1;
+                        if (bit64(mid_lo, mid_hi, midx)) {
+                            if (STATS) { st.child_ptrs++; st.mask_words++; }
+                            leaf_i = mid_base + rank64(mid_lo, mid_hi, midx);
+                            L4 = 0;
+                            mode = W_LEAF;
+                        }
+                    }
+                }
+            }
+        } else if (op == W_LEAF) {
+            if (mode == W_LEAF) {
+                const uint4 leaf = __ldg(&leaves[leaf_i]);
+                if (STATS) st.dbg[10]++;
+                const f3 lo = mk3(o.x - (float)(jx << 2), o.y - (float)(jy << 2), o.z - (float)(jz << 2));   // hit.rint:140
+                float th; uint32_t vox;
+                if (leaf_dda_inv<STATS>(lo, d, inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]) && tmin <= th && th <= cur) {   // reportIntersectionEXT
+                    if (pw >> 31) { hit = true; exhausted = true; }                    // any hit ends a shadow ray
+                    else if (!hit || th < cur || inst < b_inst) {                      // (t, instance) lexicographic
+                        hit = true; cur = th; b_inst = inst; b_leaf = leaf_i;
+                        b_pos = (uint32_t)jx | ((uint32_t)jy << 10) | ((uint32_t)jz << 20); b_vox = vox;
+                    }
+                    mode = W_NEXT;                                                     // first accepted hit is this instance's closest
+                } else { mode = W_WALK; L4 = 1; }
+            }
+        } else {
+            bool need = false;
+            if (mode == W_NEXT) {
+                bool entered = false;
+                if (!exhausted) {
+                    const uint32_t key = sm[j * DUST_THREADS];
+                    ++j;
+                    if (j == WF_CANDS) exhausted = true;
+                    if (key == 0xFFFFFFFFu || __uint_as_float(key & ~id_mask) > cur) exhausted = true;   // end of list / sorted: nothing further can beat the best hit
+                    else {
+                        inst = key & id_mask;
+                        const DInstance &in = sc.inst[inst];
+                        object_ray(in, ro, rd, o, d);
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(in.bounds));
+                        bnd0 = bw.x; bnd1 = bw.y; bnd2 = bw.z;
+                        const int bx0 = (int)(bnd0 & 0xFFFFu) << 2, by0 = (int)(bnd1 & 0xFFFFu) << 2, bz0 = (int)(bnd2 & 0xFFFFu) << 2;
+                        const int bx1 = bx0 + ((int)(bnd0 >> 16) << 2), by1 = by0 + ((int)(bnd1 >> 16) << 2), bz1 = bz0 + ((int)(bnd2 >> 16) << 2);
+                        const float t0x = ((float)bx0 - o.x) * inv.x, t0y = ((float)by0 - o.y) * inv.y, t0z = ((float)bz0 - o.z) * inv.z;
+                        const float t1x = ((float)bx1 - o.x) * inv.x, t1y = ((float)by1 - o.y) * inv.y, t1z = ((float)bz1 - o.z) * inv.z;
+                        const float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+                        const float tmax_pad = cur + (fabsf(cur) * 3.814697265625e-06f + 9.5367431640625e-07f);
+                        t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
+                        if (t_enter <= t_exit && bx1 > bx0) {
+                            const int ix = __float2int_rd(__fmaf_rn(d.x, t_enter, o.x));
+                            const int iy = __float2int_rd(__fmaf_rn(d.y, t_enter, o.y));
+                            const int iz = __float2int_rd(__fmaf_rn(d.z, t_enter, o.z));
+                            jx = min(max(ix, bx0), bx1 - 1) >> 2; jy = min(max(iy, by0), by1 - 1) >> 2; jz = min(max(iz, bz0), bz1 - 1) >> 2;
+                            const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(&in.n16));
+                            n16 = reinterpret_cast<const DNode16 *>(p01.x);
+                            mids = reinterpret_cast<const uint4 *>(p01.y);
+                            leaves = in.leaves;
+                            if (NL == 0) four = bw.w == 4u;
+                            have_mid = false;
+                            L4 = 0;
+                            mode = W_WALK;
+                            entered = true;
+                        }
+                    }
+                }
+                need = !entered && exhausted;
+            }
+            // lanes whose ray is finished: write the result, claim the next ray of the queue (one atomic per warp)
+            const unsigned want = __ballot_sync(full, need);
+            if (want) {
+                if (need && have_ray) {
+                    if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = hit ? 1 : 0;
+                    else p.hits[ri] = hit ? make_uint4(__float_as_uint(cur), b_inst | (b_vox << 20), b_leaf, b_pos)
+                                          : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+                }
+                const int leader = __ffs(want) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(want));
+                base = __shfl_sync(full, base, leader);
+                if (need) {
+                    const unsigned long long idx = base + (unsigned)__popc(want & ((1u << lane) - 1u));
+                    have_ray = false;
+                    if (idx >= n) mode = W_DEAD;
+                    else {
+                        ri = (uint32_t)idx;
+                        const uint4 c0 = __ldg(&p.cand[2 * (size_t)ri]), c1 = __ldg(&p.cand[2 * (size_t)ri + 1]);
+                        if (c0.x != 0xFFFFFFFEu) {                                     // else: overflow ray, wf_trace does it
+                            const float4 a = __ldg(&q.a[ri]), b = __ldg(&q.b[ri]);
+                            pw = __ldg(&q.path[ri]);
+                            ro = mk3(a.x, a.y, a.z); tmin = a.w; rd = mk3(b.x, b.y, b.z); cur = b.w;
+                            sm[0 * DUST_THREADS] = c0.x; sm[1 * DUST_THREADS] = c0.y; sm[2 * DUST_THREADS] = c0.z; sm[3 * DUST_THREADS] = c0.w;
+                            sm[4 * DUST_THREADS] = c1.x; sm[5 * DUST_THREADS] = c1.y; sm[6 * DUST_THREADS] = c1.z; sm[7 * DUST_THREADS] = c1.w;
+                            hit = false; b_inst = 0xFFFFFFFFu;
+                            j = 0; exhausted = false;
+                            have_ray = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (STATS) flush_counters(p.f.counters, st);
+}
+
+// octahedral 8x8 direction bin (a sorting heuristic only: no result depends on it)
+__device__ __forceinline__ uint32_t wf_direction_bin(f3 d)
+{
+    const float s = 1.0f / ((fabsf(d.x) + fabsf(d.y)) + fabsf(d.z));
+    float u = d.x * s, v = d.z * s;
+    if (d.y < 0.0f) {
+        const float fu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+        u = fu; v = fv;
+    }
+    const int bu = min(max((int)((u * 0.5f + 0.5f) * 8.0f), 0), 7), bv = min(max((int)((v * 0.5f + 0.5f) * 8.0f), 0), 7);
+    return (uint32_t)(bv * 8 + bu);
+}
+
+// One thread per ray of the closest queue of depth p.depth: apply the pending sun term, consume the
+// hit, emit the vertex's shadow and bounce rays.  The per-path arithmetic is frame_kernel's, in order.
+template <bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__ WfParams p)
+{
+    __shared__ uint32_t s_hist[WF_BINS];
+    const unsigned full = 0xffffffffu;
+    const DustTraceConfig &cfg = p.f.cfg;
+    const uint32_t n = wf_in_count(p);
+    if (blockIdx.x * DUST_THREADS >= n) return;
+    if (threadIdx.x < WF_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    bool live = i < n;
+    Counters st = {};
+    uint32_t path = 0;
+    bool emit_shadow = false, emit_bounce = false;
+    f3 ro = mk3(0.0f, 0.0f, 0.0f), rd = mk3(0.0f, 0.0f, 0.0f);
+    uint32_t bin = 0;
+    if (live) {
+        path = __ldg(&p.qc.path[i]);
+        const float4 a = __ldg(&p.qc.a[i]), b = __ldg(&p.qc.b[i]);
+        const uint4 hw = __ldg(&p.hits[i]);
+        const float4 s0 = p.ps0[path];
+        f3 T = mk3(s0.x, s0.y, s0.z), L = mk3(0.0f, 0.0f, 0.0f);
+        const uint32_t s1 = __float_as_uint(s0.w);
+        ro = mk3(a.x, a.y, a.z); rd = mk3(b.x, b.y, b.z);
+        uint32_t px = 0, py = 0, oi = 0;
+        bool valid = true;
+        uint32_t smp = 1;
+        if (p.depth == 0) {
+            const uint32_t slot = path / p.batch_spp;
+            smp = p.batch_first + (path - slot * p.batch_spp);
+            valid = wf_pixel(p.f, slot, px, py, oi);
+        } else {
+            const float4 s1v = p.ps1[path], s2v = p.ps2[path];
+            L = mk3(s1v.x, s1v.y, s1v.z);
+            if ((__float_as_uint(s1v.w) & WF_PEND) && !p.vis[path]) { L.x += s2v.x; L.y += s2v.y; L.z += s2v.z; }   // nee.rmiss:11-22
+        }
+        uint32_t flags = 0;
+        f3 pend = mk3(0.0f, 0.0f, 0.0f);
+        if (valid) {
+            const bool hit = hw.y != 0xFFFFFFFFu;
+            if (STATS) { if (p.depth == 0) st.primary_rays++; else st.bounce_rays++; }
+            if (p.depth == 0 && smp == 0 && (cfg.flags & DUST_TRACE_WRITE_HITS) && p.f.hit_instance) {
+                const uint32_t pi = py * cfg.width + px;
+                p.f.hit_instance[pi] = hit ? (hw.y & 0xFFFFFu) : 0xFFFFFFFFu; p.f.hit_leaf[pi] = hit ? hw.z : 0xFFFFFFFFu;
+                p.f.hit_voxel[pi] = hit ? (uint8_t)(hw.y >> 20) : (uint8_t)0xFF; p.f.hit_t[pi] = hit ? __uint_as_float(hw.x) : CUDART_INF_F;
+            }
+            if (hit) {
+                Hit h;
+                h.hit = true; h.t = __uint_as_float(hw.x); h.inst = hw.y & 0xFFFFFu; h.voxel = hw.y >> 20; h.leaf = hw.z; h.pos = hw.w;
+                f3 sn;
+                const f3 al = surface_at<STATS>(p.f.scene, h, ro, rd, sn, st);          // ro becomes the offset hit point
+                if (p.depth == 0) T = al;                                               // tone_map.comp:195-203
+                else { T.x = T.x * al.x; T.y = T.y * al.y; T.z = T.z * al.z; }          // final_gather.rchit:76-80
+                if (dot3(mk3(p.f.sky.direction[0], p.f.sky.direction[1], p.f.sky.direction[2]), sn) > 0.0f) {   // ambient_occlusion.rgen:33-50
+                    if (STATS) st.shadow_rays++;
+                    const float ndl = dot3(sn, mk3(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2]));
+                    const f3 ts = acescg2srgb(mk3(p.f.sun_nee[0] * ndl, p.f.sun_nee[1] * ndl, p.f.sun_nee[2] * ndl));
+                    pend = mk3(T.x * ts.x, T.y * ts.y, T.z * ts.z);
+                    flags |= WF_PEND;
+                    emit_shadow = true;
+                }
+                if (p.depth < cfg.max_bounces) {
+                    const uint32_t v = p.depth;
+                    const float u1 = u01(pcg(s1 + 2u + 2u * v)), u2 = u01(pcg(s1 + 3u + 2u * v));   // final_gather.rgen:32-34
+                    const float rr = sqrtf(u1), cz = sqrtf(1.0f - u1);
+                    float c, s;
+                    cossin_2pi(u2, c, s);
+                    rd = normalize3(rotate_by_normal(sn, mk3(rr * c, rr * s, cz)));
+                    bin = wf_direction_bin(rd);
+                    emit_bounce = true;
+                }
+            } else {
+                const f3 dn = normalize3(rd);
+                f3 sk, su;
+                sky_eval(p.f.sky, p.f.sun_ar2, dn.x, dn.y, dn.z, p.depth == 0, sk.x, sk.y, sk.z, su.x, su.y, su.z);
+                if (p.depth == 0) {                                                     // miss.rmiss:8-14
+                    L = acescg2srgb(mk3((sk.x + su.x) / 3.14f, (sk.y + su.y) / 3.14f, (sk.z + su.z) / 3.14f));
+                } else {                                                                // final_gather.rmiss:13-17
+                    const f3 ts = acescg2srgb(sk);
+                    L.x += T.x * ts.x; L.y += T.y * ts.y; L.z += T.z * ts.z;
+                }
+            }
+        }
+        p.ps0[path] = make_float4(T.x, T.y, T.z, __uint_as_float(s1));
+        p.ps1[path] = make_float4(L.x, L.y, L.z, __uint_as_float(flags));
+        p.ps2[path] = make_float4(pend.x, pend.y, pend.z, 0.0f);
+    }
+    // ---- compact the emitted rays into the queues: one atomic per warp and queue
+    {
+        const unsigned m = __ballot_sync(full, emit_shadow);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&p.counts[4 * p.depth + 1], (uint32_t)__popc(m));
+            base = __shfl_sync(full, base, __ffs(m) - 1);
+            if (emit_shadow) {
+                const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
+                p.qs.b[k] = make_float4(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2], 10000.0f);
+                p.qs.path[k] = path | 0x80000000u;
+            }
+        }
+    }
+    {
+        const unsigned m = __ballot_sync(full, emit_bounce);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&p.counts[4 * p.depth + 2], (uint32_t)__popc(m));
+            base = __shfl_sync(full, base, __ffs(m) - 1);
+            if (emit_bounce) {
+                const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                p.qg.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
+                p.qg.b[k] = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
+                p.qg.path[k] = path;
+                p.bin[k] = (uint8_t)bin;
+                atomicAdd(&s_hist[bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < WF_BINS && s_hist[threadIdx.x]) atomicAdd(&p.bins[2 * WF_BINS * p.depth + threadIdx.x], s_hist[threadIdx.x]);
+    if (STATS) flush_counters(p.f.counters, st);
+}
+
+// Counting sort of the staging queue by direction bin into the (next) closest queue.
+__global__ void __launch_bounds__(WF_SCATTER_THREADS) wf_scatter(const __grid_constant__ WfParams p)
+{
+    __shared__ uint32_t s_hist[WF_BINS], s_base[WF_BINS];
+    const uint32_t n = p.counts[4 * p.depth + 2];
+    const uint32_t chunk = blockIdx.x * WF_SCATTER_CHUNK;
+    if (chunk >= n) return;
+    uint32_t *totals = p.bins + 2 * WF_BINS * p.depth, *cursors = totals + WF_BINS;
+    if (threadIdx.x < WF_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    constexpr int PER = WF_SCATTER_CHUNK / WF_SCATTER_THREADS;
+    uint32_t rank[PER], b[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const uint32_t e = chunk + k * WF_SCATTER_THREADS + threadIdx.x;
+        b[k] = 0xFFFFFFFFu;
+        if (e < n) { b[k] = p.bin[e]; rank[k] = atomicAdd(&s_hist[b[k]], 1u); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // exclusive scan of the 64 bin totals (two per lane), then reserve this chunk's range in every bin
+        const uint32_t t0 = totals[2 * threadIdx.x], t1 = totals[2 * threadIdx.x + 1];
+        uint32_t s = t0 + t1;
+        for (int ofs = 1; ofs < 32; ofs <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, s, ofs); if ((int)threadIdx.x >= ofs) s += v; }
+        const uint32_t excl = s - (t0 + t1);
+        const uint32_t h0 = s_hist[2 * threadIdx.x], h1 = s_hist[2 * threadIdx.x + 1];
+        s_base[2 * threadIdx.x] = excl + (h0 ? atomicAdd(&cursors[2 * threadIdx.x], h0) : 0u);
+        s_base[2 * threadIdx.x + 1] = excl + t0 + (h1 ? atomicAdd(&cursors[2 * threadIdx.x + 1], h1) : 0u);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        if (b[k] == 0xFFFFFFFFu) continue;
+        const uint32_t e = chunk + k * WF_SCATTER_THREADS + threadIdx.x;
+        const uint32_t dst = s_base[b[k]] + rank[k];
+        p.qc.a[dst] = p.qg.a[e]; p.qc.b[dst] = p.qg.b[e]; p.qc.path[dst] = p.qg.path[e];
+    }
+}
+
+// One thread per pixel slot: last pending sun term, sRGB -> ACEScg, sum in sample order (tone_map.comp:192-203 input)
+__global__ void __launch_bounds__(256) wf_resolve(const __grid_constant__ WfParams p)
+{
+    const uint32_t slot = blockIdx.x * 256u + threadIdx.x;
+    if (slot >= p.n_slots) return;
+    uint32_t px, py, oi;
+    if (!wf_pixel(p.f, slot, px, py, oi)) return;
+    f3 acc = mk3(0.0f, 0.0f, 0.0f);
+    if (p.batch_first) { const float4 a = p.acc[slot]; acc = mk3(a.x, a.y, a.z); }
+    for (uint32_t s = 0; s < p.batch_spp; s++) {
+        const uint32_t path = slot * p.batch_spp + s;
+        const float4 s1v = p.ps1[path];
+        f3 L = mk3(s1v.x, s1v.y, s1v.z);
+        if ((__float_as_uint(s1v.w) & WF_PEND) && !p.vis[path]) { const float4 s2v = p.ps2[path]; L.x += s2v.x; L.y += s2v.y; L.z += s2v.z; }
+        const f3 Lc = srgb2acescg(L);
+        acc.x += Lc.x; acc.y += Lc.y; acc.z += Lc.z;
+    }
+    if (!p.last_batch) { p.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f); return; }
+    const float n = (float)p.f.cfg.spp;
+    const float4 outv = make_float4(acc.x / n, acc.y / n, acc.z / n, 1.0f);
+    if (p.f.radiance32) p.f.radiance32[oi] = outv;
+    if (p.f.radiance16) {
+        __half2 a = __floats2half2_rn(outv.x, outv.y), b = __floats2half2_rn(outv.z, outv.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&a); pk.y = *reinterpret_cast<uint32_t *>(&b);
+        reinterpret_cast<uint2 *>(p.f.radiance16)[oi] = pk;
+    }
+}
+
+}  // namespace dust

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (DUST_FMT_RGBA16F, DUST_FMT_RGBA32F, DUST_MEM_DEVICE, DUST_MEM_HOST, DUST_TRACE_STATS,
+from .capi import (PIPELINE_FLAGS, DUST_FMT_RGBA16F, DUST_FMT_RGBA32F, DUST_MEM_DEVICE, DUST_MEM_HOST, DUST_TRACE_STATS,
                    DUST_TRACE_WRITE_HITS, DustFrame, DustInstance, DustStats, DustTraceConfig, check)
 
 MISS = 0xFFFFFFFF
@@ -123,11 +123,12 @@ class Scene:
 
     # ---- dust_trace ------------------------------------------------------------------------------
     def trace(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0,
-              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None):
-        """Host-buffer call: returns dict(radiance[H,W,4], hit_instance, hit_leaf, hit_voxel, hit_t)."""
+              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None, pipeline=None):
+        """Host-buffer call: returns dict(radiance[H,W,4], hit_instance, hit_leaf, hit_voxel, hit_t).
+        pipeline: None / "auto", "megakernel" or "wavefront" (DUST_TRACE_PIPELINE_*; same results)."""
         ctx, lib = self.ctx, self.ctx.lib
         cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count,
-                              (DUST_TRACE_WRITE_HITS if hits else 0) | (DUST_TRACE_STATS if stats else 0))
+                              (DUST_TRACE_WRITE_HITS if hits else 0) | (DUST_TRACE_STATS if stats else 0) | PIPELINE_FLAGS[pipeline])
         res = {}
         if shard_count == 1:
             n_out, shape = width * height, (height, width, 4)
@@ -153,10 +154,10 @@ class Scene:
         return res
 
     def trace_device(self, camera, sky, width, height, radiance, spp=1, max_bounces=0, seed=0, frame_index=0,
-                     shard_index=0, shard_count=1, stats=False, fmt=DUST_FMT_RGBA32F, hit_buffers=None):
+                     shard_index=0, shard_count=1, stats=False, fmt=DUST_FMT_RGBA32F, hit_buffers=None, pipeline=None):
         """Device-buffer call (no copies, no sync): `radiance` is a CUDA tensor the kernel writes."""
         ctx, lib = self.ctx, self.ctx.lib
-        flags = (DUST_TRACE_STATS if stats else 0) | (DUST_TRACE_WRITE_HITS if hit_buffers else 0)
+        flags = (DUST_TRACE_STATS if stats else 0) | (DUST_TRACE_WRITE_HITS if hit_buffers else 0) | PIPELINE_FLAGS[pipeline]
         cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count, flags)
         fr = DustFrame(_ptr(radiance), None, None, None, None, DUST_MEM_DEVICE, fmt)
         if hit_buffers:

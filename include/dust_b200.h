@@ -97,7 +97,10 @@ typedef struct DustSky {
 
 enum {
     DUST_TRACE_WRITE_HITS = 1u,   /* fill the hit_* arrays of DustFrame (sample-0 primary ray) */
-    DUST_TRACE_STATS      = 2u    /* count rays / visited words; read back with dust_get_stats */
+    DUST_TRACE_STATS      = 2u,   /* count rays / visited words; read back with dust_get_stats */
+    /* pipeline override (default: chosen per frame).  Results are bit-identical either way. */
+    DUST_TRACE_PIPELINE_MEGAKERNEL = 4u,   /* one launch, a path stays in its thread */
+    DUST_TRACE_PIPELINE_WAVEFRONT  = 8u    /* rays re-ordered between path vertices (frames with bounces) */
 };
 
 /* Replaces the push constants + launch size of the four vkCmdTraceRaysKHR dispatches

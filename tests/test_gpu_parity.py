@@ -60,11 +60,15 @@ def test_teapot_primary_hits_bit_exact(teapot, host):
     _assert_radiance_close(g, o)
 
 
-@pytest.mark.parametrize("spp,bounces", [(1, 1), (4, 1), (2, 2)])
-def test_teapot_bounces_radiance(teapot, host, spp, bounces):
+PIPELINES = ["megakernel", "wavefront"]
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
+@pytest.mark.parametrize("spp,bounces", [(1, 1), (4, 1), (2, 2), (3, 0)])
+def test_teapot_bounces_radiance(teapot, host, spp, bounces, pipeline):
     W = H = 128
     cam, sky = _cam_for(teapot, host, W, H), host.sunlight_bake()
-    g = teapot.loaded.scene.trace(cam, sky, W, H, spp=spp, max_bounces=bounces, seed=7, frame_index=3, hits=True)
+    g = teapot.loaded.scene.trace(cam, sky, W, H, spp=spp, max_bounces=bounces, seed=7, frame_index=3, hits=True, pipeline=pipeline)
     o = teapot.oscene.render(cam, sky, W, H, spp=spp, max_bounces=bounces, seed=7, frame_index=3)
     _assert_hits_equal(g, o)
     _assert_radiance_close(g, o)
@@ -84,11 +88,12 @@ def test_castle_small_instances_bit_exact(castle_small, host):
     _assert_radiance_close(g, o)
 
 
-def test_castle_small_gi(castle_small, host):
+@pytest.mark.parametrize("pipeline", PIPELINES)
+def test_castle_small_gi(castle_small, host, pipeline):
     W, H = 160, 96
     cam = _cam_for(castle_small, host, W, H, eye_dir=(0.7, 0.5, 0.9))
     sky = host.sunlight_bake()
-    g = castle_small.loaded.scene.trace(cam, sky, W, H, spp=2, max_bounces=2, seed=11, hits=True, stats=True)
+    g = castle_small.loaded.scene.trace(cam, sky, W, H, spp=2, max_bounces=2, seed=11, hits=True, stats=True, pipeline=pipeline)
     o = castle_small.oscene.render(cam, sky, W, H, spp=2, max_bounces=2, seed=11)
     _assert_hits_equal(g, o)
     _assert_radiance_close(g, o)
@@ -129,8 +134,24 @@ def test_fp16_output_and_device_buffers(teapot, host, ctx):
     assert np.array_equal(dev.cpu().numpy(), ref)
 
 
+def test_wavefront_sample_batches_equal_megakernel(castle_small, host, monkeypatch):
+    """The wavefront pipeline splits the samples of a frame into batches when the path state would not
+    fit its budget; pixel sums must still be accumulated in sample order: bit-identical frames."""
+    W, H = 200, 120                                   # ragged tiles: 7 x 4 tiles of 32x32
+    cam = _cam_for(castle_small, host, W, H, eye_dir=(0.6, 0.8, 0.7))
+    sky = host.sunlight_bake()
+    kw = dict(spp=5, max_bounces=2, seed=13, frame_index=2)
+    mega = castle_small.loaded.scene.trace(cam, sky, W, H, pipeline="megakernel", **kw)["radiance"]
+    one = castle_small.loaded.scene.trace(cam, sky, W, H, pipeline="wavefront", **kw)["radiance"]
+    monkeypatch.setenv("DUST_WF_MAX_PATHS", str(28 * 1024 * 2))      # 2 samples per batch -> batches of 2, 2, 1
+    many = castle_small.loaded.scene.trace(cam, sky, W, H, pipeline="wavefront", **kw)["radiance"]
+    assert np.array_equal(one, mega)
+    assert np.array_equal(many, mega)
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
 @pytest.mark.parametrize("shards", [2, 3, 8])
-def test_sharded_frame_equals_whole_frame(castle_small, host, ctx, shards):
+def test_sharded_frame_equals_whole_frame(castle_small, host, ctx, shards, pipeline):
     """Tile-sharded render + resolve == single-GPU frame, bit for bit (ragged 200x120 frame)."""
     import torch
     from dust_b200.pipeline import resolve_shards, shard_layout
@@ -142,7 +163,7 @@ def test_sharded_frame_equals_whole_frame(castle_small, host, ctx, shards):
     gathered = torch.zeros((shards, per, 4), dtype=torch.float32, device="cuda")
     for s in range(shards):
         castle_small.loaded.scene.trace_device(cam, sky, W, H, gathered[s], spp=2, max_bounces=1, seed=5,
-                                               shard_index=s, shard_count=shards)
+                                               shard_index=s, shard_count=shards, pipeline=pipeline)
     out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     resolve_shards(ctx, W, H, shards, gathered, out)
     ctx.synchronize()
