@@ -16,6 +16,9 @@
 //       4^3 node  : 1 word, base = slot of its first leaf               = 16 B    (was 264 B)
 //       leaf      : 1 word, mask = occupancy, base = material_ptr       = 16 B    (was 24 B)
 //
+//   * per 16^3 node one extra 64-bit BLOCK mask (bit per 4x4x4 block of children): the walk asks it first
+//     and leaves an empty block as one cell of 4x the edge (64 voxels under a 256^3 root).
+//
 // Everything a ray touches above the leaves of a 256^3 model is ~100 KB and stays in L1/L2.
 #pragma once
 #include <stdint.h>
@@ -38,7 +41,7 @@ struct alignas(16) DInstance {
     const uint4 *leaves;
     const uint8_t *materials;
     const float4 *palette_lin;     // 256 x SRGBToLinear(rgb/255), w unused
-    uint64_t _pad0;
+    const uint2 *blocks;           // per 16^3 node: 64-bit block mask, bit bx<<4|by<<2|bz = "some child in that 4x4x4 block of children"
     float o2w[9];                  // linear part of object -> world (normals)
     uint32_t _pad1[3];
 };

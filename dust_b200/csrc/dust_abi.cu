@@ -1,7 +1,6 @@
 // C ABI of libdust_b200.so (include/dust_b200.h): context, one-time tree re-layout + upload,
 // instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
 // launches sm_100a kernels or fails.
-#include "sched.cuh"
 #include "wavefront.cuh"
 
 #include <cstdlib>
@@ -25,13 +24,11 @@ struct DustCtx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     DCounters *d_counters = nullptr;
-    unsigned long long *d_work = nullptr;   // work-item counter of the persistent kernels
     // wavefront pipeline: path state + ray queues (grown on demand), queue / bin counters (fixed size)
     void *wf_scratch = nullptr;
     size_t wf_scratch_bytes = 0;
     uint32_t *d_wf_counters = nullptr;
     int sms = 148;
-    int kernel_variant = 2;           // 2 = one thread per sample / ray (default); 3 = persistent fully operation-scheduled lanes (DUST_KERNEL=v3, A/B only)
     DustStats stats{};
 };
 
@@ -40,6 +37,7 @@ struct DustTree {
     void *blob = nullptr;            // one device allocation
     size_t blob_bytes = 0;
     const DNode16 *n16 = nullptr;
+    const uint2 *blocks = nullptr;
     const uint4 *mids = nullptr;
     const uint4 *leaves = nullptr;
     const uint8_t *materials = nullptr;
@@ -301,8 +299,8 @@ int32_t fetch_counters(DustCtx *ctx)
 // ---- wavefront pipeline (wavefront.cuh) ---------------------------------------------------------
 
 constexpr uint32_t kWfMaxDepths = 65;                                  // max_bounces <= 64
-// per depth: 4 queue counters, 2 x WF_BINS bin totals / cursors, 2 overflow counters, 2 x 64-bit work counters
-constexpr size_t kWfCounterWords = (size_t)kWfMaxDepths * (4 + 2 * WF_BINS + 2 + 4);
+// per depth: 4 queue counters, 2 overflow counters, 2 x 64-bit work counters
+constexpr size_t kWfCounterWords = (size_t)kWfMaxDepths * (4 + 2 + 4);
 
 int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_shard, int nl, bool stats)
 {
@@ -315,13 +313,13 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     const uint64_t n_paths = (uint64_t)n_slots * batch_spp;
     if (n_paths >= (1ull << 31)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "frame too large for one wavefront batch");
 
-    // carve the scratch: [ps0 ps1 ps2 | qc qs qg (a, b, path) | hits | acc | vis | bin]
+    // carve the scratch: [ps0 ps1 ps2 | 3 queues (a, b, path) | hits | acc | vis | cand | overflow]
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_ps0 = take(n_paths * 16), o_ps1 = take(n_paths * 16), o_ps2 = take(n_paths * 16);
     size_t o_q[3][3];
     for (int q = 0; q < 3; q++) { o_q[q][0] = take(n_paths * 16); o_q[q][1] = take(n_paths * 16); o_q[q][2] = take(n_paths * 4); }
-    const size_t o_hits = take(n_paths * 16), o_acc = take((size_t)n_slots * 16), o_vis = take(n_paths), o_bin = take(n_paths);
+    const size_t o_hits = take(n_paths * 16), o_acc = take((size_t)n_slots * 16), o_vis = take(n_paths);
     const size_t o_cand = take(n_paths * 32), o_ovf = take(n_paths * 4);
     if (off > ctx->wf_scratch_bytes) {
         if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
@@ -336,16 +334,17 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     p.f = fp;
     p.n_slots = n_slots;
     p.ps0 = reinterpret_cast<float4 *>(base + o_ps0); p.ps1 = reinterpret_cast<float4 *>(base + o_ps1); p.ps2 = reinterpret_cast<float4 *>(base + o_ps2);
-    WfQueue *qs[3] = { &p.qc, &p.qs, &p.qg };
+    WfQueue *qs[3] = { &p.qc, &p.qs, &p.qn };
     for (int q = 0; q < 3; q++) {
         qs[q]->a = reinterpret_cast<float4 *>(base + o_q[q][0]); qs[q]->b = reinterpret_cast<float4 *>(base + o_q[q][1]);
         qs[q]->path = reinterpret_cast<uint32_t *>(base + o_q[q][2]);
     }
+    const WfQueue q_even = p.qc, q_odd = p.qn;                         // closest queues of even / odd depths
     p.hits = reinterpret_cast<uint4 *>(base + o_hits); p.acc = reinterpret_cast<float4 *>(base + o_acc);
-    p.vis = base + o_vis; p.bin = base + o_bin;
+    p.vis = base + o_vis;
     p.cand = reinterpret_cast<uint4 *>(base + o_cand); p.overflow = reinterpret_cast<uint32_t *>(base + o_ovf);
-    p.counts = ctx->d_wf_counters; p.bins = ctx->d_wf_counters + 4 * kWfMaxDepths;
-    uint32_t *ovf_counts = p.bins + 2 * WF_BINS * kWfMaxDepths;                                  // [2 * depth + (shadow ? 1 : 0)]
+    p.counts = ctx->d_wf_counters;
+    uint32_t *ovf_counts = p.counts + 4 * kWfMaxDepths;                                          // [2 * depth + (shadow ? 1 : 0)]
     unsigned long long *work = reinterpret_cast<unsigned long long *>(ovf_counts + 2 * kWfMaxDepths);   // 8-byte aligned: all counts above are even
     // queues of incoherent rays (bounce rays and the shadow rays behind them) are pre-culled and traced by persistent lanes
     uint32_t pt_depth = 1;
@@ -382,20 +381,18 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         p.last_batch = first + p.batch_spp >= cfg.spp;
         const uint32_t grid128 = (p.n_paths + DUST_THREADS - 1) / DUST_THREADS, grid256 = (p.n_paths + 255) / 256;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_wf_counters, 0, kWfCounterWords * sizeof(uint32_t), ctx->stream));
+        p.qc = q_even; p.qn = q_odd;
         wf_gen_primary<<<grid256, 256, 0, ctx->stream>>>(p);
         count_launch(ctx);
         for (uint32_t depth = 0; depth <= cfg.max_bounces; depth++) {
             p.depth = depth;
+            p.qc = depth & 1 ? q_odd : q_even; p.qn = depth & 1 ? q_even : q_odd;
             // queue sizes live on the device: launch for the largest possible queue, surplus CTAs exit at once
             const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : p.counts + 3;
             if (depth >= pt_depth) trace_pt(p.qc, n_closest, 2 * depth, grid128); else trace(p.qc, n_closest, nullptr, grid128);
             if (stats) wf_shade<true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_shade<false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p);
             count_launch(ctx);
             if (depth >= pt_depth) trace_pt(p.qs, p.counts + 4 * depth + 1, 2 * depth + 1, grid128); else trace(p.qs, p.counts + 4 * depth + 1, nullptr, grid128);
-            if (depth < cfg.max_bounces) {
-                wf_scatter<<<(p.n_paths + WF_SCATTER_CHUNK - 1) / WF_SCATTER_CHUNK, WF_SCATTER_THREADS, 0, ctx->stream>>>(p);
-                count_launch(ctx);
-            }
         }
         wf_resolve<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(p);
         count_launch(ctx);
@@ -422,13 +419,11 @@ int32_t dust_ctx_create(int32_t device, DustCtx **out)
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_work, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_counters, sizeof(DCounters)) != cudaSuccess) {
         delete ctx;
         return DUST_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
-    if (const char *k = std::getenv("DUST_KERNEL")) ctx->kernel_variant = (k[0] == 'v' && k[1] == '3') ? 3 : 2;   // A/B only
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return DUST_OK;
@@ -441,7 +436,6 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
     if (ctx->d_wf_counters) cudaFree(ctx->d_wf_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -489,9 +483,22 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
         pal[i] = make_float4(srgb_to_linear((float)c[0] / 255.0f), srgb_to_linear((float)c[1] / 255.0f), srgb_to_linear((float)c[2] / 255.0f), 0.0f);
     }
 
-    // one allocation: [n16 | mids | leaves | palette_lin | materials], each 256-byte aligned
+    // block masks: bit bx<<4|by<<2|bz of node n = "some child bit set in the 4x4x4 block (bx,by,bz) of its 16^3 children"
+    std::vector<uint2> blocks(r.n16.size());
+    for (size_t n = 0; n < r.n16.size(); n++) {
+        uint64_t bm = 0;
+        for (uint32_t w = 0; w < 64; w++) {                           // word w holds children x = w >> 2, y = 4 * (w & 3) + (bit >> 4), z = bit & 15
+            const uint64_t m = ((uint64_t)r.n16[n].word[w].y << 32) | r.n16[n].word[w].x;
+            for (uint32_t bz = 0; bz < 4; bz++)
+                if (m & (0x000F000F000F000Full << (4 * bz))) bm |= 1ull << (((w >> 4) << 4) | ((w & 3) << 2) | bz);
+        }
+        blocks[n] = make_uint2((uint32_t)bm, (uint32_t)(bm >> 32));
+    }
+
+    // one allocation: [n16 | blocks | mids | leaves | palette_lin | materials], each 256-byte aligned
     const size_t off_n16 = 0;
-    const size_t off_mids = align_up(off_n16 + r.n16.size() * sizeof(DNode16), 256);
+    const size_t off_blocks = align_up(off_n16 + r.n16.size() * sizeof(DNode16), 256);
+    const size_t off_mids = align_up(off_blocks + blocks.size() * sizeof(uint2), 256);
     const size_t off_leaves = align_up(off_mids + r.mids.size() * sizeof(uint4), 256);
     const size_t off_pal = align_up(off_leaves + r.leaves.size() * sizeof(uint4), 256);
     const size_t off_mat = align_up(off_pal + sizeof pal, 256);
@@ -507,6 +514,7 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
         return bytes ? cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
     };
     e = put(off_n16, r.n16.data(), r.n16.size() * sizeof(DNode16));
+    if (e == cudaSuccess) e = put(off_blocks, blocks.data(), blocks.size() * sizeof(uint2));
     if (e == cudaSuccess) e = put(off_mids, r.mids.data(), r.mids.size() * sizeof(uint4));
     if (e == cudaSuccess) e = put(off_leaves, r.leaves.data(), r.leaves.size() * sizeof(uint4));
     if (e == cudaSuccess) e = put(off_pal, pal, sizeof pal);
@@ -516,6 +524,7 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     t->n_levels = desc->n_levels;
     t->blob_bytes = total;
     t->n16 = reinterpret_cast<const DNode16 *>(base + off_n16);
+    t->blocks = reinterpret_cast<const uint2 *>(base + off_blocks);
     t->mids = reinterpret_cast<const uint4 *>(base + off_mids);
     t->leaves = reinterpret_cast<const uint4 *>(base + off_leaves);
     t->palette_lin = reinterpret_cast<const float4 *>(base + off_pal);
@@ -566,10 +575,10 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         world2obj(m, d.w2o);
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
         d.n_levels = t->n_levels;
-        d.n16 = t->n16; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin;
+        d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin;
         // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
         for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
-        d._pad0 = 0; d._pad1[0] = d._pad1[1] = d._pad1[2] = 0;
+        d._pad1[0] = d._pad1[1] = d._pad1[2] = 0;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove
@@ -735,24 +744,6 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     if (wavefront) {
         const int32_t rc = trace_wavefront(ctx, p, tiles_per_shard, nl, stats);
         if (rc != DUST_OK) return rc;
-    } else if (ctx->kernel_variant == 3) {
-        // persistent lanes: one resident wave of CTAs, pixels claimed from a global counter
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
-        const uint32_t n_items = tiles_per_shard * 1024u;
-        cudaError_t le = cudaSuccess;
-        auto launch = [&](auto kernel) {
-            int per_sm = 0;
-            le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
-            if (le != cudaSuccess) return;
-            const uint32_t want = (n_items + DUST_THREADS - 1) / DUST_THREADS;
-            const uint32_t pgrid = std::min<uint32_t>(want, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
-            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, ctx->d_work, n_items);
-        };
-        if (nl == 3) { if (stats) launch(frame_kernel_pt<3, true>); else launch(frame_kernel_pt<3, false>); }
-        else if (nl == 4) { if (stats) launch(frame_kernel_pt<4, true>); else launch(frame_kernel_pt<4, false>); }
-        else { if (stats) launch(frame_kernel_pt<0, true>); else launch(frame_kernel_pt<0, false>); }
-        CU_TRY(ctx, le);
-        count_launch(ctx);
     } else {
         auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
         if (nl == 3) { if (stats) launch(frame_kernel<3, true>); else launch(frame_kernel<3, false>); }
@@ -806,21 +797,7 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     const uint64_t want = (n + DUST_THREADS - 1) / DUST_THREADS;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 64u);
     const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
-    if (ctx->kernel_variant == 3) {
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
-        cudaError_t le = cudaSuccess;
-        auto launch = [&](auto kernel) {
-            int per_sm = 0;
-            le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
-            if (le != cudaSuccess) return;
-            const uint32_t pgrid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * std::max(per_sm, 1));
-            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, ctx->d_work);
-        };
-        if (nl == 3) { if (stats) launch(rays_kernel_pt<3, true>); else launch(rays_kernel_pt<3, false>); }
-        else if (nl == 4) { if (stats) launch(rays_kernel_pt<4, true>); else launch(rays_kernel_pt<4, false>); }
-        else { if (stats) launch(rays_kernel_pt<0, true>); else launch(rays_kernel_pt<0, false>); }
-        CU_TRY(ctx, le);
-    } else {
+    {
         auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
         if (nl == 3) { if (stats) launch(rays_kernel<3, true>); else launch(rays_kernel<3, false>); }
         else if (nl == 4) { if (stats) launch(rays_kernel<4, true>); else launch(rays_kernel<4, false>); }

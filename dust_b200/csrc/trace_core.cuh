@@ -75,9 +75,230 @@ __device__ __forceinline__ float box_entry(float lx, float ly, float lz, float h
     return t0 <= t1 ? t0 : CUDART_INF_F;
 }
 
+// 1/d for the box tests only: a zero component gets a huge FINITE inverse so (lo - o) * inv is never 0 * inf
+__device__ __forceinline__ f3 cull_inverse(f3 rd)
+{
+    return mk3(fabsf(rd.x) < 1e-30f ? copysignf(1e30f, rd.x) : 1.0f / rd.x,
+               fabsf(rd.y) < 1e-30f ? copysignf(1e30f, rd.y) : 1.0f / rd.y,
+               fabsf(rd.z) < 1e-30f ? copysignf(1e30f, rd.z) : 1.0f / rd.z);
+}
+
+// ---------------------------------------------------------------------------------------- the cull
+// Candidates = instances whose padded box the ray touches, kept sorted by a 32-bit key
+// (entry t truncated downwards | instance) in this lane's shared-memory column sm[0 .. nc); the BVH
+// stack grows down from the top of the same column, sm[sp .. WORDS).  The result of a ray does not
+// depend on the visiting order (lexicographic min of (t, instance)), only the pruning does.
+
+__device__ __forceinline__ uint32_t cand_key(float te, uint32_t instance, uint32_t id_mask)
+{
+    return (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | instance;
+}
+
+// start a ray: scene box test; returns false when the ray misses the whole scene
+__device__ __forceinline__ bool cull_begin(const DSceneView &sc, f3 ro, f3 winv, float tmin, float tmax, uint32_t id_mask,
+                                           uint32_t *sm, int &sp, int &pend, int &nc)
+{
+    sp = DUST_SCRATCH_WORDS; pend = -1; nc = 0;
+    if (!sc.n_inst) return false;
+    const float te = box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], ro, winv, tmin, tmax);
+    if (te == CUDART_INF_F) return false;
+    if (sc.root_ref >= 0) pend = sc.root_ref;
+    else { sm[0] = cand_key(te, (uint32_t)~sc.root_ref, id_mask); nc = 1; }
+    return true;
+}
+
+// room for one more expansion (2 candidates + 1 stack entry)?
+__device__ __forceinline__ bool cull_room(int sp, int nc) { return nc + 3 <= sp; }
+
+// expand BVH node `pend` (both children: one 64-byte node); instances go to the candidate list, inner
+// nodes to `pend` / the stack
+template <bool STATS>
+__device__ __forceinline__ void cull_expand(const DSceneView &sc, f3 ro, f3 winv, float tmin, float tmax, uint32_t id_mask,
+                                            uint32_t *sm, int &sp, int &pend, int &nc, Counters &st)
+{
+    const float4 *n = reinterpret_cast<const float4 *>(sc.bvh + pend);
+    const float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), e = __ldg(n + 3);
+    if (STATS) st.dbg[13]++;
+    float t0 = box_entry(a.x, a.y, a.z, b.x, b.y, b.z, ro, winv, tmin, tmax);
+    float t1 = box_entry(c.x, c.y, c.z, e.x, e.y, e.z, ro, winv, tmin, tmax);
+    int c0 = __float_as_int(a.w), c1 = __float_as_int(b.w);
+    if (t1 < t0) { const float tf = t0; t0 = t1; t1 = tf; const int ci = c0; c0 = c1; c1 = ci; }
+    int next = -1;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const float te = s ? t1 : t0;
+        const int ch = s ? c1 : c0;
+        if (te == CUDART_INF_F) continue;
+        if (ch >= 0) {
+            if (next < 0) next = ch; else sm[--sp * DUST_THREADS] = (uint32_t)ch;
+        } else {                                                      // instance: insertion sort by key
+            const uint32_t key = cand_key(te, (uint32_t)~ch, id_mask);
+            int k = nc++;
+            if (STATS) st.dbg[14]++;
+            while (k > 0) {
+                const uint32_t prev = sm[(k - 1) * DUST_THREADS];
+                if (prev <= key) break;
+                sm[k * DUST_THREADS] = prev; --k;
+            }
+            sm[k * DUST_THREADS] = key;
+        }
+    }
+    if (next < 0 && sp < DUST_SCRATCH_WORDS) next = (int)sm[sp++ * DUST_THREADS];
+    pend = next;
+}
+
+// ------------------------------------------------------------------------------- the instance walk
+// State of one ray inside one instance.  Coordinates are in LEAF units (voxel >> 2): no consumer reads
+// the low two bits (floor / clamp commute with the monotone shift).
+
+struct Walk {
+    f3 o, d, inv;                    // object-space ray, exact 1/d
+    int jx, jy, jz;                  // current cell
+    int L4;                          // != 0: the cell of that edge (leaf units) containing (jx,jy,jz) is empty / done: leave it first
+    float t_exit;
+    uint32_t bnd0, bnd1, bnd2;       // occupied bounds per axis: lo | size << 16
+    const DNode16 *n16;
+    const uint2 *blocks;
+    const uint4 *mids, *leaves;
+    uint32_t blk_lo, blk_hi;         // block mask of the 16^3 node above the mids (kept in registers for 3-level trees)
+    uint32_t mid_lo, mid_hi, mid_base;
+    uint32_t inst, leaf_i;
+    bool have_mid;                   // the 4^3 node of the current 16-cell is in registers
+    bool four;                       // this instance has 4 levels
+};
+
+enum : int { WS_WALK = 0, WS_LEAF = 1, WS_OUT = 2 };
+
+// Enter instance `inst`: world -> object ray (hit.rint:140-141), reciprocals, clip against the occupied
+// bounds.  Returns false when the ray does not reach the instance within [tmin, cur].
+template <int NL, bool STATS>
+__device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32_t inst, f3 ro, f3 rd, float tmin, float cur, Counters &st)
+{
+    w.inst = inst;
+    if (STATS) st.dbg[12]++;
+    const DInstance &in = sc.inst[inst];
+    object_ray(in, ro, rd, w.o, w.d);
+    w.inv = mk3(1.0f / w.d.x, 1.0f / w.d.y, 1.0f / w.d.z);
+    const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(in.bounds));
+    w.bnd0 = bw.x; w.bnd1 = bw.y; w.bnd2 = bw.z;
+    const int bx0 = (int)(bw.x & 0xFFFFu) << 2, by0 = (int)(bw.y & 0xFFFFu) << 2, bz0 = (int)(bw.z & 0xFFFFu) << 2;
+    const int bx1 = bx0 + ((int)(bw.x >> 16) << 2), by1 = by0 + ((int)(bw.y >> 16) << 2), bz1 = bz0 + ((int)(bw.z >> 16) << 2);
+    // plane times are (plane - o) * inv: difference first, plane*inv - o*inv would cancel (|o/d| >> t)
+    const float t0x = ((float)bx0 - w.o.x) * w.inv.x, t0y = ((float)by0 - w.o.y) * w.inv.y, t0z = ((float)bz0 - w.o.z) * w.inv.z;
+    const float t1x = ((float)bx1 - w.o.x) * w.inv.x, t1y = ((float)by1 - w.o.y) * w.inv.y, t1z = ((float)bz1 - w.o.z) * w.inv.z;
+    const float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+    // walk a hair past tmax (acceptance stays exact): DESIGN.md "Traversal semantics"
+    const float tmax_pad = cur + (fabsf(cur) * 3.814697265625e-06f + 9.5367431640625e-07f);
+    w.t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
+    if (!(t_enter <= w.t_exit) || bx1 <= bx0) return false;
+    const int ix = __float2int_rd(__fmaf_rn(w.d.x, t_enter, w.o.x));
+    const int iy = __float2int_rd(__fmaf_rn(w.d.y, t_enter, w.o.y));
+    const int iz = __float2int_rd(__fmaf_rn(w.d.z, t_enter, w.o.z));
+    w.jx = min(max(ix, bx0), bx1 - 1) >> 2; w.jy = min(max(iy, by0), by1 - 1) >> 2; w.jz = min(max(iz, bz0), bz1 - 1) >> 2;
+    const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(&in.n16));
+    w.n16 = reinterpret_cast<const DNode16 *>(p01.x);
+    w.mids = reinterpret_cast<const uint4 *>(p01.y);
+    w.leaves = in.leaves;
+    w.blocks = in.blocks;
+    if (NL == 0) w.four = bw.w == 4u;
+    if (NL == 3 || (NL == 0 && !w.four)) { const uint2 b = __ldg(w.blocks); w.blk_lo = b.x; w.blk_hi = b.y; }
+    w.have_mid = false;
+    w.L4 = 0;
+    return true;
+}
+
+// One step of the walk: leave the cell marked by L4 (if any), then descend to the cell that now
+// contains (jx,jy,jz) with the InternalNode::get index arithmetic (crates/vdb/src/node/internal.rs:77-95)
+// on the re-laid-out nodes.  Every 16^3 node is first asked per 4x4x4 BLOCK of children ("is anything
+// in this block": one bit of a 64-bit block mask) — an empty block is left as one cell of 4x the edge.
+template <int NL, bool STATS>
+__device__ __forceinline__ int walk_step(Walk &w, Counters &st)
+{
+    if (w.L4) {
+        const int L4 = w.L4;
+        if (STATS) st.dbg[L4 == 1 ? 7 : (L4 == 4 ? 8 : 9)]++;
+        // leave the cell of edge L4 that contains (jx,jy,jz): DESIGN.md "Traversal semantics", "t_next"
+        const int cx = w.jx & ~(L4 - 1), cy = w.jy & ~(L4 - 1), cz = w.jz & ~(L4 - 1);
+        const bool px_ = w.d.x > 0.0f, py_ = w.d.y > 0.0f, pz_ = w.d.z > 0.0f;
+        const float tx = ((float)((px_ ? cx + L4 : cx) << 2) - w.o.x) * w.inv.x;
+        const float ty = ((float)((py_ ? cy + L4 : cy) << 2) - w.o.y) * w.inv.y;
+        const float tz = ((float)((pz_ ? cz + L4 : cz) << 2) - w.o.z) * w.inv.z;
+        const float t_next = fminf(fminf(tx, ty), tz);
+        bool out = !(t_next <= w.t_exit);                             // inclusive
+        int nx = w.jx, ny = w.jy, nz = w.jz;
+        // axes whose plane time ties the minimum step one cell; the others are re-derived from the ray at
+        // t_next and clamped into the cell's own range — a no-op at leaf granularity when L4 == 1
+        if (tx <= t_next) { nx = px_ ? cx + L4 : cx - 1; out |= (uint32_t)(nx - (int)(w.bnd0 & 0xFFFFu)) >= (w.bnd0 >> 16); }
+        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.x, t_next, w.o.x)) >> 2; nx = min(max(ip, cx), cx + L4 - 1); }
+        if (ty <= t_next) { ny = py_ ? cy + L4 : cy - 1; out |= (uint32_t)(ny - (int)(w.bnd1 & 0xFFFFu)) >= (w.bnd1 >> 16); }
+        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.y, t_next, w.o.y)) >> 2; ny = min(max(ip, cy), cy + L4 - 1); }
+        if (tz <= t_next) { nz = pz_ ? cz + L4 : cz - 1; out |= (uint32_t)(nz - (int)(w.bnd2 & 0xFFFFu)) >= (w.bnd2 >> 16); }
+        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.z, t_next, w.o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
+        // the cached 4^3 node survives a step that stays inside its 16-cell
+        w.have_mid = w.have_mid && (((uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz)) >> 2) == 0u);
+        w.jx = nx; w.jy = ny; w.jz = nz;
+        w.L4 = 0;
+        if (out) return WS_OUT;
+    }
+    const int jx = w.jx, jy = w.jy, jz = w.jz;
+    const bool four = NL == 4 || (NL == 0 && w.four);
+    if (!w.have_mid) {
+        const DNode16 *node = w.n16;
+        uint32_t blo = w.blk_lo, bhi = w.blk_hi;
+        if (four) {
+            const uint2 tb = __ldg(w.blocks);
+            if (STATS) st.mask_words++;
+            if (!bit64(tb.x, tb.y, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
+            const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
+            const uint4 q = __ldg(&node->word[tidx >> 6]);
+            if (STATS) st.mask_words++;
+            const uint32_t b = tidx & 63u;
+            if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
+            if (STATS) st.child_ptrs++;
+            const uint32_t ni = q.z + rank64(q.x, q.y, b);
+            node = w.n16 + ni;
+            const uint2 cb = __ldg(w.blocks + ni);
+            blo = cb.x; bhi = cb.y;
+        }
+        if (STATS) st.mask_words++;
+        if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
+        const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
+        if (STATS) st.mask_words++;
+        const uint4 q = __ldg(&node->word[ridx >> 6]);
+        const uint32_t b = ridx & 63u;
+        if (!bit64(q.x, q.y, b)) { w.L4 = 4; return WS_WALK; }
+        const uint4 mid = __ldg(&w.mids[q.z + rank64(q.x, q.y, b)]);
+        w.mid_lo = mid.x; w.mid_hi = mid.y; w.mid_base = mid.z;
+        w.have_mid = true;
+    } else if (STATS) {
+        if (four) { st.mask_words += 2; st.child_ptrs++; }
+        st.mask_words += 2;
+    }
+    if (STATS) { st.child_ptrs++; st.mask_words++; }
+    const uint32_t midx = ((uint32_t)(jx & 3) << 4) | ((uint32_t)(jy & 3) << 2) | (uint32_t)(jz & 3);
+    if (!bit64(w.mid_lo, w.mid_hi, midx)) { w.L4 = 1; return WS_WALK; }
+    if (STATS) { st.child_ptrs++; st.mask_words++; }
+    w.leaf_i = w.mid_base + rank64(w.mid_lo, w.mid_hi, midx);
+    return WS_LEAF;
+}
+
+// Leaf step on leaf w.leaf_i: one 128-bit load (occupancy + material_ptr), then hit.rint's DDA.  Returns
+// true with (t, voxel) when a voxel is reached; the caller applies reportIntersectionEXT's [tmin, tmax].
+template <bool STATS>
+__device__ __forceinline__ bool walk_leaf(const Walk &w, float tmin, float &th, uint32_t &vox, Counters &st)
+{
+    const uint4 leaf = __ldg(&w.leaves[w.leaf_i]);
+    if (STATS) st.dbg[10]++;
+    const f3 lo = mk3(w.o.x - (float)(w.jx << 2), w.o.y - (float)(w.jy << 2), w.o.z - (float)(w.jz << 2));   // hit.rint:140
+    return leaf_dda_inv<STATS>(lo, w.d, w.inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]);
+}
+
+__device__ __forceinline__ uint32_t walk_pos(const Walk &w) { return (uint32_t)w.jx | ((uint32_t)w.jy << 10) | ((uint32_t)w.jz << 20); }
+
+// ----------------------------------------------------------------------------------- one ray, one warp
 // Closest hit = lexicographic minimum of (t, instance) over all instances; `any`: the first accepted
 // hit ends the ray (gl_RayFlagsTerminateOnFirstHitEXT).  The BVH only culls (boxes are padded, see
-// dust_scene_create), so the result equals the oracle's linear instance loop.
+// dust_scene_create), so the result equals the CPU checker's linear instance loop.
 // All 32 lanes of the warp must call this together; lanes without a ray pass live = false.
 // NL = 3 / 4: every instance has that many levels; NL = 0: mixed scene, decided per instance.
 // `sm` = this lane's column of the block's scratch: word k lives at sm[k * DUST_THREADS].
@@ -90,182 +311,51 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     float cur = tmax;                                                 // current tmax: shrinks to the best hit
     const uint32_t id_mask = (1u << sc.id_bits) - 1u;
     if (STATS && (threadIdx.x & 31u) == 0) st.dbg[15]++;
+    const f3 winv = cull_inverse(rd);
+    int sp = DUST_SCRATCH_WORDS, pend = -1, nc = 0;
+    if (live) cull_begin(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc);
 
-    // ---- ray set-up for the cull: a zero component gets a huge FINITE inverse so (lo - o) * inv is never 0 * inf
-    const f3 winv = mk3(fabsf(rd.x) < 1e-30f ? copysignf(1e30f, rd.x) : 1.0f / rd.x,
-                        fabsf(rd.y) < 1e-30f ? copysignf(1e30f, rd.y) : 1.0f / rd.y,
-                        fabsf(rd.z) < 1e-30f ? copysignf(1e30f, rd.z) : 1.0f / rd.z);
-    int sp = DUST_SCRATCH_WORDS;                                      // stack = sm[sp .. WORDS)
-    int pend = -1;                                                    // inner BVH node waiting to be expanded
-    int nc = 0;                                                       // candidates = sm[0 .. nc)
-    if (live && sc.n_inst) {
-        const float te = box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], ro, winv, tmin, cur);
-        if (te != CUDART_INF_F) {
-            if (sc.root_ref >= 0) pend = sc.root_ref;
-            else { sm[0] = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~sc.root_ref; nc = 1; }
-        }
-    }
-
-    // per-instance walk state
-    int mode, j;
-    uint32_t inst = 0, leaf_i = 0;
-    f3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(1.0f, 1.0f, 1.0f), inv = mk3(1.0f, 1.0f, 1.0f);
-    int jx = 0, jy = 0, jz = 0;                                       // current cell, leaf units (voxel >> 2)
-    int L4 = 0;                                                       // != 0: leave the cell of that edge (leaf units) first
-    float t_exit = 0.0f;
-    uint32_t bnd0 = 0, bnd1 = 0, bnd2 = 0;
-    const DNode16 *n16 = nullptr;
-    const uint4 *mids = nullptr, *leaves = nullptr;
-    uint32_t mid_lo = 0, mid_hi = 0, mid_base = 0;
-    bool have_mid = false;                                            // the 4^3 node of the current 16-cell is in registers
-    bool four = NL == 4;
-
+    Walk w;
+    w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
     for (;;) {
-        // ------------------------------------------------------------------ phase 1: cull
-        // Collect the instances whose padded box the ray touches, sorted by (entry t, instance).  The
-        // result does not depend on the visiting order (lexicographic min of (t, instance)), only the pruning does.
-        while (pend >= 0 && nc + 3 <= sp) {
-            const float4 *n = reinterpret_cast<const float4 *>(sc.bvh + pend);
-            const float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), e = __ldg(n + 3);
-            if (STATS) st.dbg[13]++;
-            float t0 = box_entry(a.x, a.y, a.z, b.x, b.y, b.z, ro, winv, tmin, cur);
-            float t1 = box_entry(c.x, c.y, c.z, e.x, e.y, e.z, ro, winv, tmin, cur);
-            int c0 = __float_as_int(a.w), c1 = __float_as_int(b.w);
-            if (t1 < t0) { const float tf = t0; t0 = t1; t1 = tf; const int ci = c0; c0 = c1; c1 = ci; }
-            int next = -1;
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const float te = s ? t1 : t0;
-                const int ch = s ? c1 : c0;
-                if (te == CUDART_INF_F) continue;
-                if (ch >= 0) {
-                    if (next < 0) next = ch; else sm[--sp * DUST_THREADS] = (uint32_t)ch;
-                } else {                                              // instance: insertion sort by key
-                    const uint32_t key = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~ch;
-                    int k = nc++;
-                    if (STATS) st.dbg[14]++;
-                    while (k > 0) {
-                        const uint32_t prev = sm[(k - 1) * DUST_THREADS];
-                        if (prev <= key) break;
-                        sm[k * DUST_THREADS] = prev; --k;
-                    }
-                    sm[k * DUST_THREADS] = key;
-                }
-            }
-            if (next < 0 && sp < DUST_SCRATCH_WORDS) next = (int)sm[sp++ * DUST_THREADS];
-            pend = next;
-        }
+        // ---- phase 1: cull
+        while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc, st);
 
-        // ------------------------------------------------------------------ phase 2: walk
-        mode = nc > 0 ? M_NEXT : M_DONE;
-        j = 0;
+        // ---- phase 2: walk.  NEXT: enter the next candidate; WALK: one cell; LEAF: the 4x4x4 DDA.  Each trip
+        // the warp votes and executes the ONE operation most lanes wait for (ties to the cheaper one).
+        int mode = nc > 0 ? M_NEXT : M_DONE, j = 0;
         for (;;) {
             const unsigned m_next = __ballot_sync(full, mode == M_NEXT);
             const unsigned m_walk = __ballot_sync(full, mode == M_WALK);
             const unsigned m_leaf = __ballot_sync(full, mode == M_LEAF);
             if ((m_next | m_walk | m_leaf) == 0) break;
-            // the operation most lanes wait for; ties go to the cheaper one (it feeds the dearer one)
             const int n_next = __popc(m_next), n_walk = __popc(m_walk), n_leaf = __popc(m_leaf);
             int op = M_WALK, cnt = n_walk;
             if (n_next > cnt) { op = M_NEXT; cnt = n_next; }
-            if (n_leaf > cnt) { op = M_LEAF; }
+            if (n_leaf > cnt) { op = M_LEAF; cnt = n_leaf; }
             if (STATS && (threadIdx.x & 31u) == 0) {
                 st.dbg[op == M_WALK ? 0 : (op == M_LEAF ? 1 : 2)]++;
-                st.dbg[op == M_WALK ? 3 : (op == M_LEAF ? 4 : 5)] += op == M_WALK ? n_walk : (op == M_LEAF ? n_leaf : n_next);
+                st.dbg[op == M_WALK ? 3 : (op == M_LEAF ? 4 : 5)] += cnt;
                 st.dbg[6] += 32 - n_walk - n_leaf - n_next;
             }
-
             if (op == M_WALK) {
                 if (mode == M_WALK) {
-                    if (L4) {
-                        if (STATS) st.dbg[L4 == 1 ? 7 : (L4 == 4 ? 8 : 9)]++;
-                        // leave the cell of edge L4 that contains (jx,jy,jz): oracle trace_instance, "t_next"
-                        const int cx = jx & ~(L4 - 1), cy = jy & ~(L4 - 1), cz = jz & ~(L4 - 1);
-                        const bool px_ = d.x > 0.0f, py_ = d.y > 0.0f, pz_ = d.z > 0.0f;
-                        const float tx = ((float)((px_ ? cx + L4 : cx) << 2) - o.x) * inv.x;
-                        const float ty = ((float)((py_ ? cy + L4 : cy) << 2) - o.y) * inv.y;
-                        const float tz = ((float)((pz_ ? cz + L4 : cz) << 2) - o.z) * inv.z;
-                        const float t_next = fminf(fminf(tx, ty), tz);
-                        bool out = !(t_next <= t_exit);               // inclusive, DESIGN.md "Traversal semantics"
-                        int nx = jx, ny = jy, nz = jz;
-                        // axes whose plane time ties the minimum step one cell; the others are re-derived from the
-                        // ray at t_next and clamped into the cell's own range — a no-op at leaf granularity when
-                        // L4 == 1 (the clamp range is the single leaf cell)
-                        if (tx <= t_next) { nx = px_ ? cx + L4 : cx - 1; out |= (uint32_t)(nx - (int)(bnd0 & 0xFFFFu)) >= (bnd0 >> 16); }
-                        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.x, t_next, o.x)) >> 2; nx = min(max(ip, cx), cx + L4 - 1); }
-                        if (ty <= t_next) { ny = py_ ? cy + L4 : cy - 1; out |= (uint32_t)(ny - (int)(bnd1 & 0xFFFFu)) >= (bnd1 >> 16); }
-                        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.y, t_next, o.y)) >> 2; ny = min(max(ip, cy), cy + L4 - 1); }
-                        if (tz <= t_next) { nz = pz_ ? cz + L4 : cz - 1; out |= (uint32_t)(nz - (int)(bnd2 & 0xFFFFu)) >= (bnd2 >> 16); }
-                        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.z, t_next, o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
-                        // the cached 4^3 node survives a step that stays inside its 16-cell
-                        have_mid = have_mid && (((uint32_t)((nx ^ jx) | (ny ^ jy) | (nz ^ jz)) >> 2) == 0u);
-                        jx = nx; jy = ny; jz = nz;
-                        L4 = 0;
-                        if (out) mode = M_NEXT;
-                    }
-                    if (mode == M_WALK) {
-                        // descend to the cell containing (jx,jy,jz): InternalNode::get index arithmetic
-                        // (crates/vdb/src/node/internal.rs:77-95) on the re-laid-out nodes
-                        if (!have_mid) {
-                            const DNode16 *node = n16;
-                            bool alive = true;
-                            if (NL == 4 || (NL == 0 && four)) {
-                                const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
-                                const uint4 w = __ldg(&node->word[tidx >> 6]);
-                                if (STATS) st.mask_words++;
-                                const uint32_t b = tidx & 63u;
-                                if (!bit64(w.x, w.y, b)) { L4 = 64; alive = false; }
-                                else {
-                                    if (STATS) st.child_ptrs++;
-                                    node = n16 + (w.z + rank64(w.x, w.y, b));
-                                }
-                            }
-                            if (alive) {
-                                const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
-                                if (STATS) st.mask_words++;
-                                const uint4 w = __ldg(&node->word[ridx >> 6]);
-                                const uint32_t b = ridx & 63u;
-                                L4 = 4;
-                                if (bit64(w.x, w.y, b)) {
-                                    const uint4 mid = __ldg(&mids[w.z + rank64(w.x, w.y, b)]);
-                                    mid_lo = mid.x; mid_hi = mid.y; mid_base = mid.z;
-                                    have_mid = true;
-                                }
-                            }
-                        } else if (STATS) {
-                            if (NL == 4 || (NL == 0 && four)) { st.mask_words++; st.child_ptrs++; }
-                            st.mask_words++;
-                        }
-                        if (have_mid) {
-                            if (STATS) { st.child_ptrs++; st.mask_words++; }
-                            const uint32_t midx = ((uint32_t)(jx & 3) << 4) | ((uint32_t)(jy & 3) << 2) | (uint32_t)(jz & 3);
-                            L4 = 1;
-                            if (bit64(mid_lo, mid_hi, midx)) {
-                                if (STATS) { st.child_ptrs++; st.mask_words++; }
-                                leaf_i = mid_base + rank64(mid_lo, mid_hi, midx);
-                                L4 = 0;
-                                mode = M_LEAF;
-                            }
-                        }
-                    }
+                    const int r = walk_step<NL, STATS>(w, st);
+                    mode = r == WS_LEAF ? M_LEAF : (r == WS_OUT ? M_NEXT : M_WALK);
                 }
             } else if (op == M_LEAF) {
                 if (mode == M_LEAF) {
-                    // leaf step: one 128-bit load (occupancy + material_ptr), then hit.rint's DDA
-                    const uint4 leaf = __ldg(&leaves[leaf_i]);
-                    if (STATS) st.dbg[10]++;
-                    const f3 lo = mk3(o.x - (float)(jx << 2), o.y - (float)(jy << 2), o.z - (float)(jz << 2));   // hit.rint:140
                     float th; uint32_t vox;
-                    if (leaf_dda_inv<STATS>(lo, d, inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]) && tmin <= th && th <= cur) {   // reportIntersectionEXT
-                        if (any) { best.hit = true; best.inst = inst; mode = M_DONE; pend = -1; sp = DUST_SCRATCH_WORDS; }
+                    if (walk_leaf<STATS>(w, tmin, th, vox, st) && tmin <= th && th <= cur) {       // reportIntersectionEXT
+                        if (any) { best.hit = true; best.inst = w.inst; mode = M_DONE; pend = -1; sp = DUST_SCRATCH_WORDS; }
                         else {
-                            if (!best.hit || th < cur || inst < best.inst) {          // (t, instance) lexicographic
-                                best.hit = true; best.t = th; cur = th; best.inst = inst; best.leaf = leaf_i;
-                                best.pos = (uint32_t)jx | ((uint32_t)jy << 10) | ((uint32_t)jz << 20); best.voxel = vox;
+                            if (!best.hit || th < cur || w.inst < best.inst) {                     // (t, instance) lexicographic
+                                best.hit = true; best.t = th; cur = th; best.inst = w.inst; best.leaf = w.leaf_i;
+                                best.pos = walk_pos(w); best.voxel = vox;
                             }
-                            mode = M_NEXT;                                             // first accepted hit is this instance's closest
+                            mode = M_NEXT;                                                          // first accepted hit is this instance's closest
                         }
-                    } else { mode = M_WALK; L4 = 1; }
+                    } else { mode = M_WALK; w.L4 = 1; }
                 }
             } else {
                 if (mode == M_NEXT) {
@@ -273,40 +363,8 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
                     if (j < nc) {
                         const uint32_t key = sm[j * DUST_THREADS];
                         ++j;
-                        if (!(__uint_as_float(key & ~id_mask) > cur)) {               // sorted: nothing further can beat the best hit
-                            // enter instance: world -> object ray, reciprocals, clip against the occupied bounds
-                            mode = M_NEXT;
-                            inst = key & id_mask;
-                            if (STATS) st.dbg[12]++;
-                            const DInstance &in = sc.inst[inst];
-                            object_ray(in, ro, rd, o, d);
-                            inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                            const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(in.bounds));
-                            bnd0 = bw.x; bnd1 = bw.y; bnd2 = bw.z;
-                            const int bx0 = (int)(bnd0 & 0xFFFFu) << 2, by0 = (int)(bnd1 & 0xFFFFu) << 2, bz0 = (int)(bnd2 & 0xFFFFu) << 2;
-                            const int bx1 = bx0 + ((int)(bnd0 >> 16) << 2), by1 = by0 + ((int)(bnd1 >> 16) << 2), bz1 = bz0 + ((int)(bnd2 >> 16) << 2);
-                            // plane times are (plane - o) * inv: difference first, plane*inv - o*inv would cancel (|o/d| >> t)
-                            const float t0x = ((float)bx0 - o.x) * inv.x, t0y = ((float)by0 - o.y) * inv.y, t0z = ((float)bz0 - o.z) * inv.z;
-                            const float t1x = ((float)bx1 - o.x) * inv.x, t1y = ((float)by1 - o.y) * inv.y, t1z = ((float)bz1 - o.z) * inv.z;
-                            const float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-                            // walk a hair past tmax (acceptance stays exact): DESIGN.md "Traversal semantics"
-                            const float tmax_pad = cur + (fabsf(cur) * 3.814697265625e-06f + 9.5367431640625e-07f);
-                            t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
-                            if (t_enter <= t_exit && bx1 > bx0) {
-                                const int ix = __float2int_rd(__fmaf_rn(d.x, t_enter, o.x));
-                                const int iy = __float2int_rd(__fmaf_rn(d.y, t_enter, o.y));
-                                const int iz = __float2int_rd(__fmaf_rn(d.z, t_enter, o.z));
-                                jx = min(max(ix, bx0), bx1 - 1) >> 2; jy = min(max(iy, by0), by1 - 1) >> 2; jz = min(max(iz, bz0), bz1 - 1) >> 2;
-                                const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(&in.n16));
-                                n16 = reinterpret_cast<const DNode16 *>(p01.x);
-                                mids = reinterpret_cast<const uint4 *>(p01.y);
-                                leaves = in.leaves;
-                                if (NL == 0) four = bw.w == 4u;
-                                have_mid = false;
-                                L4 = 0;
-                                mode = M_WALK;
-                            }
-                        }
+                        if (!(__uint_as_float(key & ~id_mask) > cur))                               // sorted: nothing further can beat the best hit
+                            mode = walk_enter<NL, STATS>(sc, w, key & id_mask, ro, rd, tmin, cur, st) ? M_WALK : M_NEXT;
                     }
                 }
             }

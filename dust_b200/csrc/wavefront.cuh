@@ -2,35 +2,31 @@
 //
 // frame_kernel (kernels.cuh) keeps a path in one thread from camera ray to pixel.  That is ideal for
 // coherent rays (primary-only frames: 27 of 32 lanes busy per traversal step), but diffuse bounce rays
-// of neighbouring pixels point in unrelated directions: on the castle frame the warp then runs with 13
-// busy lanes and 17 lanes waiting for the slowest ray (profiles/r01_history.md); forcing one bounce
-// direction per warp — an experiment, not a valid render — halves the frame time.  The wavefront
-// pipeline gets that coherence legitimately by RE-ORDERING rays between path vertices:
+// of neighbouring pixels meet unrelated fates: on the castle frame the warp then runs with 13 busy
+// lanes and 17 lanes waiting for the slowest ray of the warp (profiles/r01_history.md).  The wavefront
+// pipeline cuts a path at its vertices and keeps rays, not paths, in flight:
 //
 //   wf_gen_primary   camera rays of every (pixel, sample) path of the batch          -> closest queue
 //   per depth v = 0 .. max_bounces:
-//     wf_trace       closest hit of every ray of the queue                           -> hit records
+//     trace          closest hit of every ray of the queue                           -> hit records
 //     wf_shade       apply the previous vertex's sun visibility, consume the hit (sky on a miss,
 //                    surface on a hit), emit the sun-shadow ray -> shadow queue and the cosine-weighted
-//                    bounce ray -> staging queue with a direction bin (octahedral 8x8)
-//     wf_trace       any hit of every shadow ray                                     -> visibility byte per path
-//     wf_scatter     counting sort of the staging queue by direction bin (stable per 2048-ray chunk, i.e.
-//                    Morton pixel order inside a bin)                                -> next closest queue
+//                    bounce ray -> next closest queue (compacted, one atomic per warp)
+//     trace          any hit of every shadow ray                                     -> visibility byte per path
 //   wf_resolve       last visibility, sRGB -> ACEScg, mean over samples in sample order -> frame
 //
-// Rays of one warp of the bounce pass then start within a few voxels of each other and point into the
-// same 1/64 of the sphere.  Every ray is traced by the same trace_scene as in the megakernel and every
-// float of a path is accumulated in the same order, so results are bit-identical to frame_kernel;
-// queue order (atomics) varies from run to run but no result depends on it.
-// Path state and queues live in HBM: ~175 B per path per batch, ~0.3 KB of traffic per ray.
+// trace = wf_trace (one thread per ray) for the coherent depth-0 queues; for the incoherent queues
+// behind a bounce it is wf_cull + wf_trace_pt: candidate instances are collected with all lanes busy,
+// then persistent lanes walk them and CLAIM THE NEXT RAY of the queue the moment their own is finished.
+// Every ray is traced by the same walk code as in the megakernel and every float of a path is
+// accumulated in the same order, so results are bit-identical to frame_kernel; queue order (atomics)
+// varies from run to run but no result depends on it.  (Sorting the bounce rays by direction bin was
+// tried and removed: with refilling lanes it only added a pass and scattered the path-state accesses.)
+// Path state and queues live in HBM: ~200 B per path per batch.
 #pragma once
 #include "kernels.cuh"
 
 namespace dust {
-
-#define WF_BINS 64
-#define WF_SCATTER_THREADS 256
-#define WF_SCATTER_CHUNK 2048
 
 struct WfQueue {
     float4 *a;          // origin.xyz, tmin
@@ -46,14 +42,12 @@ struct WfParams {
     uint32_t depth;                   // vertex index of the closest queue being traced / shaded
     uint32_t last_batch;
     float4 *ps0, *ps1, *ps2;          // path state: (T, s1) (L, flags) (pending sun term, -)
-    WfQueue qc, qs, qg;               // closest queue, shadow queue, staging (unsorted bounce rays)
+    WfQueue qc, qs, qn;               // closest queue of this depth, shadow queue, closest queue of the next depth
     uint4 *hits;                      // per closest-queue slot: t, instance | voxel << 20, leaf, leaf origin
     uint8_t *vis;                     // per path: 1 = its pending shadow ray was occluded
-    uint8_t *bin;                     // per staging slot
     uint4 *cand;                      // per queue slot: 2 x uint4 = up to WF_CANDS sorted candidate keys (wf_cull)
     uint32_t *overflow;               // queue slots whose candidate list did not fit: traced by wf_trace with the full cull
     uint32_t *counts;                 // per depth: [4v+1] shadow rays, [4v+2] bounce rays (= next closest queue); [3] = n_paths
-    uint32_t *bins;                   // per depth: WF_BINS totals, then WF_BINS cursors
     float4 *acc;                      // per pixel slot, carried across batches
 };
 
@@ -130,9 +124,9 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
 
 // ---------------------------------------------------------------- incoherent rays: pre-cull + persistent lanes
 //
-// wf_trace gives every ray a thread; a warp lasts as long as its longest ray.  For sorted bounce rays
-// that still leaves 13 of 32 lanes idle (profiles/r01_history.md): neighbouring rays of one direction
-// bin start a few voxels apart and meet different fates.  For those queues the work is split:
+// wf_trace gives every ray a thread; a warp lasts as long as its longest ray.  For bounce rays that
+// leaves 13 of 32 lanes idle (profiles/r01_history.md) — also after sorting them by direction bin:
+// neighbouring rays start a few voxels apart and meet different fates.  For those queues the work is split:
 //   wf_cull      one thread per ray, all lanes busy: walk the instance BVH, store the sorted candidate
 //                keys of the ray (<= WF_CANDS; rays that touch more go to an overflow list for wf_trace)
 //   wf_trace_pt  persistent lanes over the queue: NEXT / WALK / LEAF voted as in trace_scene, and a lane
@@ -151,51 +145,16 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
     const DSceneView &sc = p.f.scene;
     uint32_t *sm = s_scratch + threadIdx.x;
     const uint32_t id_mask = (1u << sc.id_bits) - 1u;
+    Counters st = {};
     bool over = false;
     if (i < n) {
         const float4 a = __ldg(&q.a[i]), b = __ldg(&q.b[i]);
         const f3 ro = mk3(a.x, a.y, a.z), rd = mk3(b.x, b.y, b.z);
         const float tmin = a.w, tmax = b.w;
-        const f3 winv = mk3(fabsf(rd.x) < 1e-30f ? copysignf(1e30f, rd.x) : 1.0f / rd.x,
-                            fabsf(rd.y) < 1e-30f ? copysignf(1e30f, rd.y) : 1.0f / rd.y,
-                            fabsf(rd.z) < 1e-30f ? copysignf(1e30f, rd.z) : 1.0f / rd.z);
-        int sp = DUST_SCRATCH_WORDS, pend = -1, nc = 0;
-        if (sc.n_inst) {
-            const float te = box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2], ro, winv, tmin, tmax);
-            if (te != CUDART_INF_F) {
-                if (sc.root_ref >= 0) pend = sc.root_ref;
-                else { sm[0] = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~sc.root_ref; nc = 1; }
-            }
-        }
-        while (pend >= 0 && nc + 3 <= sp) {                           // same expansion as trace_scene phase 1
-            const float4 *nd = reinterpret_cast<const float4 *>(sc.bvh + pend);
-            const float4 na = __ldg(nd), nb = __ldg(nd + 1), ncx = __ldg(nd + 2), ne = __ldg(nd + 3);
-            float t0 = box_entry(na.x, na.y, na.z, nb.x, nb.y, nb.z, ro, winv, tmin, tmax);
-            float t1 = box_entry(ncx.x, ncx.y, ncx.z, ne.x, ne.y, ne.z, ro, winv, tmin, tmax);
-            int c0 = __float_as_int(na.w), c1 = __float_as_int(nb.w);
-            if (t1 < t0) { const float tf = t0; t0 = t1; t1 = tf; const int ci = c0; c0 = c1; c1 = ci; }
-            int next = -1;
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const float te = s ? t1 : t0;
-                const int ch = s ? c1 : c0;
-                if (te == CUDART_INF_F) continue;
-                if (ch >= 0) {
-                    if (next < 0) next = ch; else sm[--sp * DUST_THREADS] = (uint32_t)ch;
-                } else {
-                    const uint32_t key = (__float_as_uint(fmaxf(te, 0.0f)) & ~id_mask) | (uint32_t)~ch;
-                    int k = nc++;
-                    while (k > 0) {
-                        const uint32_t prev = sm[(k - 1) * DUST_THREADS];
-                        if (prev <= key) break;
-                        sm[k * DUST_THREADS] = prev; --k;
-                    }
-                    sm[k * DUST_THREADS] = key;
-                }
-            }
-            if (next < 0 && sp < DUST_SCRATCH_WORDS) next = (int)sm[sp++ * DUST_THREADS];
-            pend = next;
-        }
+        const f3 winv = cull_inverse(rd);
+        int sp, pend, nc;
+        cull_begin(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc);
+        while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc, st);
         over = pend >= 0 || nc > WF_CANDS;                            // list incomplete or too long: slow path
         uint32_t c[WF_CANDS];
 #pragma unroll
@@ -211,6 +170,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
         base = __shfl_sync(full, base, __ffs(m) - 1);
         if (over) p.overflow[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
     }
+    if (STATS) flush_counters(p.f.counters, st);
 }
 
 #ifndef DUST_PT_MIN_BLOCKS2
@@ -239,16 +199,8 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
     uint32_t b_inst = 0xFFFFFFFFu, b_leaf = 0, b_pos = 0, b_vox = 0;
     int mode = W_NEXT, j = 0;                                          // j == WF_CANDS or key 0xFFFFFFFF: list exhausted
     bool exhausted = true;
-    // instance walk
-    uint32_t inst = 0, leaf_i = 0;
-    f3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(1.0f, 1.0f, 1.0f), inv = mk3(1.0f, 1.0f, 1.0f);
-    int jx = 0, jy = 0, jz = 0, L4 = 0;
-    float t_exit = 0.0f;
-    uint32_t bnd0 = 0, bnd1 = 0, bnd2 = 0;
-    const DNode16 *n16 = nullptr;
-    const uint4 *mids = nullptr, *leaves = nullptr;
-    uint32_t mid_lo = 0, mid_hi = 0, mid_base = 0;
-    bool have_mid = false, four = NL == 4;
+    Walk w;
+    w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
 
 #pragma unroll 1
     for (;;) {
@@ -267,85 +219,19 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
 
         if (op == W_WALK) {
             if (mode == W_WALK) {
-                if (L4) {
-                    if (STATS) st.dbg[L4 == 1 ? 7 : (L4 == 4 ? 8 : 9)]++;
-                    const int cx = jx & ~(L4 - 1), cy = jy & ~(L4 - 1), cz = jz & ~(L4 - 1);
-                    const bool px_ = d.x > 0.0f, py_ = d.y > 0.0f, pz_ = d.z > 0.0f;
-                    const float tx = ((float)((px_ ? cx + L4 : cx) << 2) - o.x) * inv.x;
-                    const float ty = ((float)((py_ ? cy + L4 : cy) << 2) - o.y) * inv.y;
-                    const float tz = ((float)((pz_ ? cz + L4 : cz) << 2) - o.z) * inv.z;
-                    const float t_next = fminf(fminf(tx, ty), tz);
-                    bool out = !(t_next <= t_exit);                   // inclusive, DESIGN.md "Traversal semantics"
-                    int nx = jx, ny = jy, nz = jz;
-                    if (tx <= t_next) { nx = px_ ? cx + L4 : cx - 1; out |= (uint32_t)(nx - (int)(bnd0 & 0xFFFFu)) >= (bnd0 >> 16); }
-                    else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.x, t_next, o.x)) >> 2; nx = min(max(ip, cx), cx + L4 - 1); }
-                    if (ty <= t_next) { ny = py_ ? cy + L4 : cy - 1; out |= (uint32_t)(ny - (int)(bnd1 & 0xFFFFu)) >= (bnd1 >> 16); }
-                    else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.y, t_next, o.y)) >> 2; ny = min(max(ip, cy), cy + L4 - 1); }
-                    if (tz <= t_next) { nz = pz_ ? cz + L4 : cz - 1; out |= (uint32_t)(nz - (int)(bnd2 & 0xFFFFu)) >= (bnd2 >> 16); }
-                    else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(d.z, t_next, o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
-                    have_mid = have_mid && (((uint32_t)((nx ^ jx) | (ny ^ jy) | (nz ^ jz)) >> 2) == 0u);
-                    jx = nx; jy = ny; jz = nz;
-                    L4 = 0;
-                    if (out) mode = W_NEXT;
-                }
-                if (mode == W_WALK) {
-                    if (!have_mid) {
-                        const DNode16 *node = n16;
-                        bool alive = true;
-                        if (NL == 4 || (NL == 0 && four)) {
-                            const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
-                            const uint4 w = __ldg(&node->word[tidx >> 6]);
-                            if (STATS) st.mask_words++;
-                            const uint32_t b = tidx & 63u;
-                            if (!bit64(w.x, w.y, b)) { L4 = 64; alive = false; }
-                            else {
-                                if (STATS) st.child_ptrs++;
-                                node = n16 + (w.z + rank64(w.x, w.y, b));
-                            }
-                        }
-                        if (alive) {
-                            const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
-                            if (STATS) st.mask_words++;
-                            const uint4 w = __ldg(&node->word[ridx >> 6]);
-                            const uint32_t b = ridx & 63u;
-                            L4 = 4;
-                            if (bit64(w.x, w.y, b)) {
-                                const uint4 mid = __ldg(&mids[w.z + rank64(w.x, w.y, b)]);
-                                mid_lo = mid.x; mid_hi = mid.y; mid_base = mid.z;
-                                have_mid = true;
-                            }
-                        }
-                    } else if (STATS) {
-                        if (NL == 4 || (NL == 0 && four)) { st.mask_words++; st.child_ptrs++; }
-                        st.mask_words++;
-                    }
-                    if (have_mid) {
-                        if (STATS) { st.child_ptrs++; st.mask_words++; }
-                        const uint32_t midx = ((uint32_t)(jx & 3) << 4) | ((uint32_t)(jy & 3) << 2) | (uint32_t)(jz & 3);
-                        L4 = 1;
-                        if (bit64(mid_lo, mid_hi, midx)) {
-                            if (STATS) { st.child_ptrs++; st.mask_words++; }
-                            leaf_i = mid_base + rank64(mid_lo, mid_hi, midx);
-                            L4 = 0;
-                            mode = W_LEAF;
-                        }
-                    }
-                }
+                const int r = walk_step<NL, STATS>(w, st);
+                mode = r == WS_LEAF ? W_LEAF : (r == WS_OUT ? W_NEXT : W_WALK);
             }
         } else if (op == W_LEAF) {
             if (mode == W_LEAF) {
-                const uint4 leaf = __ldg(&leaves[leaf_i]);
-                if (STATS) st.dbg[10]++;
-                const f3 lo = mk3(o.x - (float)(jx << 2), o.y - (float)(jy << 2), o.z - (float)(jz << 2));   // hit.rint:140
                 float th; uint32_t vox;
-                if (leaf_dda_inv<STATS>(lo, d, inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]) && tmin <= th && th <= cur) {   // reportIntersectionEXT
+                if (walk_leaf<STATS>(w, tmin, th, vox, st) && tmin <= th && th <= cur) {               // reportIntersectionEXT
                     if (pw >> 31) { hit = true; exhausted = true; }                    // any hit ends a shadow ray
-                    else if (!hit || th < cur || inst < b_inst) {                      // (t, instance) lexicographic
-                        hit = true; cur = th; b_inst = inst; b_leaf = leaf_i;
-                        b_pos = (uint32_t)jx | ((uint32_t)jy << 10) | ((uint32_t)jz << 20); b_vox = vox;
+                    else if (!hit || th < cur || w.inst < b_inst) {                    // (t, instance) lexicographic
+                        hit = true; cur = th; b_inst = w.inst; b_leaf = w.leaf_i; b_pos = walk_pos(w); b_vox = vox;
                     }
                     mode = W_NEXT;                                                     // first accepted hit is this instance's closest
-                } else { mode = W_WALK; L4 = 1; }
+                } else { mode = W_WALK; w.L4 = 1; }
             }
         } else {
             bool need = false;
@@ -356,36 +242,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
                     ++j;
                     if (j == WF_CANDS) exhausted = true;
                     if (key == 0xFFFFFFFFu || __uint_as_float(key & ~id_mask) > cur) exhausted = true;   // end of list / sorted: nothing further can beat the best hit
-                    else {
-                        inst = key & id_mask;
-                        const DInstance &in = sc.inst[inst];
-                        object_ray(in, ro, rd, o, d);
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                        const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(in.bounds));
-                        bnd0 = bw.x; bnd1 = bw.y; bnd2 = bw.z;
-                        const int bx0 = (int)(bnd0 & 0xFFFFu) << 2, by0 = (int)(bnd1 & 0xFFFFu) << 2, bz0 = (int)(bnd2 & 0xFFFFu) << 2;
-                        const int bx1 = bx0 + ((int)(bnd0 >> 16) << 2), by1 = by0 + ((int)(bnd1 >> 16) << 2), bz1 = bz0 + ((int)(bnd2 >> 16) << 2);
-                        const float t0x = ((float)bx0 - o.x) * inv.x, t0y = ((float)by0 - o.y) * inv.y, t0z = ((float)bz0 - o.z) * inv.z;
-                        const float t1x = ((float)bx1 - o.x) * inv.x, t1y = ((float)by1 - o.y) * inv.y, t1z = ((float)bz1 - o.z) * inv.z;
-                        const float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-                        const float tmax_pad = cur + (fabsf(cur) * 3.814697265625e-06f + 9.5367431640625e-07f);
-                        t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
-                        if (t_enter <= t_exit && bx1 > bx0) {
-                            const int ix = __float2int_rd(__fmaf_rn(d.x, t_enter, o.x));
-                            const int iy = __float2int_rd(__fmaf_rn(d.y, t_enter, o.y));
-                            const int iz = __float2int_rd(__fmaf_rn(d.z, t_enter, o.z));
-                            jx = min(max(ix, bx0), bx1 - 1) >> 2; jy = min(max(iy, by0), by1 - 1) >> 2; jz = min(max(iz, bz0), bz1 - 1) >> 2;
-                            const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(&in.n16));
-                            n16 = reinterpret_cast<const DNode16 *>(p01.x);
-                            mids = reinterpret_cast<const uint4 *>(p01.y);
-                            leaves = in.leaves;
-                            if (NL == 0) four = bw.w == 4u;
-                            have_mid = false;
-                            L4 = 0;
-                            mode = W_WALK;
-                            entered = true;
-                        }
-                    }
+                    else if (walk_enter<NL, STATS>(sc, w, key & id_mask, ro, rd, tmin, cur, st)) { mode = W_WALK; entered = true; }
                 }
                 need = !entered && exhausted;
             }
@@ -426,31 +283,15 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
     if (STATS) flush_counters(p.f.counters, st);
 }
 
-// octahedral 8x8 direction bin (a sorting heuristic only: no result depends on it)
-__device__ __forceinline__ uint32_t wf_direction_bin(f3 d)
-{
-    const float s = 1.0f / ((fabsf(d.x) + fabsf(d.y)) + fabsf(d.z));
-    float u = d.x * s, v = d.z * s;
-    if (d.y < 0.0f) {
-        const float fu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
-        u = fu; v = fv;
-    }
-    const int bu = min(max((int)((u * 0.5f + 0.5f) * 8.0f), 0), 7), bv = min(max((int)((v * 0.5f + 0.5f) * 8.0f), 0), 7);
-    return (uint32_t)(bv * 8 + bu);
-}
-
 // One thread per ray of the closest queue of depth p.depth: apply the pending sun term, consume the
 // hit, emit the vertex's shadow and bounce rays.  The per-path arithmetic is frame_kernel's, in order.
 template <bool STATS>
 __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__ WfParams p)
 {
-    __shared__ uint32_t s_hist[WF_BINS];
     const unsigned full = 0xffffffffu;
     const DustTraceConfig &cfg = p.f.cfg;
     const uint32_t n = wf_in_count(p);
     if (blockIdx.x * DUST_THREADS >= n) return;
-    if (threadIdx.x < WF_BINS) s_hist[threadIdx.x] = 0;
-    __syncthreads();
     const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     bool live = i < n;
@@ -458,7 +299,6 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
     uint32_t path = 0;
     bool emit_shadow = false, emit_bounce = false;
     f3 ro = mk3(0.0f, 0.0f, 0.0f), rd = mk3(0.0f, 0.0f, 0.0f);
-    uint32_t bin = 0;
     if (live) {
         path = __ldg(&p.qc.path[i]);
         const float4 a = __ldg(&p.qc.a[i]), b = __ldg(&p.qc.b[i]);
@@ -511,7 +351,6 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
                     float c, s;
                     cossin_2pi(u2, c, s);
                     rd = normalize3(rotate_by_normal(sn, mk3(rr * c, rr * s, cz)));
-                    bin = wf_direction_bin(rd);
                     emit_bounce = true;
                 }
             } else {
@@ -553,56 +392,13 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
             base = __shfl_sync(full, base, __ffs(m) - 1);
             if (emit_bounce) {
                 const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                p.qg.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
-                p.qg.b[k] = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
-                p.qg.path[k] = path;
-                p.bin[k] = (uint8_t)bin;
-                atomicAdd(&s_hist[bin], 1u);
+                p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
+                p.qn.b[k] = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
+                p.qn.path[k] = path;
             }
         }
     }
-    __syncthreads();
-    if (threadIdx.x < WF_BINS && s_hist[threadIdx.x]) atomicAdd(&p.bins[2 * WF_BINS * p.depth + threadIdx.x], s_hist[threadIdx.x]);
     if (STATS) flush_counters(p.f.counters, st);
-}
-
-// Counting sort of the staging queue by direction bin into the (next) closest queue.
-__global__ void __launch_bounds__(WF_SCATTER_THREADS) wf_scatter(const __grid_constant__ WfParams p)
-{
-    __shared__ uint32_t s_hist[WF_BINS], s_base[WF_BINS];
-    const uint32_t n = p.counts[4 * p.depth + 2];
-    const uint32_t chunk = blockIdx.x * WF_SCATTER_CHUNK;
-    if (chunk >= n) return;
-    uint32_t *totals = p.bins + 2 * WF_BINS * p.depth, *cursors = totals + WF_BINS;
-    if (threadIdx.x < WF_BINS) s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    constexpr int PER = WF_SCATTER_CHUNK / WF_SCATTER_THREADS;
-    uint32_t rank[PER], b[PER];
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const uint32_t e = chunk + k * WF_SCATTER_THREADS + threadIdx.x;
-        b[k] = 0xFFFFFFFFu;
-        if (e < n) { b[k] = p.bin[e]; rank[k] = atomicAdd(&s_hist[b[k]], 1u); }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        // exclusive scan of the 64 bin totals (two per lane), then reserve this chunk's range in every bin
-        const uint32_t t0 = totals[2 * threadIdx.x], t1 = totals[2 * threadIdx.x + 1];
-        uint32_t s = t0 + t1;
-        for (int ofs = 1; ofs < 32; ofs <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, s, ofs); if ((int)threadIdx.x >= ofs) s += v; }
-        const uint32_t excl = s - (t0 + t1);
-        const uint32_t h0 = s_hist[2 * threadIdx.x], h1 = s_hist[2 * threadIdx.x + 1];
-        s_base[2 * threadIdx.x] = excl + (h0 ? atomicAdd(&cursors[2 * threadIdx.x], h0) : 0u);
-        s_base[2 * threadIdx.x + 1] = excl + t0 + (h1 ? atomicAdd(&cursors[2 * threadIdx.x + 1], h1) : 0u);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        if (b[k] == 0xFFFFFFFFu) continue;
-        const uint32_t e = chunk + k * WF_SCATTER_THREADS + threadIdx.x;
-        const uint32_t dst = s_base[b[k]] + rank[k];
-        p.qc.a[dst] = p.qg.a[e]; p.qc.b[dst] = p.qg.b[e]; p.qc.path[dst] = p.qg.path[e];
-    }
 }
 
 // One thread per pixel slot: last pending sun term, sRGB -> ACEScg, sum in sample order (tone_map.comp:192-203 input)

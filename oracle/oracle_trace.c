@@ -279,8 +279,9 @@ typedef struct InstHit {
  * HDDA over the InternalNode levels (DESIGN.md "Traversal semantics"; defined here, the
  * reference has none).  State = integer voxel coordinate `iv` of the cell being examined.
  * Per iteration: descend from the root with the InternalNode::get index arithmetic
- * (crates/vdb/src/node/internal.rs:77-95) until a clear child_mask bit (empty cell of edge L)
- * or a leaf (L = 4, LEAF STEP); then leave the cell through its exit planes
+ * (crates/vdb/src/node/internal.rs:77-95) until a clear child_mask bit (empty cell of edge L),
+ * an empty 4x4x4 block of children of a 16^3 node (empty cell of edge 4L), or a leaf (L = 4,
+ * LEAF STEP); then leave the cell through its exit planes
  * t_a = (plane_a - o_a) * (1/d_a)  (the difference first: plane*inv - o*inv would cancel
  * catastrophically, |o/d| >> t); axes whose t_a equals the minimum step one cell
  * (ties step together, like hit.rint:102-104), the others are re-derived from the ray at that t
@@ -329,7 +330,18 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
         for (;;) {
             if (lv == 0) { L = 4; break; }
             uint32_t f = t->fanout_log2[lv], c = t->extent_log2[lv - 1], m = (1u << f) - 1u;
-            uint32_t idx = ((((uint32_t)iv[0] >> c) & m) << (2 * f)) | ((((uint32_t)iv[1] >> c) & m) << f) | (((uint32_t)iv[2] >> c) & m);
+            uint32_t ccx = ((uint32_t)iv[0] >> c) & m, ccy = ((uint32_t)iv[1] >> c) & m, ccz = ((uint32_t)iv[2] >> c) & m;
+            if (f == 4) {
+                /* BLOCK level (defined here, DESIGN.md "Traversal semantics"): a 16^3 node is first asked per
+                 * 4x4x4 block of children; a block without any set child_mask bit is one empty cell of 4x the
+                 * child edge.  Child bit = x<<8 | y<<4 | z  =>  word x*4 + (y>>2), bit (y&3)<<4 | z. */
+                st->mask_words++;
+                const uint64_t *words = (const uint64_t *)node;
+                uint64_t sel = 0x000F000F000F000Full << (4u * (ccz >> 2)), any = 0;
+                for (uint32_t x = ccx & ~3u; x < (ccx & ~3u) + 4u; x++) any |= words[x * 4u + (ccy >> 2)] & sel;
+                if (!any) { L = (int32_t)4 << c; break; }
+            }
+            uint32_t idx = (ccx << (2 * f)) | (ccy << f) | ccz;
             st->mask_words++;
             if (!o_bitmask_get((const uint64_t *)node, idx)) { L = (int32_t)1 << c; break; }
             st->child_ptrs++;
