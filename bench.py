@@ -123,12 +123,11 @@ def cpu_sample_rows(height, n_rows):
 
 
 def run_cpu_rows(osc, cam, sky, cfg, rows, spp):
-    """Times the oracle on `rows` (each its own o_render call over all threads). Returns (rays, seconds)."""
-    rays, t0 = 0, time.perf_counter()
-    for y in rows:
-        r = osc.render(cam, sky, cfg["width"], cfg["height"], spp=spp, max_bounces=cfg["max_bounces"], seed=SEED, y0=y, y1=y + 1, hits=False)
-        rays += r["stats"]["primary_rays"] + r["stats"]["bounce_rays"]
-    return rays, time.perf_counter() - t0
+    """Times the oracle on `rows` (ONE o_render_rows call: all host threads share the rows). Returns (rays, seconds)."""
+    t0 = time.perf_counter()
+    r = osc.render(cam, sky, cfg["width"], cfg["height"], spp=spp, max_bounces=cfg["max_bounces"], seed=SEED, hits=False, rows=rows)
+    dt = time.perf_counter() - t0
+    return r["stats"]["primary_rays"] + r["stats"]["bounce_rays"], dt
 
 
 def reference_arm(args, cfg):
@@ -305,22 +304,30 @@ def ours(args, cfg):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (frame_kernel): algorithmic bytes of THIS rank's launch / its duration
+    # ---- roofline: algorithmic bytes of THIS rank's frame / the device time of the kernels of one dust_trace call
+    # (one launch for primary-only frames; the wavefront pipeline's launches for frames with bounces — events on
+    # the launching stream bracket all of them; per-kernel shares: profiles/).
     peak, peak_src = measured_peak()
     alg_bytes = float(rank_counts[6].item())
     achieved = alg_bytes / (kern_ms_max * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("frame_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("config%d_dram_bytes_per_step" % args.config)
+            traffic_note = tj.get("how")
         except Exception:
             traffic = None
+    launches_per_step = launches / max(1, args.steps) - (2 if world > 1 else 0)
+    pipeline = "frame_kernel (megakernel, 1 launch)" if cfg["max_bounces"] == 0 else \
+        "wavefront pipeline: wf_gen_primary, wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_resolve (%d launches)" % launches_per_step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "dust::frame_kernel", "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "dust_trace = " + pipeline, "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_ray": alg_bytes / max(1.0, float(rank_counts[0].item() + rank_counts[1].item())), "peak_source": peak_src,
-                "note": "scene (tree %.1f MB) is L2-resident after first touch; the kernel is latency/divergence-bound, not HBM-bound"
-                        % (loaded.device_bytes / 1e6)}
+                "traffic_source": traffic_note,
+                "note": "scene (tree %.1f MB) is L2-resident after first touch: the traversal kernels are instruction-issue bound "
+                        "(70-80 %% issue slots busy), not HBM-bound; see profiles/" % (loaded.device_bytes / 1e6)}
 
     # ---- CPU baseline beside it: oracle port on all host threads, bounded sample of the same frame
     cpu = None

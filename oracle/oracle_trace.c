@@ -504,6 +504,8 @@ typedef struct Frame {
     float *radiance; uint32_t *hit_instance, *hit_leaf; uint8_t *hit_voxel; float *hit_t;
     float sun_dir[3];        /* normalize(sunlight_config.direction.xyz) */
     float sun_cone;          /* 1 - cos(solar radius), nee.rmiss:18-19 */
+    const uint32_t *rows;    /* o_render_rows: the rows to render (NULL: cfg->y0 .. cfg->y1) */
+    uint32_t n_rows;
 } Frame;
 
 static void shade_pixel(const Frame *F, uint32_t px, uint32_t py, OStats *st)
@@ -606,27 +608,35 @@ static void *render_worker(void *arg)
 {
     Job *j = (Job *)arg;
     const OTraceConfig *cfg = j->F->cfg;
+    OStats st;                      /* thread-local: the jobs array is contiguous, counting in place would share cache lines */
+    memset(&st, 0, sizeof st);
     /* 32-pixel spans of the row range, dealt round-robin: even a single row keeps every thread busy */
-    const uint64_t total = (uint64_t)(cfg->y1 - cfg->y0) * cfg->width, span = 32;
+    const uint32_t n_rows = j->F->rows ? j->F->n_rows : cfg->y1 - cfg->y0;
+    const uint64_t total = (uint64_t)n_rows * cfg->width, span = 32;
     for (uint64_t base = (uint64_t)j->tid * span; base < total; base += (uint64_t)j->nthreads * span) {
         uint64_t end = base + span < total ? base + span : total;
-        for (uint64_t i = base; i < end; i++)
-            shade_pixel(j->F, (uint32_t)(i % cfg->width), cfg->y0 + (uint32_t)(i / cfg->width), &j->st);
+        for (uint64_t i = base; i < end; i++) {
+            const uint32_t r = (uint32_t)(i / cfg->width);
+            shade_pixel(j->F, (uint32_t)(i % cfg->width), j->F->rows ? j->F->rows[r] : cfg->y0 + r, &st);
+        }
     }
+    j->st = st;
     return NULL;
 }
 
 static void *rays_worker(void *arg)
 {
     Job *j = (Job *)arg;
+    OStats st;
+    memset(&st, 0, sizeof st);
     const uint64_t chunk = 4096;
     for (uint64_t base = (uint64_t)j->tid * chunk; base < j->n; base += (uint64_t)j->nthreads * chunk) {
         uint64_t end = base + chunk < j->n ? base + chunk : j->n;
         for (uint64_t i = base; i < end; i++) {
             const ORay *r = &j->rays[i];
             SceneHit h;
-            trace_closest(j->s, r->o, r->d, r->tmin, r->tmax, &h, &j->st);
-            j->st.primary_rays++;
+            trace_closest(j->s, r->o, r->d, r->tmin, r->tmax, &h, &st);
+            st.primary_rays++;
             OHitRec *o = &j->hits[i];
             if (h.hit) {
                 o->t = h.ih.t; o->instance = h.instance;
@@ -636,6 +646,7 @@ static void *rays_worker(void *arg)
             }
         }
     }
+    j->st = st;
     return NULL;
 }
 
@@ -660,7 +671,17 @@ void o_render(const OScene *s, const OCamera *cam, const OSky *sky, const OTrace
               float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
               OStats *stats, uint32_t n_threads)
 {
-    Frame F = { s, cam, sky, cfg, radiance, hit_instance, hit_leaf, hit_voxel, hit_t, { 0, 0, 0 }, 0.0f };
+    o_render_rows(s, cam, sky, cfg, NULL, 0, radiance, hit_instance, hit_leaf, hit_voxel, hit_t, stats, n_threads);
+}
+
+/* As o_render, for an explicit list of rows (rows == NULL: cfg->y0 .. cfg->y1): bench.py's bounded CPU
+ * sample is spread over the frame and wants ONE call (one set of threads) for all of its rows. */
+void o_render_rows(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
+                   const uint32_t *rows, uint32_t n_rows,
+                   float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
+                   OStats *stats, uint32_t n_threads)
+{
+    Frame F = { s, cam, sky, cfg, radiance, hit_instance, hit_leaf, hit_voxel, hit_t, { 0, 0, 0 }, 0.0f, rows, n_rows };
     normalize3(sky->direction, F.sun_dir);                              /* ambient_occlusion.rgen:45 */
     F.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
     if (n_threads < 1) n_threads = 1;
@@ -676,7 +697,7 @@ uint32_t o_debug_pixel(const OScene *s, const OCamera *cam, const OSky *sky, con
                        uint32_t px, uint32_t py, ORay *rays, OHitRec *hits, uint32_t cap, float rgba[4])
 {
     float *rad = (float *)calloc((size_t)cfg->width * cfg->height, 4 * sizeof(float));
-    Frame F = { s, cam, sky, cfg, rad, NULL, NULL, NULL, NULL, { 0, 0, 0 }, 0.0f };
+    Frame F = { s, cam, sky, cfg, rad, NULL, NULL, NULL, NULL, { 0, 0, 0 }, 0.0f, NULL, 0 };
     normalize3(sky->direction, F.sun_dir);
     F.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
     OStats st;

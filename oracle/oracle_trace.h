@@ -80,6 +80,11 @@ void    o_scene_set_cull(OScene *s, int enabled);
 void o_render(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
               float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
               OStats *stats, uint32_t n_threads);
+/* the same for an explicit list of rows (bounded CPU samples spread over the frame) */
+void o_render_rows(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
+                   const uint32_t *rows, uint32_t n_rows,
+                   float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
+                   OStats *stats, uint32_t n_threads);
 
 /* Explicit ray batch, closest hit (BASELINE config 5) */
 void o_trace_rays(const OScene *s, const ORay *rays, uint64_t n, OHitRec *hits, OStats *stats, uint32_t n_threads);

@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
         "o_scene_create": (vp, [u32, pf32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]), "o_scene_destroy": (None, [vp]),
         "o_scene_set_cull": (None, [vp, i32]),
         "o_render": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
+        "o_render_rows": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, u32, vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
         "o_trace_rays": (None, [vp, vp, u64, vp, C.POINTER(OStats), u32]),
         "o_debug_pixel": (u32, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), u32, u32, vp, vp, u32, pf32]),
         "o_leaf_dda": (i32, [pf32, pf32, u64, f32, pf32, pu32]),
@@ -333,7 +334,8 @@ class Scene:
         lib().o_scene_set_cull(self._h, int(bool(enabled)))
 
     def render(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0, y0=0, y1=None,
-               hits=True, threads=None):
+               hits=True, threads=None, rows=None):
+        """rows: optional list of rows rendered in ONE call (the other rows of the returned frame stay zero)."""
         cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
         sk = sky if isinstance(sky, OSky) else as_struct(OSky, sky)
         y1 = height if y1 is None else y1
@@ -348,8 +350,13 @@ class Scene:
             res["hit_t"] = np.full((height, width), np.inf, np.float32)
             hp = [res[k].ctypes.data for k in ("hit_instance", "hit_leaf", "hit_voxel", "hit_t")]
         st = OStats()
-        lib().o_render(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), rad.ctypes.data, hp[0], hp[1], hp[2], hp[3],
-                       C.byref(st), threads or os.cpu_count() or 1)
+        if rows is not None:
+            ra = np.ascontiguousarray(rows, dtype=np.uint32)
+            lib().o_render_rows(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), ra.ctypes.data, len(ra), rad.ctypes.data,
+                                hp[0], hp[1], hp[2], hp[3], C.byref(st), threads or os.cpu_count() or 1)
+        else:
+            lib().o_render(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), rad.ctypes.data, hp[0], hp[1], hp[2], hp[3],
+                           C.byref(st), threads or os.cpu_count() or 1)
         res["stats"] = st.as_dict()
         return res
 
