@@ -36,6 +36,8 @@ CONFIGS = {
     1: dict(width=1920, height=1080, spp=1, max_bounces=0, name="castle 1920x1080 primary-only 1spp"),
     2: dict(width=1920, height=1080, spp=4, max_bounces=1, name="castle 1920x1080 primary+1 GI bounce 4spp"),
     3: dict(width=3840, height=2160, spp=8, max_bounces=2, name="castle 3840x2160 primary+2 GI bounces 8spp"),
+    # BASELINE.json configs[4]: synthetic 4096^3-domain VDB (1 % of the leaf slots filled), random-origin ray batch
+    5: dict(rays=20_000_000, name="synthetic 4096^3 VDB 1% fill, random ray batch"),
 }
 SEED = 2
 
@@ -360,6 +362,93 @@ def ours(args, cfg):
         dist.destroy_process_group()
 
 
+def rays_config(args, cfg):
+    """--config 5: the out-of-L2 case.  A step = one dust_trace_rays call over the whole batch (device buffers);
+    e2e = the same call with host buffers (H2D of the rays, D2H of the hits inside the timed region)."""
+    import torch
+    from dust_b200 import host, scenes
+    from dust_b200.pipeline import Context, Scene, HIT_DTYPE
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = int(args.rays or cfg["rays"])
+    t0 = time.perf_counter()
+    dom = host.SynthDomain(seed=5, fill=0.01, domain_leaves=1024)
+    ctx = Context(local)
+    dtree = ctx.upload_tree(dom.describe())
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    scene = Scene(ctx, [(ident, dtree)])
+    build_s = time.perf_counter() - t0
+    rays = scenes.ray_batch(n, dom.extent, seed=5 + rank)            # weak scaling: every rank its own batch, tree replicated
+    ctx.use_torch_stream()
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    scene.trace_rays_device(d_rays, d_hits, n, stats=True)
+    torch.cuda.synchronize()
+    st = ctx.stats()
+    alg = algorithmic_bytes(st, 0, rays_in=n, hits_out=n)
+    for _ in range(max(3, args.warmup)):
+        scene.trace_rays_device(d_rays, d_hits, n)
+    torch.cuda.synchronize()
+    launches0 = ctx.stats()["kernel_launches"]
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        scene.trace_rays_device(d_rays, d_hits, n)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    launches = ctx.stats()["kernel_launches"] - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # e2e through the host-buffer call
+    ctx.set_stream(None)
+    n_e2e = min(n, 5_000_000)
+    hits_host = np.empty(n_e2e, dtype=HIT_DTYPE)
+    scene.trace_rays(rays[:n_e2e])
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        hits_host = scene.trace_rays(rays[:n_e2e])
+        int(hits_host["instance"][0])
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    achieved = alg / (ms * 1e-3) / 1e9
+    hit_frac = float((d_hits[:, 1] != -1).float().mean().item())
+    line = {
+        "metric": "Mrays/s, random-origin ray batch on the synthetic 4096^3 VDB", "value": world * n / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: {cfg['name']}", "rays_per_gpu": n, "leaves": dom.num_leaves, "tree_device_bytes": dtree.device_bytes,
+                   "hit_fraction": hit_frac, "l2": "flushed between timed steps (256 MiB write); the tree (%.0f MB) and the rays exceed L2" % (dtree.device_bytes / 1e6),
+                   "build_s": build_s},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "wf_trace_pt<4> (persistent lanes, %d launch(es))" % (launches // args.steps), "kernel_ms": ms,
+                     "algorithmic_bytes_per_launch": alg, "bytes_per_ray": alg / n, "peak_source": peak_src},
+        "cpu_baseline": None,
+        "e2e": {"value": n_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n_e2e * 32, "d2h_bytes_per_step": n_e2e * 16,
+                "api": "dust_trace_rays(DUST_MEM_HOST), %d rays per call" % n_e2e},
+        "gpu_launches": int(launches), "clocks": clk,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -369,8 +458,15 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays", type=int, default=0, help="--config 5: rays per GPU (default 2e7; BASELINE names 1e8)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    if args.config == 5:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the frame configs (2, 1, 3)"}))
+            return
+        rays_config(args, cfg)
+        return
     if args.impl == "reference":
         reference_arm(args, cfg)
     else:

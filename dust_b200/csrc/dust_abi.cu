@@ -338,6 +338,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     for (int q = 0; q < 3; q++) {
         qs[q]->a = reinterpret_cast<float4 *>(base + o_q[q][0]); qs[q]->b = reinterpret_cast<float4 *>(base + o_q[q][1]);
         qs[q]->path = reinterpret_cast<uint32_t *>(base + o_q[q][2]);
+        qs[q]->stride = 1;
     }
     const WfQueue q_even = p.qc, q_odd = p.qn;                         // closest queues of even / odd depths
     p.hits = reinterpret_cast<uint4 *>(base + o_hits); p.acc = reinterpret_cast<float4 *>(base + o_acc);
@@ -773,11 +774,8 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     if (!ctx || !scene || (n && (!rays || !hits))) return DUST_ERR_INVALID_ARGUMENT;
     if (n == 0) return DUST_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    RayParams p;
-    memset(&p, 0, sizeof p);
-    p.scene = scene->view;
-    p.n = n;
-    p.counters = ctx->d_counters;
+    const DustRay *d_rays = rays;
+    DustHit *d_hits = hits;
     uint8_t *scratch = nullptr;
     const size_t ray_bytes = align_up((size_t)n * sizeof(DustRay), 256);
     if (memory == DUST_MEM_HOST) {
@@ -785,26 +783,70 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
         if (rc != DUST_OK) return rc;
         scratch = static_cast<uint8_t *>(ctx->scratch);
         CU_TRY(ctx, cudaMemcpyAsync(scratch, rays, (size_t)n * sizeof(DustRay), cudaMemcpyHostToDevice, ctx->stream));
-        p.rays = reinterpret_cast<const DustRay *>(scratch);
-        p.hits = reinterpret_cast<DustHit *>(scratch + ray_bytes);
-    } else if (memory == DUST_MEM_DEVICE) {
-        p.rays = rays; p.hits = hits;
-    } else return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+        d_rays = reinterpret_cast<const DustRay *>(scratch);
+        d_hits = reinterpret_cast<DustHit *>(scratch + ray_bytes);
+    } else if (memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
     const bool stats = (flags & DUST_TRACE_STATS) != 0;
     if (stats) CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DCounters), ctx->stream));
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const uint64_t want = (n + DUST_THREADS - 1) / DUST_THREADS;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 64u);
     const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
-    {
-        auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
-        if (nl == 3) { if (stats) launch(rays_kernel<3, true>); else launch(rays_kernel<3, false>); }
-        else if (nl == 4) { if (stats) launch(rays_kernel<4, true>); else launch(rays_kernel<4, false>); }
-        else { if (stats) launch(rays_kernel<0, true>); else launch(rays_kernel<0, false>); }
+    if (!ctx->d_wf_counters) CU_TRY(ctx, cudaMalloc(&ctx->d_wf_counters, kWfCounterWords * sizeof(uint32_t)));
+
+    // Ray batches are incoherent by nature: persistent lanes that claim the next ray when theirs is finished
+    // (wf_trace_pt), fed by pre-culled candidate lists (wf_cull) when the scene has more than one instance.
+    const bool plain = std::getenv("DUST_RAYS_PLAIN") != nullptr;                         // A/B only: one thread per ray
+    const bool need_cull = !plain && scene->n_inst > 1;
+    const uint64_t chunk_max = need_cull ? (16ull << 20) : (1ull << 30);
+    if (need_cull) {
+        const size_t need = align_up((size_t)std::min<uint64_t>(n, chunk_max) * 32, 256) + (size_t)std::min<uint64_t>(n, chunk_max) * 4;
+        if (need > ctx->wf_scratch_bytes) {
+            if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
+            CU_TRY(ctx, cudaMalloc(&ctx->wf_scratch, need));
+            ctx->wf_scratch_bytes = need;
+        }
     }
+    cudaError_t le = cudaSuccess;
+    for (uint64_t first = 0; first < n; first += chunk_max) {
+        const uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_max, n - first);
+        WfParams p;
+        memset(&p, 0, sizeof p);
+        p.f.scene = scene->view;
+        p.f.counters = ctx->d_counters;
+        p.n_paths = cn;
+        p.hits_out = d_hits + first;
+        WfQueue q;
+        q.a = reinterpret_cast<float4 *>(const_cast<DustRay *>(d_rays + first)); q.b = q.a + 1; q.path = nullptr; q.stride = 2;
+        const uint32_t grid = (cn + DUST_THREADS - 1) / DUST_THREADS;
+        uint32_t *ovf_count = ctx->d_wf_counters;
+        unsigned long long *work = reinterpret_cast<unsigned long long *>(ctx->d_wf_counters + 2);
+        auto trace = [&](const uint32_t *count, const uint32_t *list) {
+            if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
+            else if (nl == 4) { if (stats) wf_trace<4, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<4, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
+            else { if (stats) wf_trace<0, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<0, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
+            count_launch(ctx);
+        };
+        if (plain) { trace(nullptr, nullptr); continue; }
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_wf_counters, 0, 16, ctx->stream));
+        if (need_cull) {
+            p.cand = static_cast<uint4 *>(ctx->wf_scratch);
+            p.overflow = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ctx->wf_scratch) + align_up((size_t)std::min<uint64_t>(n, chunk_max) * 32, 256));
+            if (stats) wf_cull<true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, nullptr, ovf_count);
+            else wf_cull<false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, nullptr, ovf_count);
+            count_launch(ctx);
+        }
+        auto launch = [&](auto kernel) {
+            int per_sm = 0;
+            le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
+            const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
+            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, nullptr, work);
+        };
+        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
+        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
+        else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
+        count_launch(ctx);
+        if (need_cull) trace(ovf_count, p.overflow);                   // rays whose candidate list overflowed
+    }
+    CU_TRY(ctx, le);
     CU_TRY(ctx, cudaGetLastError());
-    count_launch(ctx);
     if (memory == DUST_MEM_HOST) {
         CU_TRY(ctx, cudaMemcpyAsync(hits, scratch + ray_bytes, (size_t)n * sizeof(DustHit), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -2,7 +2,7 @@
 //   frame_kernel    per-pixel primary ray + sun next-event estimation + diffuse GI bounces + radiance
 //                   (replaces the vkCmdTraceRaysKHR passes of StandardPipeline::render,
 //                   crates/render/src/pipeline/standard.rs:477-490, 564-577, 627-640)
-//   rays_kernel     explicit ray batch, closest hit (BASELINE.json config 5)
+//   (explicit ray batches, BASELINE.json config 5, run on wavefront.cuh's wf_cull / wf_trace_pt / wf_trace)
 //   resolve_kernel  un-permute gathered shard buffers to a row-major frame
 // Reference sources restated in frame_kernel:
 //   camera ray   assets/shaders/headers/camera.glsl:1-16, primary/primary.rgen:9-21
@@ -229,45 +229,6 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) frame_kernel(co
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t *>(&a); pk.y = *reinterpret_cast<uint32_t *>(&b);
             reinterpret_cast<uint2 *>(p.radiance16)[out_index] = pk;
-        }
-    }
-    if (STATS) flush_counters(p.counters, st);
-}
-
-// ------------------------------------------------------------------------------------- ray batches
-
-struct RayParams {
-    DSceneView scene;
-    const DustRay *rays;
-    DustHit *hits;
-    unsigned long long n;
-    DCounters *counters;
-};
-
-template <int NL, bool STATS>
-__global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) rays_kernel(const __grid_constant__ RayParams p)
-{
-    __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
-    uint32_t *sm = s_scratch + threadIdx.x;
-    Counters st = {};
-    const unsigned long long stride = (unsigned long long)gridDim.x * DUST_THREADS;
-    for (unsigned long long base = (unsigned long long)blockIdx.x * DUST_THREADS; base < p.n; base += stride) {
-        const unsigned long long i = base + threadIdx.x;
-        const bool live = i < p.n;
-        // 32-byte ray = two coalesced 128-bit loads
-        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        if (live) {
-            a = __ldg(reinterpret_cast<const float4 *>(p.rays) + 2 * i);
-            b = __ldg(reinterpret_cast<const float4 *>(p.rays) + 2 * i + 1);
-        }
-        Hit h;
-        trace_scene<NL, STATS>(p.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, false, live, sm, h, st);
-        if (live) {
-            if (STATS) st.primary_rays++;
-            uint4 o;
-            if (h.hit) { o.x = __float_as_uint(h.t); o.y = h.inst; o.z = h.leaf; o.w = h.voxel; }
-            else { o.x = __float_as_uint(CUDART_INF_F); o.y = o.z = o.w = 0xFFFFFFFFu; }
-            reinterpret_cast<uint4 *>(p.hits)[i] = o;
         }
     }
     if (STATS) flush_counters(p.counters, st);

@@ -29,9 +29,10 @@
 namespace dust {
 
 struct WfQueue {
-    float4 *a;          // origin.xyz, tmin
-    float4 *b;          // direction.xyz, tmax
-    uint32_t *path;     // path index; bit 31: any-hit (shadow) ray
+    float4 *a;          // origin.xyz, tmin   of ray i at a[i * stride]
+    float4 *b;          // direction.xyz, tmax           b[i * stride]
+    uint32_t *path;     // path index; bit 31: any-hit (shadow) ray.  NULL: closest-hit rays, path = i (ray batches)
+    uint32_t stride;    // 1: separate arrays; 2: interleaved DustRay records (a = rays, b = rays + 1)
 };
 
 struct WfParams {
@@ -44,6 +45,7 @@ struct WfParams {
     float4 *ps0, *ps1, *ps2;          // path state: (T, s1) (L, flags) (pending sun term, -)
     WfQueue qc, qs, qn;               // closest queue of this depth, shadow queue, closest queue of the next depth
     uint4 *hits;                      // per closest-queue slot: t, instance | voxel << 20, leaf, leaf origin
+    DustHit *hits_out;                // != NULL (dust_trace_rays): write the caller's DustHit records instead
     uint8_t *vis;                     // per path: 1 = its pending shadow ray was occluded
     uint4 *cand;                      // per queue slot: 2 x uint4 = up to WF_CANDS sorted candidate keys (wf_cull)
     uint32_t *overflow;               // queue slots whose candidate list did not fit: traced by wf_trace with the full cull
@@ -95,6 +97,17 @@ __global__ void __launch_bounds__(256) wf_gen_primary(const __grid_constant__ Wf
     if (i == 0) p.counts[3] = p.n_paths;                               // size of the depth-0 closest queue, for kernels that read it from memory
 }
 
+__device__ __forceinline__ void wf_store_hit(const WfParams &p, uint32_t i, bool hit, float t, uint32_t inst, uint32_t leaf, uint32_t pos, uint32_t voxel)
+{
+    if (p.hits_out) {                                                  // DustHit: t, instance, leaf, voxel (one 128-bit store)
+        reinterpret_cast<uint4 *>(p.hits_out)[i] = hit ? make_uint4(__float_as_uint(t), inst, leaf, voxel)
+                                                       : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    } else {
+        p.hits[i] = hit ? make_uint4(__float_as_uint(t), inst | (voxel << 20), leaf, pos)
+                        : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    }
+}
+
 // One thread per ray of a queue; the same trace_scene as the megakernel.
 // `list` != NULL: trace only the queue slots list[0 .. *count) (the rays wf_cull could not pre-cull).
 template <int NL, bool STATS>
@@ -109,14 +122,14 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
     const uint32_t i = live && list ? __ldg(&list[k]) : k;
     float4 a = make_float4(0.0f, 0.0f, 0.0f, 1.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     uint32_t pw = 0;
-    if (live) { a = __ldg(&q.a[i]); b = __ldg(&q.b[i]); pw = __ldg(&q.path[i]); }
+    if (live) { a = __ldg(&q.a[(size_t)i * q.stride]); b = __ldg(&q.b[(size_t)i * q.stride]); pw = q.path ? __ldg(&q.path[i]) : i; }
     Counters st = {};
     Hit h;
     trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st);
     if (live) {
+        if (STATS && !q.path) st.primary_rays++;
         if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = h.hit ? 1 : 0;
-        else p.hits[i] = h.hit ? make_uint4(__float_as_uint(h.t), h.inst | (h.voxel << 20), h.leaf, h.pos)
-                               : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+        else wf_store_hit(p, i, h.hit, h.t, h.inst, h.leaf, h.pos, h.voxel);
     }
     if (STATS) flush_counters(p.f.counters, st);
 }
@@ -138,7 +151,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
 {
     __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
     const unsigned full = 0xffffffffu;
-    const uint32_t n = *count;
+    const uint32_t n = count ? *count : p.n_paths;
     if (blockIdx.x * DUST_THREADS >= n) return;
     const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -148,7 +161,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
     Counters st = {};
     bool over = false;
     if (i < n) {
-        const float4 a = __ldg(&q.a[i]), b = __ldg(&q.b[i]);
+        const float4 a = __ldg(&q.a[(size_t)i * q.stride]), b = __ldg(&q.b[(size_t)i * q.stride]);
         const f3 ro = mk3(a.x, a.y, a.z), rd = mk3(b.x, b.y, b.z);
         const float tmin = a.w, tmax = b.w;
         const f3 winv = cull_inverse(rd);
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
     const DSceneView &sc = p.f.scene;
     uint32_t *sm = s_cand + threadIdx.x;
     const uint32_t id_mask = (1u << sc.id_bits) - 1u;
-    const uint32_t n = *count;
+    const uint32_t n = count ? *count : p.n_paths;
     Counters st = {};
 
     // the ray in flight and its best hit
@@ -250,9 +263,9 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
             const unsigned want = __ballot_sync(full, need);
             if (want) {
                 if (need && have_ray) {
+                    if (STATS && !q.path) st.primary_rays++;
                     if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = hit ? 1 : 0;
-                    else p.hits[ri] = hit ? make_uint4(__float_as_uint(cur), b_inst | (b_vox << 20), b_leaf, b_pos)
-                                          : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+                    else wf_store_hit(p, ri, hit, cur, b_inst, b_leaf, b_pos, b_vox);
                 }
                 const int leader = __ffs(want) - 1;
                 unsigned long long base = 0;
@@ -264,10 +277,17 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
                     if (idx >= n) mode = W_DEAD;
                     else {
                         ri = (uint32_t)idx;
-                        const uint4 c0 = __ldg(&p.cand[2 * (size_t)ri]), c1 = __ldg(&p.cand[2 * (size_t)ri + 1]);
+                        const float4 a = __ldg(&q.a[(size_t)ri * q.stride]), b = __ldg(&q.b[(size_t)ri * q.stride]);
+                        uint4 c0, c1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                        if (p.cand) { c0 = __ldg(&p.cand[2 * (size_t)ri]); c1 = __ldg(&p.cand[2 * (size_t)ri + 1]); }
+                        else {
+                            // single-instance scene (no wf_cull pass): the candidate list is the scene box test
+                            const float te = sc.n_inst ? box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2],
+                                                                   mk3(a.x, a.y, a.z), cull_inverse(mk3(b.x, b.y, b.z)), a.w, b.w) : CUDART_INF_F;
+                            c0 = make_uint4(te != CUDART_INF_F ? cand_key(te, 0u, id_mask) : 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                        }
                         if (c0.x != 0xFFFFFFFEu) {                                     // else: overflow ray, wf_trace does it
-                            const float4 a = __ldg(&q.a[ri]), b = __ldg(&q.b[ri]);
-                            pw = __ldg(&q.path[ri]);
+                            pw = q.path ? __ldg(&q.path[ri]) : ri;
                             ro = mk3(a.x, a.y, a.z); tmin = a.w; rd = mk3(b.x, b.y, b.z); cur = b.w;
                             sm[0 * DUST_THREADS] = c0.x; sm[1 * DUST_THREADS] = c0.y; sm[2 * DUST_THREADS] = c0.z; sm[3 * DUST_THREADS] = c0.w;
                             sm[4 * DUST_THREADS] = c1.x; sm[5 * DUST_THREADS] = c1.y; sm[6 * DUST_THREADS] = c1.z; sm[7 * DUST_THREADS] = c1.w;

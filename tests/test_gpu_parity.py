@@ -190,6 +190,23 @@ def test_ray_batch_small_domain(oracle, host, ctx):
     assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
 
 
+def test_ray_batch_many_instances(castle_small, host, monkeypatch):
+    """dust_trace_rays on a multi-instance scene: pre-culled candidate lists + persistent lanes (and the
+    one-thread-per-ray kernel, DUST_RAYS_PLAIN) against the oracle's linear instance loop, bit for bit."""
+    from dust_b200 import scenes
+    lo, hi = castle_small.bounds()
+    rays = scenes.ray_batch(150_000, 1.0, seed=8)
+    rays["o"] = lo.astype(np.float32) - 20 + rays["o"] * (hi - lo + 40).astype(np.float32)
+    rays["tmax"][::3] = 150.0                               # mix of bounded and unbounded rays
+    o, _ = castle_small.oscene.trace_rays(rays)
+    assert 0.1 < (o["instance"] != 0xFFFFFFFF).mean() < 0.95
+    g = castle_small.loaded.scene.trace_rays(rays)
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+    monkeypatch.setenv("DUST_RAYS_PLAIN", "1")
+    g2 = castle_small.loaded.scene.trace_rays(rays)
+    assert np.array_equal(g2.view(np.uint32), o.view(np.uint32))
+
+
 def test_empty_scene_and_errors(host, ctx):
     from dust_b200.capi import DustError
     from dust_b200.pipeline import Scene
