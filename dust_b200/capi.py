@@ -82,11 +82,16 @@ class DustTraceConfig(C.Structure):
                 ("width", "height", "spp", "max_bounces", "seed", "frame_index", "shard_index", "shard_count", "flags")]
 
 
+class DustGBuffer(C.Structure):
+    _fields_ = [("albedo", C.c_void_p), ("depth", C.c_void_p), ("normal", C.c_void_p), ("motion", C.c_void_p), ("voxel_id", C.c_void_p)]
+
+
 class DustFrame(C.Structure):
     _fields_ = [
         ("radiance", C.c_void_p), ("hit_instance", C.c_void_p), ("hit_leaf", C.c_void_p),
         ("hit_voxel", C.c_void_p), ("hit_t", C.c_void_p),
         ("memory", C.c_uint32), ("radiance_format", C.c_uint32),
+        ("gbuffer", C.POINTER(DustGBuffer)),
     ]
 
 
@@ -114,6 +119,7 @@ SYMBOLS = {
     "dust_tree_device_bytes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dust_scene_create": (C.c_int32, [C.c_void_p, C.POINTER(DustInstance), C.c_uint32, C.POINTER(C.c_void_p)]),
     "dust_scene_destroy": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "dust_scene_set_previous_transforms": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "dust_trace": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(DustCamera), C.POINTER(DustSky),
                                C.POINTER(DustTraceConfig), C.POINTER(DustFrame)]),
     "dust_trace_rays": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
@@ -137,7 +143,7 @@ def load() -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.dust_abi_version() != 1:
+    if lib.dust_abi_version() != 2:
         raise RuntimeError("libdust_b200.so ABI version mismatch")
     _lib = lib
     return lib

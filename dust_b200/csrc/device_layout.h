@@ -42,8 +42,9 @@ struct alignas(16) DInstance {
     const uint8_t *materials;
     const float4 *palette_lin;     // 256 x SRGBToLinear(rgb/255), w unused
     const uint2 *blocks;           // per 16^3 node: 64-bit block mask, bit bx<<4|by<<2|bz = "some child in that 4x4x4 block of children"
+    const uchar4 *palette_raw;     // 256 x RGBA8 as uploaded (G-buffer albedo)
     float o2w[9];                  // linear part of object -> world (normals)
-    uint32_t _pad1[3];
+    uint32_t _pad1[1];
 };
 static_assert(sizeof(DInstance) == 160, "DInstance layout");
 
@@ -61,6 +62,7 @@ static_assert(sizeof(DBvhNode) == 64, "DBvhNode layout");
 struct DSceneView {
     const DInstance *inst;
     const DBvhNode *bvh;           // n_inst - 1 inner nodes (none for 0 / 1 instances)
+    const float4 *prev_o2w;        // 3 rows per instance: last frame's object -> world (G-buffer motion)
     float root_lo[3], root_hi[3];  // padded world box of the whole scene
     int32_t root_ref;              // >= 0 inner node, < 0 instance ~root_ref
     uint32_t n_inst;

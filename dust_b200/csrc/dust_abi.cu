@@ -42,6 +42,7 @@ struct DustTree {
     const uint4 *leaves = nullptr;
     const uint8_t *materials = nullptr;
     const float4 *palette_lin = nullptr;
+    const uchar4 *palette_raw = nullptr;
     uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0;
     int32_t bmin[3] = { 0, 0, 0 }, bmax[3] = { 0, 0, 0 };   // occupied bounds in object voxels
 };
@@ -49,6 +50,7 @@ struct DustTree {
 struct DustScene {
     DInstance *d_inst = nullptr;
     DBvhNode *d_bvh = nullptr;
+    float4 *d_prev = nullptr;        // last frame's object -> world rows (3 per instance)
     DSceneView view{};               // device pointers + root box, passed to the kernels by value
     uint32_t n_inst = 0, n_bvh = 0, max_levels = 3, min_levels = 3;
 };
@@ -502,7 +504,8 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     const size_t off_mids = align_up(off_blocks + blocks.size() * sizeof(uint2), 256);
     const size_t off_leaves = align_up(off_mids + r.mids.size() * sizeof(uint4), 256);
     const size_t off_pal = align_up(off_leaves + r.leaves.size() * sizeof(uint4), 256);
-    const size_t off_mat = align_up(off_pal + sizeof pal, 256);
+    const size_t off_praw = align_up(off_pal + sizeof pal, 256);
+    const size_t off_mat = align_up(off_praw + 1024, 256);
     const size_t total = align_up(off_mat + (size_t)desc->n_materials + 16, 256);
 
     DustTree *t = new (std::nothrow) DustTree();
@@ -519,6 +522,10 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     if (e == cudaSuccess) e = put(off_mids, r.mids.data(), r.mids.size() * sizeof(uint4));
     if (e == cudaSuccess) e = put(off_leaves, r.leaves.data(), r.leaves.size() * sizeof(uint4));
     if (e == cudaSuccess) e = put(off_pal, pal, sizeof pal);
+    uint8_t praw[1024];
+    memset(praw, 0, sizeof praw);
+    memcpy(praw, desc->palette, 255 * 4);
+    if (e == cudaSuccess) e = put(off_praw, praw, sizeof praw);
     if (e == cudaSuccess) e = put(off_mat, desc->materials, (size_t)desc->n_materials);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);     // host vectors die at return
     if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e)); }
@@ -529,6 +536,7 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     t->mids = reinterpret_cast<const uint4 *>(base + off_mids);
     t->leaves = reinterpret_cast<const uint4 *>(base + off_leaves);
     t->palette_lin = reinterpret_cast<const float4 *>(base + off_pal);
+    t->palette_raw = reinterpret_cast<const uchar4 *>(base + off_praw);
     t->materials = base + off_mat;
     t->n_leaves = r.leaves.size(); t->n_mids = r.mids.size(); t->n_n16 = r.n16.size();
     if (r.leaves.empty()) { for (int a = 0; a < 3; a++) { t->bmin[a] = 0; t->bmax[a] = 0; } }
@@ -576,10 +584,10 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         world2obj(m, d.w2o);
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
         d.n_levels = t->n_levels;
-        d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin;
+        d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin; d.palette_raw = t->palette_raw;
         // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
         for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
-        d._pad1[0] = d._pad1[1] = d._pad1[2] = 0;
+        d._pad1[0] = 0;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove
@@ -619,16 +627,21 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
         if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * std::max<size_t>(nodes.size(), 1));
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream);
+        std::vector<float> prev(12 * (size_t)n);
+        for (uint32_t k = 0; k < n; k++) memcpy(&prev[12 * (size_t)k], instances[k].obj2world, 12 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_prev, sizeof(float) * 12 * n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_prev, prev.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess && !nodes.empty()) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             if (s->d_inst) cudaFree(s->d_inst);
             if (s->d_bvh) cudaFree(s->d_bvh);
+            if (s->d_prev) cudaFree(s->d_prev);
             delete s;
             return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e));
         }
     }
-    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh;
+    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh; s->view.prev_o2w = s->d_prev;
     for (int a = 0; a < 3; a++) { s->view.root_lo[a] = root_box.lo[a]; s->view.root_hi[a] = root_box.hi[a]; }
     s->view.root_ref = root_ref; s->view.n_inst = n;
     s->view.id_bits = 8;                                   // candidate key = entry t (high bits) | instance (low id_bits)
@@ -644,7 +657,19 @@ int32_t dust_scene_destroy(DustCtx *ctx, DustScene *scene)
     cudaStreamSynchronize(ctx->stream);
     if (scene->d_inst) cudaFree(scene->d_inst);
     if (scene->d_bvh) cudaFree(scene->d_bvh);
+    if (scene->d_prev) cudaFree(scene->d_prev);
     delete scene;
+    return DUST_OK;
+}
+
+int32_t dust_scene_set_previous_transforms(DustCtx *ctx, DustScene *scene, const float *obj2world_prev, uint32_t n)
+{
+    if (!ctx || !scene || (n && !obj2world_prev)) return DUST_ERR_INVALID_ARGUMENT;
+    if (n != scene->n_inst) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "one previous transform per instance");
+    if (!n) return DUST_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpyAsync(scene->d_prev, obj2world_prev, sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));                    // the caller's array may die at return
     return DUST_OK;
 }
 
@@ -671,6 +696,8 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
         return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "hit buffers need shard_count == 1 and all four arrays");
     if (frame->radiance_format != DUST_FMT_RGBA32F && frame->radiance_format != DUST_FMT_RGBA16F)
         return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad radiance format");
+    const DustGBuffer *gb = frame->gbuffer;
+    if (gb && cfg.shard_count != 1) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "the G-buffer needs shard_count == 1");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
 
     uint32_t tiles_per_shard = 0; uint64_t shard_pixels = 0;
@@ -700,7 +727,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     p.tiles_x = (cfg.width + 31) / 32; p.tiles_y = (cfg.height + 31) / 32; p.n_local_tiles = tiles_per_shard;
 
     uint8_t *scratch = nullptr;
-    size_t off_hi = 0, off_hl = 0, off_hv = 0, off_ht = 0;
+    size_t off_hi = 0, off_hl = 0, off_hv = 0, off_ht = 0, off_gb[5] = { 0, 0, 0, 0, 0 };
     const uint64_t npx = (uint64_t)cfg.width * cfg.height;
     if (frame->memory == DUST_MEM_HOST) {
         size_t need = align_up(out_pixels * px_bytes, 256);
@@ -709,6 +736,11 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
             off_hl = need; need += align_up(npx * 4, 256);
             off_ht = need; need += align_up(npx * 4, 256);
             off_hv = need; need += align_up(npx, 256);
+        }
+        if (gb) {
+            const void *src[5] = { gb->albedo, gb->depth, gb->normal, gb->motion, gb->voxel_id };
+            const size_t bytes[5] = { 4, 4, 4, 8, 4 };
+            for (int k = 0; k < 5; k++) if (src[k]) { off_gb[k] = need; need += align_up(npx * bytes[k], 256); }
         }
         int32_t rc = ensure_scratch(ctx, need);
         if (rc != DUST_OK) return rc;
@@ -719,10 +751,21 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
             p.hit_instance = reinterpret_cast<uint32_t *>(scratch + off_hi); p.hit_leaf = reinterpret_cast<uint32_t *>(scratch + off_hl);
             p.hit_t = reinterpret_cast<float *>(scratch + off_ht); p.hit_voxel = scratch + off_hv;
         }
+        if (gb) {
+            if (gb->albedo) p.gb.albedo = reinterpret_cast<uint32_t *>(scratch + off_gb[0]);
+            if (gb->depth) p.gb.depth = reinterpret_cast<float *>(scratch + off_gb[1]);
+            if (gb->normal) p.gb.normal = reinterpret_cast<uint32_t *>(scratch + off_gb[2]);
+            if (gb->motion) p.gb.motion = reinterpret_cast<uint16_t *>(scratch + off_gb[3]);
+            if (gb->voxel_id) p.gb.voxel_id = reinterpret_cast<uint32_t *>(scratch + off_gb[4]);
+            // the reference leaves normal / voxel_id of miss pixels untouched: start from the caller's contents
+            if (gb->normal) CU_TRY(ctx, cudaMemcpyAsync(p.gb.normal, gb->normal, npx * 4, cudaMemcpyHostToDevice, ctx->stream));
+            if (gb->voxel_id) CU_TRY(ctx, cudaMemcpyAsync(p.gb.voxel_id, gb->voxel_id, npx * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
     } else if (frame->memory == DUST_MEM_DEVICE) {
         if (frame->radiance_format == DUST_FMT_RGBA32F) p.radiance32 = static_cast<float4 *>(frame->radiance);
         else p.radiance16 = static_cast<__half *>(frame->radiance);
         if (want_hits) { p.hit_instance = frame->hit_instance; p.hit_leaf = frame->hit_leaf; p.hit_voxel = frame->hit_voxel; p.hit_t = frame->hit_t; }
+        if (gb) p.gb = *gb;
     } else return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
 
     const bool stats = (cfg.flags & DUST_TRACE_STATS) != 0;
@@ -761,6 +804,12 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
             CU_TRY(ctx, cudaMemcpyAsync(frame->hit_leaf, scratch + off_hl, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CU_TRY(ctx, cudaMemcpyAsync(frame->hit_t, scratch + off_ht, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CU_TRY(ctx, cudaMemcpyAsync(frame->hit_voxel, scratch + off_hv, npx, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (gb) {
+            void *dst[5] = { gb->albedo, gb->depth, gb->normal, gb->motion, gb->voxel_id };
+            const size_t bytes[5] = { 4, 4, 4, 8, 4 };
+            for (int k = 0; k < 5; k++)
+                if (dst[k]) CU_TRY(ctx, cudaMemcpyAsync(dst[k], scratch + off_gb[k], npx * bytes[k], cudaMemcpyDeviceToHost, ctx->stream));
         }
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }

@@ -33,6 +33,7 @@ struct FrameParams {
     uint32_t *hit_instance, *hit_leaf;
     uint8_t *hit_voxel;
     float *hit_t;
+    DustGBuffer gb;            // optional G-buffer of the sample-0 primary hit (NULL members are skipped)
     DCounters *counters;
 };
 
@@ -59,7 +60,7 @@ __device__ __forceinline__ void camera_ray(const DustCamera &cam, uint32_t width
 // hit.rchit:16-76 for hit `h` of world ray (ro, rd): world normal -> sn, offset hit point
 // (ambient_occlusion.rgen:23) -> ro, returns SRGBToLinear(albedo)
 template <bool STATS>
-__device__ __forceinline__ f3 surface_at(const DSceneView &sc, const Hit &h, f3 &ro, const f3 rd, f3 &sn, Counters &st)
+__device__ __forceinline__ f3 surface_at(const DSceneView &sc, const Hit &h, f3 &ro, const f3 rd, f3 &sn, Counters &st, uint32_t *palette_index = nullptr)
 {
     const DInstance &in = sc.inst[h.inst];
     f3 o, d;
@@ -81,9 +82,69 @@ __device__ __forceinline__ f3 surface_at(const DSceneView &sc, const Hit &h, f3 
     const uint32_t off = rank64(leaf.x, leaf.y, vox);                              // hit.rchit:60-61
     const uint8_t pi = __ldg(&in.materials[leaf.z + off]);                         // :71
     const float4 c = __ldg(&in.palette_lin[pi]);                                   // :72-74 + SRGBToLinear
+    if (palette_index) *palette_index = pi;
     ro = mk3((t * rd.x + ro.x) + sn.x * 0.01f, (t * rd.y + ro.y) + sn.y * 0.01f, (t * rd.z + ro.z) + sn.z * 0.01f);
     if (STATS) st.hits_shaded++;
     return mk3(c.x, c.y, c.z);
+}
+
+// ------------------------------------------------------------------------------------------ G-buffer
+
+// float -> UNORM (Vulkan "round to nearest"): rint(clamp(x, 0, 1) * (2^bits - 1))
+__device__ __forceinline__ uint32_t unorm(float x, float maxv) { return (uint32_t)rintf(fminf(fmaxf(x, 0.0f), 1.0f) * maxv); }
+// A2R10G10B10_UNORM_PACK32: A 31..30, R 29..20, G 19..10, B 9..0
+__device__ __forceinline__ uint32_t pack_a2r10g10b10(float r, float g, float b, float a)
+{
+    return (unorm(a, 3.0f) << 30) | (unorm(r, 1023.0f) << 20) | (unorm(g, 1023.0f) << 10) | unorm(b, 1023.0f);
+}
+
+// The image stores of hit.rchit:57-94 (hit) / miss.rmiss:13-16 (miss) for pixel `pi`.  (ro, rd) is the
+// world-space primary ray BEFORE surface_at offsets its origin; sn the world normal surface_at returned.
+__device__ __forceinline__ void gbuffer_store(const DustGBuffer &gb, const DSceneView &sc, uint32_t pi, bool hit, float t, uint32_t inst,
+                                              uint32_t voxel, uint32_t palette_index, f3 ro, f3 rd, f3 sn)
+{
+    if (!hit) {
+        if (gb.albedo) gb.albedo[pi] = 0xFFFFFFFFu;                                // vec4(1.0)
+        if (gb.depth) gb.depth[pi] = CUDART_INF_F;                                 // 1.0 / 0.0
+        if (gb.motion) reinterpret_cast<uint2 *>(gb.motion)[pi] = make_uint2(0u, 0u);
+        return;
+    }
+    const DInstance &in = sc.inst[inst];
+    if (gb.albedo) {
+        const uchar4 c = __ldg(&in.palette_raw[palette_index]);                    // hit.rchit:72-76
+        gb.albedo[pi] = pack_a2r10g10b10((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, 1.0f);
+    }
+    if (gb.depth) gb.depth[pi] = t;                                                // :81
+    if (gb.normal) {
+        // NRD_FrontEnd_PackNormalAndRoughness(normalWorld, 1.0, palette_index), headers/nrd.glsl:1-52 (R10G10B10A2 encoding)
+        const float s = (fabsf(sn.x) + fabsf(sn.y)) + fabsf(sn.z);
+        const float vx = sn.x / s, vy = sn.y / s, vz = sn.z / s;
+        const float wx = (1.0f - fabsf(vy)) * ((vx < 0.0f ? 0.0f : 1.0f) * 2.0f - 1.0f);
+        const float wy = (1.0f - fabsf(vx)) * ((vy < 0.0f ? 0.0f : 1.0f) * 2.0f - 1.0f);
+        const float ex = vz >= 0.0f ? vx : wx, ey = vz >= 0.0f ? vy : wy;
+        gb.normal[pi] = pack_a2r10g10b10(ex * 0.5f + 0.5f, ey * 0.5f + 0.5f, 1.0f, fminf(fmaxf((float)palette_index / 3.0f, 0.0f), 1.0f));
+    }
+    if (gb.voxel_id) gb.voxel_id[pi] = (voxel << 24) | (inst & 0xFFFFu) | (palette_index << 16);   // :87
+    if (gb.motion) {
+        // :90-94: world hit point -> model space -> last frame's world position
+        const f3 hw = mk3(t * rd.x + ro.x, t * rd.y + ro.y, t * rd.z + ro.z);
+        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(in.w2o)), r1 = __ldg(reinterpret_cast<const float4 *>(in.w2o) + 1),
+                     r2 = __ldg(reinterpret_cast<const float4 *>(in.w2o) + 2);
+        const f3 hm = mk3(((r0.x * hw.x + r0.y * hw.y) + r0.z * hw.z) + r0.w, ((r1.x * hw.x + r1.y * hw.y) + r1.z * hw.z) + r1.w,
+                          ((r2.x * hw.x + r2.y * hw.y) + r2.z * hw.z) + r2.w);
+        const float4 p0 = __ldg(&sc.prev_o2w[3 * inst]), p1 = __ldg(&sc.prev_o2w[3 * inst + 1]), p2 = __ldg(&sc.prev_o2w[3 * inst + 2]);
+        const f3 last = mk3(((p0.x * hm.x + p0.y * hm.y) + p0.z * hm.z) + p0.w, ((p1.x * hm.x + p1.y * hm.y) + p1.z * hm.z) + p1.w,
+                            ((p2.x * hm.x + p2.y * hm.y) + p2.z * hm.z) + p2.w);
+        const __half2 a = __floats2half2_rn(last.x - hw.x, last.y - hw.y), b = __floats2half2_rn(last.z - hw.z, 0.0f);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&a); pk.y = *reinterpret_cast<const uint32_t *>(&b);
+        reinterpret_cast<uint2 *>(gb.motion)[pi] = pk;
+    }
+}
+
+__device__ __forceinline__ bool gbuffer_wanted(const DustGBuffer &gb)
+{
+    return gb.albedo || gb.depth || gb.normal || gb.motion || gb.voxel_id;
 }
 
 __device__ __forceinline__ void flush_counters(DCounters *g, const Counters &st)
@@ -170,8 +231,13 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) frame_kernel(co
                     p.hit_instance[pixel_index] = h.hit ? h.inst : 0xFFFFFFFFu; p.hit_leaf[pixel_index] = h.hit ? h.leaf : 0xFFFFFFFFu;
                     p.hit_voxel[pixel_index] = h.hit ? (uint8_t)h.voxel : (uint8_t)0xFF; p.hit_t[pixel_index] = h.hit ? h.t : CUDART_INF_F;
                 }
+                const bool want_gb = kind == RAY_PRIMARY && smp == 0 && gbuffer_wanted(p.gb);
+                const f3 ro0 = ro;
+                if (want_gb && !h.hit) gbuffer_store(p.gb, p.scene, pixel_index, false, 0.0f, 0u, 0u, 0u, ro0, rd, sn);
                 if (h.hit) {
-                    const f3 a = surface_at<STATS>(p.scene, h, ro, rd, sn, st);
+                    uint32_t pidx = 0;
+                    const f3 a = surface_at<STATS>(p.scene, h, ro, rd, sn, st, &pidx);
+                    if (want_gb) gbuffer_store(p.gb, p.scene, pixel_index, true, h.t, h.inst, h.voxel, pidx, ro0, rd, sn);
                     if (kind == RAY_PRIMARY) { T = a; v = 0; }                         // tone_map.comp:195-203
                     else { T.x = T.x * a.x; T.y = T.y * a.y; T.z = T.z * a.z; v += 1; }   // final_gather.rchit:76-80
                     to_vertex = true;

@@ -38,6 +38,9 @@ struct Counters {
 #define DUST_SCRATCH_WORDS 24                  // shared words per lane: candidates grow up, the BVH stack grows down
 #endif
 #define DUST_MAX_BVH_DEPTH (DUST_SCRATCH_WORDS - 4)
+#ifndef DUST_WALK_REPS
+#define DUST_WALK_REPS 2                       // cells a lane may walk per voted WALK operation
+#endif
 
 enum : int { M_NEXT = 0, M_WALK = 1, M_LEAF = 2, M_DONE = 3 };
 
@@ -284,6 +287,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
 
 // Leaf step on leaf w.leaf_i: one 128-bit load (occupancy + material_ptr), then hit.rint's DDA.  Returns
 // true with (t, voxel) when a voxel is reached; the caller applies reportIntersectionEXT's [tmin, tmax].
+// (A resumable DDA — at most K iterations per voted LEAF operation — was tried: more trips, slower.)
 template <bool STATS>
 __device__ __forceinline__ bool walk_leaf(const Walk &w, float tmin, float &th, uint32_t &vox, Counters &st)
 {
@@ -339,10 +343,12 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
                 st.dbg[6] += 32 - n_walk - n_leaf - n_next;
             }
             if (op == M_WALK) {
-                if (mode == M_WALK) {
-                    const int r = walk_step<NL, STATS>(w, st);
-                    mode = r == WS_LEAF ? M_LEAF : (r == WS_OUT ? M_NEXT : M_WALK);
-                }
+#pragma unroll 1
+                for (int rep = 0; rep < DUST_WALK_REPS; rep++)             // several cells per vote: WALK -> WALK is the common transition
+                    if (mode == M_WALK) {
+                        const int r = walk_step<NL, STATS>(w, st);
+                        mode = r == WS_LEAF ? M_LEAF : (r == WS_OUT ? M_NEXT : M_WALK);
+                    }
             } else if (op == M_LEAF) {
                 if (mode == M_LEAF) {
                     float th; uint32_t vox;

@@ -231,10 +231,12 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
         }
 
         if (op == W_WALK) {
-            if (mode == W_WALK) {
-                const int r = walk_step<NL, STATS>(w, st);
-                mode = r == WS_LEAF ? W_LEAF : (r == WS_OUT ? W_NEXT : W_WALK);
-            }
+#pragma unroll 1
+            for (int rep = 0; rep < DUST_WALK_REPS; rep++)                 // several cells per vote: WALK -> WALK is the common transition
+                if (mode == W_WALK) {
+                    const int r = walk_step<NL, STATS>(w, st);
+                    mode = r == WS_LEAF ? W_LEAF : (r == WS_OUT ? W_NEXT : W_WALK);
+                }
         } else if (op == W_LEAF) {
             if (mode == W_LEAF) {
                 float th; uint32_t vox;
@@ -349,11 +351,16 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
                 p.f.hit_instance[pi] = hit ? (hw.y & 0xFFFFFu) : 0xFFFFFFFFu; p.f.hit_leaf[pi] = hit ? hw.z : 0xFFFFFFFFu;
                 p.f.hit_voxel[pi] = hit ? (uint8_t)(hw.y >> 20) : (uint8_t)0xFF; p.f.hit_t[pi] = hit ? __uint_as_float(hw.x) : CUDART_INF_F;
             }
+            const bool want_gb = p.depth == 0 && smp == 0 && gbuffer_wanted(p.f.gb);
+            if (want_gb && !hit) gbuffer_store(p.f.gb, p.f.scene, py * cfg.width + px, false, 0.0f, 0u, 0u, 0u, ro, rd, ro);
             if (hit) {
                 Hit h;
                 h.hit = true; h.t = __uint_as_float(hw.x); h.inst = hw.y & 0xFFFFFu; h.voxel = hw.y >> 20; h.leaf = hw.z; h.pos = hw.w;
                 f3 sn;
-                const f3 al = surface_at<STATS>(p.f.scene, h, ro, rd, sn, st);          // ro becomes the offset hit point
+                const f3 ro0 = ro;
+                uint32_t pidx = 0;
+                const f3 al = surface_at<STATS>(p.f.scene, h, ro, rd, sn, st, &pidx);   // ro becomes the offset hit point
+                if (want_gb) gbuffer_store(p.f.gb, p.f.scene, py * cfg.width + px, true, h.t, h.inst, h.voxel, pidx, ro0, rd, sn);
                 if (p.depth == 0) T = al;                                               // tone_map.comp:195-203
                 else { T.x = T.x * al.x; T.y = T.y * al.y; T.z = T.z * al.z; }          // final_gather.rchit:76-80
                 if (dot3(mk3(p.f.sky.direction[0], p.f.sky.direction[1], p.f.sky.direction[2]), sn) > 0.0f) {   // ambient_occlusion.rgen:33-50

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import capi
 from .capi import (PIPELINE_FLAGS, DUST_FMT_RGBA16F, DUST_FMT_RGBA32F, DUST_MEM_DEVICE, DUST_MEM_HOST, DUST_TRACE_STATS,
-                   DUST_TRACE_WRITE_HITS, DustFrame, DustInstance, DustStats, DustTraceConfig, check)
+                   DUST_TRACE_WRITE_HITS, DustFrame, DustGBuffer, DustInstance, DustStats, DustTraceConfig, check)
 
 MISS = 0xFFFFFFFF
 HIT_DTYPE = np.dtype([("t", "<f4"), ("instance", "<u4"), ("leaf", "<u4"), ("voxel", "<u4")])
@@ -113,6 +113,12 @@ class Scene:
         self.h = h
         self.n_instances = len(instances)
 
+    def set_previous_transforms(self, obj2world_prev):
+        """Last frame's object->world matrices, [n_instances, 12] (DustGBuffer.motion, hit.rchit:90-94)."""
+        a = np.ascontiguousarray(np.asarray(obj2world_prev, dtype=np.float32).reshape(-1, 12))
+        check(self.ctx.h, self.ctx.lib.dust_scene_set_previous_transforms(self.ctx.h, self.h, a.ctypes.data, len(a)),
+              "dust_scene_set_previous_transforms")
+
     def close(self):
         if getattr(self, "h", None) and self.ctx.h:
             self.ctx.lib.dust_scene_destroy(self.ctx.h, self.h)
@@ -123,7 +129,7 @@ class Scene:
 
     # ---- dust_trace ------------------------------------------------------------------------------
     def trace(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0,
-              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None, pipeline=None):
+              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None, pipeline=None, gbuffer=False):
         """Host-buffer call: returns dict(radiance[H,W,4], hit_instance, hit_leaf, hit_voxel, hit_t).
         pipeline: None / "auto", "megakernel" or "wavefront" (DUST_TRACE_PIPELINE_*; same results)."""
         ctx, lib = self.ctx, self.ctx.lib
@@ -147,6 +153,14 @@ class Scene:
             res["hit_t"] = np.empty((height, width), np.float32)
             fr.hit_instance, fr.hit_leaf = _ptr(res["hit_instance"]), _ptr(res["hit_leaf"])
             fr.hit_voxel, fr.hit_t = _ptr(res["hit_voxel"]), _ptr(res["hit_t"])
+        if gbuffer:
+            # DustGBuffer images (standard.rs:880-917); normal / voxel_id keep their initial value on miss pixels
+            g = {"albedo": np.zeros((height, width), np.uint32), "depth": np.zeros((height, width), np.float32),
+                 "normal": np.zeros((height, width), np.uint32), "motion": np.zeros((height, width, 4), np.float16),
+                 "voxel_id": np.full((height, width), 0xFFFFFFFF, np.uint32)}
+            gb = DustGBuffer(*[_ptr(g[k]) for k in ("albedo", "depth", "normal", "motion", "voxel_id")])
+            fr.gbuffer = C.pointer(gb)
+            res["gbuffer"] = g
         check(ctx.h, lib.dust_trace(ctx.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr)), "dust_trace")
         res["radiance"] = rad
         if stats:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DUST_ABI_VERSION 1
+#define DUST_ABI_VERSION 2
 
 enum {
     DUST_OK = 0,
@@ -121,6 +121,19 @@ enum { DUST_FMT_RGBA32F = 0, DUST_FMT_RGBA16F = 1 };
 /* Replaces the GBuffer images the reference writes (standard.rs:880-917).  With shard_count == 1
  * every array is row-major width*height.  With shard_count > 1 `radiance` is the compact
  * per-shard tile buffer (dust_shard_layout) and the hit arrays must be NULL. */
+/* The G-buffer images of the primary hit that hit.rchit:57-94 / miss.rmiss:13-16 write for the downstream
+ * consumers (NRD, tone map; formats: GBuffer, standard.rs:880-917), for sample 0 of every pixel.  Row-major
+ * width*height, same memory space as the frame, shard_count == 1 only; NULL members are skipped.
+ * On a miss albedo = (1,1,1,1), depth = +inf, motion = 0 and — like the reference — normal and voxel_id are
+ * left untouched. */
+typedef struct DustGBuffer {
+    uint32_t *albedo;          /* A2R10G10B10_UNORM_PACK32: vec4(palette[..].rgb / 255, 1)                  hit.rchit:71-76 */
+    float *depth;              /* R32_SFLOAT: gl_HitTEXT                                                    hit.rchit:81 */
+    uint32_t *normal;          /* A2R10G10B10_UNORM_PACK32: NRD_FrontEnd_PackNormalAndRoughness(normalWorld, 1.0, palette_index)  :83 */
+    uint16_t *motion;          /* R16G16B16A16_SFLOAT: last-frame world position - world position, a = 0     hit.rchit:90-94 */
+    uint32_t *voxel_id;        /* R32_UINT: voxel << 24 | palette_index << 16 | instance & 0xFFFF            hit.rchit:87 */
+} DustGBuffer;
+
 typedef struct DustFrame {
     void *radiance;            /* RGBA32F (ACEScg rgb, a = 1) or RGBA16F */
     uint32_t *hit_instance;    /* 0xFFFFFFFF = miss */
@@ -129,6 +142,7 @@ typedef struct DustFrame {
     float *hit_t;              /* gl_HitTEXT; +inf on miss (miss.rmiss:15) */
     uint32_t memory;           /* DUST_MEM_HOST or DUST_MEM_DEVICE */
     uint32_t radiance_format;  /* DUST_FMT_* */
+    const DustGBuffer *gbuffer; /* optional (NULL: none) */
 } DustFrame;
 
 typedef struct DustRay { float o[3]; float tmin; float d[3]; float tmax; } DustRay;       /* 32 B */
@@ -165,6 +179,10 @@ int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out);
 /* Replaces BLAS build + tlas_system + TLASStore::accel_struct (blas.rs:125-230, tlas.rs:37-132) */
 int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t n, DustScene **out);
 int32_t dust_scene_destroy(DustCtx *ctx, DustScene *scene);
+/* Last frame's object->world matrices (n x 12 floats, row-major 3x4), the `instances[]` buffer of
+ * hit.rchit:92 (PreviousFrameGlobalTransform, standard.rs:845-854); used only for DustGBuffer.motion.
+ * Until called, last frame == this frame. */
+int32_t dust_scene_set_previous_transforms(DustCtx *ctx, DustScene *scene, const float *obj2world_prev, uint32_t n);
 
 /* Replaces StandardPipeline::render (standard.rs:228-810) for the primary + bounce passes. */
 int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,

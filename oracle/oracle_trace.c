@@ -13,6 +13,7 @@
 
 typedef struct OInstance {
     float obj2world[12];
+    float prev_obj2world[12];      /* last frame (hit.rchit:92) */
     float w2o[12];
     const OTree *tree;
     const uint8_t *materials;
@@ -126,6 +127,7 @@ OScene *o_scene_create(uint32_t n, const float *obj2world, const OTree *const *t
     for (uint32_t k = 0; k < n; k++) {
         OInstance *in = &s->inst[k];
         memcpy(in->obj2world, obj2world + 12 * (size_t)k, sizeof in->obj2world);
+        memcpy(in->prev_obj2world, in->obj2world, sizeof in->prev_obj2world);
         o_world2obj(in->obj2world, in->w2o);
         in->tree = trees[k]; in->materials = materials[k]; in->palette = palettes[k];
         if (in->tree->fanout_log2[0] != 2) { o_scene_destroy(s); return NULL; }   /* 64-bit leaf masks only */
@@ -180,6 +182,11 @@ OScene *o_scene_create(uint32_t n, const float *obj2world, const OTree *const *t
 }
 
 void o_scene_set_cull(OScene *s, int enabled) { s->cull = enabled; }
+
+void o_scene_set_previous(OScene *s, const float *obj2world_prev)
+{
+    for (uint32_t k = 0; k < s->n; k++) memcpy(s->inst[k].prev_obj2world, obj2world_prev + 12 * (size_t)k, 12 * sizeof(float));
+}
 
 /* 1/d for the box tests only; a zero component becomes a huge FINITE value so that (b - o) * inv is
  * never 0 * inf */
@@ -464,7 +471,7 @@ typedef struct Surface {
     float x[3];        /* world hit point + 0.01 * n */
     float n[3];        /* world normal */
     float albedo[3];   /* palette rgb / 255 (non-linear sRGB) */
-    uint32_t leaf, voxel;
+    uint32_t leaf, voxel, palette_index;
 } Surface;
 
 /* assets/shaders/primary/hit.rchit:16-76 for the hit `h` of world ray (o, d) */
@@ -496,6 +503,7 @@ static void surface_of(const OScene *s, const SceneHit *h, const float o[3], con
         sf->x[a] = (ih->t * d[a] + o[a]) + sf->n[a] * 0.01f;
     sf->leaf = in->leaf_order[ih->leaf_ptr];
     sf->voxel = ih->voxel;
+    sf->palette_index = pi;
     st->hits_shaded++;
 }
 
@@ -506,7 +514,60 @@ typedef struct Frame {
     float sun_cone;          /* 1 - cos(solar radius), nee.rmiss:18-19 */
     const uint32_t *rows;    /* o_render_rows: the rows to render (NULL: cfg->y0 .. cfg->y1) */
     uint32_t n_rows;
+    const OGBuffer *gb;
 } Frame;
+
+/* float -> UNORM: round to nearest (even) of clamp(x, 0, 1) * (2^bits - 1) */
+static uint32_t unorm(float x, float maxv) { return (uint32_t)rintf(fminf(fmaxf(x, 0.0f), 1.0f) * maxv); }
+/* A2R10G10B10_UNORM_PACK32: A 31..30, R 29..20, G 19..10, B 9..0 */
+static uint32_t pack_a2r10g10b10(float r, float g, float b, float a)
+{
+    return (unorm(a, 3.0f) << 30) | (unorm(r, 1023.0f) << 20) | (unorm(g, 1023.0f) << 10) | unorm(b, 1023.0f);
+}
+
+/* the image stores of hit.rchit:57-94 for the primary hit `h` of world ray (o, d) */
+static void gbuffer_hit(const Frame *F, uint32_t pi, const SceneHit *h, const Surface *sf, const float o[3], const float d[3])
+{
+    const OGBuffer *gb = F->gb;
+    const OInstance *in = &F->s->inst[h->instance];
+    if (gb->albedo) gb->albedo[pi] = pack_a2r10g10b10(sf->albedo[0], sf->albedo[1], sf->albedo[2], 1.0f);       /* :71-76 */
+    if (gb->depth) gb->depth[pi] = h->ih.t;                                                                    /* :81 */
+    if (gb->normal) {
+        /* NRD_FrontEnd_PackNormalAndRoughness(normalWorld, 1.0, float(palette_index)), headers/nrd.glsl:1-52 */
+        const float *n = sf->n;
+        float s = (fabsf(n[0]) + fabsf(n[1])) + fabsf(n[2]);
+        float vx = n[0] / s, vy = n[1] / s, vz = n[2] / s;
+        float wx = (1.0f - fabsf(vy)) * ((vx < 0.0f ? 0.0f : 1.0f) * 2.0f - 1.0f);
+        float wy = (1.0f - fabsf(vx)) * ((vy < 0.0f ? 0.0f : 1.0f) * 2.0f - 1.0f);
+        float ex = vz >= 0.0f ? vx : wx, ey = vz >= 0.0f ? vy : wy;
+        gb->normal[pi] = pack_a2r10g10b10(ex * 0.5f + 0.5f, ey * 0.5f + 0.5f, 1.0f,
+                                          fminf(fmaxf((float)sf->palette_index / 3.0f, 0.0f), 1.0f));         /* :83 */
+    }
+    if (gb->voxel_id) gb->voxel_id[pi] = (sf->voxel << 24) | (h->instance & 0xFFFFu) | (sf->palette_index << 16);   /* :87 */
+    if (gb->motion) {                                                                                          /* :90-94 */
+        float hw[3], hm[3];
+        for (int a = 0; a < 3; a++) hw[a] = h->ih.t * d[a] + o[a];
+        for (int a = 0; a < 3; a++) {
+            const float *M = in->w2o + 4 * a;
+            hm[a] = ((M[0] * hw[0] + M[1] * hw[1]) + M[2] * hw[2]) + M[3];
+        }
+        for (int a = 0; a < 3; a++) {
+            const float *P = in->prev_obj2world + 4 * a;
+            float last = ((P[0] * hm[0] + P[1] * hm[1]) + P[2] * hm[2]) + P[3];
+            gb->motion[4 * (size_t)pi + a] = last - hw[a];
+        }
+        gb->motion[4 * (size_t)pi + 3] = 0.0f;
+    }
+}
+
+/* miss.rmiss:13-16 */
+static void gbuffer_miss(const Frame *F, uint32_t pi)
+{
+    const OGBuffer *gb = F->gb;
+    if (gb->albedo) gb->albedo[pi] = 0xFFFFFFFFu;
+    if (gb->depth) gb->depth[pi] = INFINITY;
+    if (gb->motion) for (int a = 0; a < 4; a++) gb->motion[4 * (size_t)pi + a] = 0.0f;
+}
 
 static void shade_pixel(const Frame *F, uint32_t px, uint32_t py, OStats *st)
 {
@@ -537,6 +598,7 @@ static void shade_pixel(const Frame *F, uint32_t px, uint32_t py, OStats *st)
                 F->hit_instance[pixel_index] = O_MISS; F->hit_leaf[pixel_index] = O_MISS;
                 F->hit_voxel[pixel_index] = 0xFF; F->hit_t[pixel_index] = INFINITY;      /* miss.rmiss:15 depth = 1/0 */
             }
+            if (smp == 0 && F->gb) gbuffer_miss(F, pixel_index);
         } else {
             Surface sf;
             surface_of(F->s, &h, o, d, &sf, st);
@@ -544,6 +606,7 @@ static void shade_pixel(const Frame *F, uint32_t px, uint32_t py, OStats *st)
                 F->hit_instance[pixel_index] = h.instance; F->hit_leaf[pixel_index] = sf.leaf;
                 F->hit_voxel[pixel_index] = (uint8_t)sf.voxel; F->hit_t[pixel_index] = h.ih.t;
             }
+            if (smp == 0 && F->gb) gbuffer_hit(F, pixel_index, &h, &sf, o, d);
             float T[3];                             /* throughput, starts at the primary albedo (tone_map.comp:195-203) */
             for (int a = 0; a < 3; a++) T[a] = o_srgb_to_linear(sf.albedo[a]);
             for (uint32_t v = 0;; v++) {
@@ -681,7 +744,15 @@ void o_render_rows(const OScene *s, const OCamera *cam, const OSky *sky, const O
                    float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
                    OStats *stats, uint32_t n_threads)
 {
-    Frame F = { s, cam, sky, cfg, radiance, hit_instance, hit_leaf, hit_voxel, hit_t, { 0, 0, 0 }, 0.0f, rows, n_rows };
+    o_render_g(s, cam, sky, cfg, rows, n_rows, radiance, hit_instance, hit_leaf, hit_voxel, hit_t, NULL, stats, n_threads);
+}
+
+void o_render_g(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
+                const uint32_t *rows, uint32_t n_rows,
+                float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
+                const OGBuffer *gbuffer, OStats *stats, uint32_t n_threads)
+{
+    Frame F = { s, cam, sky, cfg, radiance, hit_instance, hit_leaf, hit_voxel, hit_t, { 0, 0, 0 }, 0.0f, rows, n_rows, gbuffer };
     normalize3(sky->direction, F.sun_dir);                              /* ambient_occlusion.rgen:45 */
     F.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
     if (n_threads < 1) n_threads = 1;
@@ -697,7 +768,7 @@ uint32_t o_debug_pixel(const OScene *s, const OCamera *cam, const OSky *sky, con
                        uint32_t px, uint32_t py, ORay *rays, OHitRec *hits, uint32_t cap, float rgba[4])
 {
     float *rad = (float *)calloc((size_t)cfg->width * cfg->height, 4 * sizeof(float));
-    Frame F = { s, cam, sky, cfg, rad, NULL, NULL, NULL, NULL, { 0, 0, 0 }, 0.0f, NULL, 0 };
+    Frame F = { s, cam, sky, cfg, rad, NULL, NULL, NULL, NULL, { 0, 0, 0 }, 0.0f, NULL, 0, NULL };
     normalize3(sky->direction, F.sun_dir);
     F.sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
     OStats st;

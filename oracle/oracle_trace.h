@@ -80,6 +80,25 @@ void    o_scene_set_cull(OScene *s, int enabled);
 void o_render(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
               float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
               OStats *stats, uint32_t n_threads);
+/* The G-buffer images of the sample-0 primary hit (assets/shaders/primary/hit.rchit:57-94, miss.rmiss:13-16;
+ * formats crates/render/src/pipeline/standard.rs:880-917).  NULL members are skipped; on a miss normal and
+ * voxel_id stay untouched, like in the reference. */
+typedef struct OGBuffer {
+    uint32_t *albedo;    /* A2R10G10B10_UNORM_PACK32 */
+    float *depth;        /* R32_SFLOAT */
+    uint32_t *normal;    /* A2R10G10B10_UNORM_PACK32, NRD_FrontEnd_PackNormalAndRoughness */
+    float *motion;       /* xyz0 as float32 (the image is R16G16B16A16_SFLOAT: the caller rounds to half) */
+    uint32_t *voxel_id;  /* R32_UINT */
+} OGBuffer;
+
+/* last frame's object->world matrices (n x 12), the `instances[]` buffer of hit.rchit:92; default: this frame's */
+void o_scene_set_previous(OScene *s, const float *obj2world_prev);
+
+void o_render_g(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
+                const uint32_t *rows, uint32_t n_rows,
+                float *radiance, uint32_t *hit_instance, uint32_t *hit_leaf, uint8_t *hit_voxel, float *hit_t,
+                const OGBuffer *gbuffer, OStats *stats, uint32_t n_threads);
+
 /* the same for an explicit list of rows (bounded CPU samples spread over the frame) */
 void o_render_rows(const OScene *s, const OCamera *cam, const OSky *sky, const OTraceConfig *cfg,
                    const uint32_t *rows, uint32_t n_rows,

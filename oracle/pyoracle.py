@@ -60,6 +60,10 @@ class OStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class OGBuffer(C.Structure):
+    _fields_ = [("albedo", C.c_void_p), ("depth", C.c_void_p), ("normal", C.c_void_p), ("motion", C.c_void_p), ("voxel_id", C.c_void_p)]
+
+
 class OVoxInstance(C.Structure):
     _fields_ = [("model_id", C.c_uint32), ("obj2world", C.c_float * 12)]
 
@@ -108,6 +112,9 @@ def lib() -> C.CDLL:
         "o_scene_create": (vp, [u32, pf32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]), "o_scene_destroy": (None, [vp]),
         "o_scene_set_cull": (None, [vp, i32]),
         "o_render": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
+        "o_render_g": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, u32, vp, vp, vp, vp, vp,
+                              C.POINTER(OGBuffer), C.POINTER(OStats), u32]),
+        "o_scene_set_previous": (None, [vp, vp]),
         "o_render_rows": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, u32, vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
         "o_trace_rays": (None, [vp, vp, u64, vp, C.POINTER(OStats), u32]),
         "o_debug_pixel": (u32, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), u32, u32, vp, vp, u32, pf32]),
@@ -333,9 +340,14 @@ class Scene:
     def set_cull(self, enabled: bool):
         lib().o_scene_set_cull(self._h, int(bool(enabled)))
 
+    def set_previous_transforms(self, obj2world_prev):
+        a = np.ascontiguousarray(np.asarray(obj2world_prev, dtype=np.float32).reshape(-1, 12))
+        lib().o_scene_set_previous(self._h, a.ctypes.data)
+
     def render(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0, y0=0, y1=None,
-               hits=True, threads=None, rows=None):
-        """rows: optional list of rows rendered in ONE call (the other rows of the returned frame stay zero)."""
+               hits=True, threads=None, rows=None, gbuffer=False):
+        """rows: optional list of rows rendered in ONE call (the other rows of the returned frame stay zero).
+        gbuffer: also return the G-buffer images of the sample-0 primary hit (motion as float16, like the image)."""
         cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
         sk = sky if isinstance(sky, OSky) else as_struct(OSky, sky)
         y1 = height if y1 is None else y1
@@ -350,7 +362,17 @@ class Scene:
             res["hit_t"] = np.full((height, width), np.inf, np.float32)
             hp = [res[k].ctypes.data for k in ("hit_instance", "hit_leaf", "hit_voxel", "hit_t")]
         st = OStats()
-        if rows is not None:
+        if gbuffer:
+            g = {"albedo": np.zeros((height, width), np.uint32), "depth": np.zeros((height, width), np.float32),
+                 "normal": np.zeros((height, width), np.uint32), "voxel_id": np.full((height, width), 0xFFFFFFFF, np.uint32)}
+            motion = np.zeros((height, width, 4), np.float32)
+            gb = OGBuffer(g["albedo"].ctypes.data, g["depth"].ctypes.data, g["normal"].ctypes.data, motion.ctypes.data, g["voxel_id"].ctypes.data)
+            ra = None if rows is None else np.ascontiguousarray(rows, dtype=np.uint32)
+            lib().o_render_g(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), None if ra is None else ra.ctypes.data, 0 if ra is None else len(ra),
+                             rad.ctypes.data, hp[0], hp[1], hp[2], hp[3], C.byref(gb), C.byref(st), threads or os.cpu_count() or 1)
+            g["motion"] = motion.astype(np.float16)           # R16G16B16A16_SFLOAT (round to nearest even)
+            res["gbuffer"] = g
+        elif rows is not None:
             ra = np.ascontiguousarray(rows, dtype=np.uint32)
             lib().o_render_rows(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), ra.ctypes.data, len(ra), rad.ctypes.data,
                                 hp[0], hp[1], hp[2], hp[3], C.byref(st), threads or os.cpu_count() or 1)

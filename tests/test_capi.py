@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (dust_[a-z0-9_]+)", out))
     assert set(names) <= exported
-    assert lib.dust_abi_version() == 1
+    assert lib.dust_abi_version() == 2
 
 
 def test_ctypes_structs_match_header(tmp_path):
@@ -42,7 +42,8 @@ def test_ctypes_structs_match_header(tmp_path):
         "DustCamera": ["view_proj", "inverse_view_proj", "camera_view_col0", "position_x", "camera_view_col2", "tan_half_fov", "near"],
         "DustSky": ["r", "g", "b", "direction", "sunlight_intensity"],
         "DustTraceConfig": ["width", "spp", "seed", "shard_index", "flags"],
-        "DustFrame": ["radiance", "hit_instance", "hit_leaf", "hit_voxel", "hit_t", "memory", "radiance_format"],
+        "DustFrame": ["radiance", "hit_instance", "hit_leaf", "hit_voxel", "hit_t", "memory", "radiance_format", "gbuffer"],
+        "DustGBuffer": ["albedo", "depth", "normal", "motion", "voxel_id"],
         "DustStats": ["primary_rays", "mask_words", "kernel_launches"],
     }
     body = "".join(f'printf("{s} %zu\\n", sizeof({s}));\n' + "".join(

@@ -102,6 +102,36 @@ def test_castle_small_gi(castle_small, host, pipeline):
         assert g["stats"][k] == o["stats"][k], k
 
 
+@pytest.mark.parametrize("pipeline", PIPELINES)
+def test_gbuffer_bit_exact(castle_small, host, pipeline):
+    """DustGBuffer (hit.rchit:57-94, miss.rmiss:13-16): albedo / normal (A2R10G10B10), depth, motion (RGBA16F, with
+    last-frame transforms that differ from this frame's) and voxel_id, bit for bit against the oracle."""
+    from dust_b200 import scenes
+    W, H = 256, 144
+    cam = host.camera_look_at(width=W, height=H, **{k: v for k, v in scenes.CASTLE_CAMERA.items()})
+    sky = host.sunlight_bake(direction=host.castle_sun_direction(0.0))
+    cur = np.stack([m for _, m in castle_small.ovox.instances]).astype(np.float32).reshape(-1, 12)
+    prev = cur.copy()
+    rng = np.random.default_rng(3)
+    prev[:, 3::4] += rng.normal(scale=0.7, size=(len(prev), 3)).astype(np.float32)
+    castle_small.oscene.set_previous_transforms(prev)
+    castle_small.loaded.scene.set_previous_transforms(prev)
+    try:
+        g = castle_small.loaded.scene.trace(cam, sky, W, H, spp=2, max_bounces=1, seed=6, hits=True, gbuffer=True, pipeline=pipeline)
+        o = castle_small.oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=6, gbuffer=True)
+    finally:
+        castle_small.oscene.set_previous_transforms(cur)
+        castle_small.loaded.scene.set_previous_transforms(cur)
+    _assert_hits_equal(g, o)
+    assert (o["hit_instance"] != 0xFFFFFFFF).mean() > 0.2
+    for k in ("albedo", "normal", "voxel_id"):
+        bad = np.argwhere(g["gbuffer"][k] != o["gbuffer"][k])
+        assert len(bad) == 0, (k, len(bad), [(tuple(p), hex(g["gbuffer"][k][tuple(p)]), hex(o["gbuffer"][k][tuple(p)])) for p in bad[:3]])
+    assert np.array_equal(g["gbuffer"]["depth"].view(np.uint32), o["gbuffer"]["depth"].view(np.uint32))
+    assert np.array_equal(g["gbuffer"]["motion"].view(np.uint16), o["gbuffer"]["motion"].view(np.uint16))
+    assert np.abs(o["gbuffer"]["motion"].astype(np.float32)).max() > 0.3
+
+
 def test_visit_counters_against_oracle(teapot, host):
     """Ray / hit counts are properties of the paths and must match the oracle exactly.  The visit
     counters W, P are properties of the ALGORITHM: the kernel culls with the padded

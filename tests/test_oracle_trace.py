@@ -169,3 +169,59 @@ def test_instance_order_independence(oracle):
     # same geometry hit; where two instances tie exactly the lower index wins in each ordering
     same = perm[b["hit_instance"][hit]] == a["hit_instance"][hit]
     assert same.mean() > 0.98
+
+
+def _unpack_a2r10g10b10(v):
+    v = np.asarray(v, np.uint32)
+    return ((v >> 20) & 1023).astype(np.float64) / 1023, ((v >> 10) & 1023).astype(np.float64) / 1023, (v & 1023).astype(np.float64) / 1023, v >> 30
+
+
+def test_gbuffer_images_of_the_primary_hit(oracle, teapot, host):
+    """The G-buffer stores of hit.rchit:57-94 / miss.rmiss:13-16: fields must agree with the hit arrays, the
+    palette and the instance transforms (formats: standard.rs:880-917)."""
+    W = H = 64
+    lo, hi = teapot.bounds()
+    c = (lo + hi) / 2
+    cam = host.camera_look_at(c + np.array([1.2, 0.9, 1.2]) * (hi - lo).max(), c, width=W, height=H)
+    sky = host.sunlight_bake()
+    r = teapot.oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=4, gbuffer=True)
+    g = r["gbuffer"]
+    hit = r["hit_instance"] != 0xFFFFFFFF
+    assert 0.05 < hit.mean() < 0.95
+    # voxel_id: voxel << 24 | palette_index << 16 | instance            hit.rchit:87
+    assert np.array_equal(g["voxel_id"][hit] >> 24, r["hit_voxel"][hit].astype(np.uint32))
+    assert np.array_equal(g["voxel_id"][hit] & 0xFFFF, r["hit_instance"][hit] & 0xFFFF)
+    assert (g["voxel_id"][~hit] == 0xFFFFFFFF).all()                    # untouched on a miss
+    # depth = gl_HitTEXT, +inf on a miss                                hit.rchit:81, miss.rmiss:15
+    assert np.array_equal(g["depth"].view(np.uint32), r["hit_t"].view(np.uint32))
+    # albedo = palette[palette_index].rgb / 255 in 10-bit UNORM, alpha 1; miss = vec4(1)
+    pidx = (g["voxel_id"][hit] >> 16) & 0xFF
+    pal = np.asarray(teapot.ovox.palette, np.float64)[:, :3] / 255
+    ar, ag, ab, aa = _unpack_a2r10g10b10(g["albedo"][hit])
+    assert (aa == 3).all()
+    assert np.abs(np.stack([ar, ag, ab], -1) - pal[pidx]).max() <= 0.5 / 1023 + 1e-9
+    assert (g["albedo"][~hit] == 0xFFFFFFFF).all()
+    # normal: octahedral encoding of an axis-aligned unit normal, roughness 1.0, material id clamp(palette_index / 3)
+    nx, ny, rough, mat = _unpack_a2r10g10b10(g["normal"][hit])
+    assert (rough == 1.0).all()
+    assert np.array_equal(mat, np.minimum(3, np.rint(np.minimum(pidx / 3.0, 1.0) * 3)).astype(np.uint32))
+    px, py = nx * 2 - 1, ny * 2 - 1
+    nz = 1 - np.abs(px) - np.abs(py)
+    t = np.clip(-nz, 0, 1)
+    px, py = px + np.where(px >= 0, -t, t), py + np.where(py >= 0, -t, t)
+    n = np.stack([px, py, nz], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    assert np.abs(np.abs(n).max(axis=-1) - 1).max() < 5e-3               # decodes to +-x / +-y / +-z
+    assert (g["normal"][~hit] == 0).all()
+    # motion: zero (up to f32 round trip through the model space) while last frame == this frame ...
+    assert np.abs(g["motion"].astype(np.float32)).max() < 1e-3
+    # ... and the instance's displacement once last frame's transform differs
+    prev = np.stack([m.copy() for _, m in teapot.ovox.instances]).astype(np.float32).reshape(-1, 12)
+    prev[:, 3] += 1.5
+    prev[:, 11] -= 0.25
+    teapot.oscene.set_previous_transforms(prev)
+    g2 = teapot.oscene.render(cam, sky, W, H, spp=1, max_bounces=0, gbuffer=True)["gbuffer"]
+    teapot.oscene.set_previous_transforms(np.stack([m for _, m in teapot.ovox.instances]).reshape(-1, 12))
+    mo = g2["motion"].astype(np.float32)
+    assert np.abs(mo[hit][:, 0] - 1.5).max() < 2e-3 and np.abs(mo[hit][:, 1]).max() < 2e-3 and np.abs(mo[hit][:, 2] + 0.25).max() < 2e-3
+    assert (mo[~hit] == 0).all() and (mo[..., 3] == 0).all()
