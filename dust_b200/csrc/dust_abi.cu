@@ -219,8 +219,16 @@ Box box_union(const Box &a, const Box &b)
     return r;
 }
 
-// Median split over box centres.  Returns the reference of the subtree (>= 0: index into `nodes`,
-// < 0: ~instance) and its box; inner nodes store the boxes of both children.
+inline float box_area(const Box &b)
+{
+    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+}
+
+// Surface-area-heuristic sweep build (exact sweep over the three sorted axes; instance counts are small and
+// the build runs once per scene).  Returns the reference of the subtree (>= 0: index into `nodes`,
+// < 0: ~instance) and its box; inner nodes store the boxes of both children.  The traversal's results do
+// not depend on the tree (boxes only cull), only the number of nodes a ray expands does.
 int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const std::vector<Box> &boxes, uint32_t begin, uint32_t end,
               Box &out_box, int depth, int &max_depth)
 {
@@ -229,30 +237,56 @@ int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const st
         out_box = boxes[ids[begin]];
         return ~(int)ids[begin];
     }
-    float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
-    for (uint32_t k = begin; k < end; k++) {
-        const Box &x = boxes[ids[k]];
-        for (int a = 0; a < 3; a++) {
-            const float c = 0.5f * (x.lo[a] + x.hi[a]);
-            clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+    const uint32_t n = end - begin;
+    uint32_t best_split = begin + n / 2;
+    int best_axis = -1;
+    float best_cost = INFINITY;
+    std::vector<float> right_area(n);
+    // SAH may peel off one box at a time; it is used only while the worse child (n - 1 boxes) could still be
+    // finished by median splits inside the traversal's depth budget
+    int levels_left = 0;
+    while ((1u << levels_left) < n - 1) levels_left++;
+    const bool sah_ok = depth + 1 + levels_left <= DUST_MAX_BVH_DEPTH;
+    for (int axis = 0; axis < 3 && sah_ok; axis++) {
+        std::sort(ids.begin() + begin, ids.begin() + end, [&](uint32_t x, uint32_t y) {
+            const float cx = boxes[x].lo[axis] + boxes[x].hi[axis], cy = boxes[y].lo[axis] + boxes[y].hi[axis];
+            return cx < cy || (cx == cy && x < y);
+        });
+        Box acc = boxes[ids[end - 1]];
+        for (uint32_t k = n - 1; k >= 1; k--) { acc = box_union(acc, boxes[ids[begin + k]]); right_area[k] = box_area(acc); }
+        acc = boxes[ids[begin]];
+        for (uint32_t k = 1; k < n; k++) {                                         // split: [begin, begin + k) | [begin + k, end)
+            acc = box_union(acc, boxes[ids[begin + k - 1]]);
+            const float cost = box_area(acc) * (float)k + right_area[k] * (float)(n - k);
+            if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = begin + k; }
         }
     }
-    int axis = 0;
-    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-    const uint32_t mid = (begin + end) / 2;
-    std::nth_element(ids.begin() + begin, ids.begin() + mid, ids.begin() + end, [&](uint32_t x, uint32_t y) {
+    if (best_axis < 0) {                                                            // median split over the widest centre extent
+        float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (uint32_t k = begin; k < end; k++)
+            for (int a = 0; a < 3; a++) {
+                const float c = boxes[ids[k]].lo[a] + boxes[ids[k]].hi[a];
+                clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+            }
+        best_axis = 0;
+        if (chi[1] - clo[1] > chi[best_axis] - clo[best_axis]) best_axis = 1;
+        if (chi[2] - clo[2] > chi[best_axis] - clo[best_axis]) best_axis = 2;
+        best_split = begin + n / 2;
+    }
+    const int axis = best_axis;
+    std::sort(ids.begin() + begin, ids.begin() + end, [&](uint32_t x, uint32_t y) {
         const float cx = boxes[x].lo[axis] + boxes[x].hi[axis], cy = boxes[y].lo[axis] + boxes[y].hi[axis];
         return cx < cy || (cx == cy && x < y);
     });
+    const uint32_t mid = best_split;
     const int me = (int)nodes.size();
     nodes.emplace_back();
     Box bl, br;
     const int l = build_bvh(nodes, ids, boxes, begin, mid, bl, depth + 1, max_depth);
     const int r = build_bvh(nodes, ids, boxes, mid, end, br, depth + 1, max_depth);
-    DBvhNode &n = nodes[me];
-    for (int a = 0; a < 3; a++) { n.lo0[a] = bl.lo[a]; n.hi0[a] = bl.hi[a]; n.lo1[a] = br.lo[a]; n.hi1[a] = br.hi[a]; }
-    n.child0 = l; n.child1 = r; n._p0 = 0; n._p1 = 0;
+    DBvhNode &nd = nodes[me];
+    for (int a = 0; a < 3; a++) { nd.lo0[a] = bl.lo[a]; nd.hi0[a] = bl.hi[a]; nd.lo1[a] = br.lo[a]; nd.hi1[a] = br.hi[a]; }
+    nd.child0 = l; nd.child1 = r; nd._p0 = 0; nd._p1 = 0;
     out_box = box_union(bl, br);
     return me;
 }
