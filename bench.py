@@ -209,6 +209,12 @@ def ours(args, cfg):
     upload_s = time.perf_counter() - t0
     scene = loaded.scene
     ctx.use_torch_stream()
+    if world > 1:
+        # the data-path collective is the library's own entry point (ncclAllGather on the ctx stream);
+        # torch.distributed only carries the 128-byte id, the barriers and the max-over-ranks of the timings
+        uid = [Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
 
     tiles, per = shard_layout(W, H, world)
     if world > 1:
@@ -223,7 +229,7 @@ def ours(args, cfg):
     def step(frame_index=0, stats=False):
         if world > 1:
             scene.trace_device(cam, sky, W, H, shard_buf, shard_index=rank, shard_count=world, frame_index=frame_index, stats=stats, **kw)
-            dist.all_gather_into_tensor(gathered.view(-1), shard_buf.view(-1))
+            ctx.allgather_framebuffer(shard_buf, gathered)
             resolve_shards(ctx, W, H, world, gathered, frame)
         else:
             scene.trace_device(cam, sky, W, H, frame, frame_index=frame_index, stats=stats, **kw)
@@ -260,7 +266,7 @@ def ours(args, cfg):
         if world > 1:
             scene.trace_device(cam, sky, W, H, shard_buf, shard_index=rank, shard_count=world, **kw)
             ev[k][2].record()
-            dist.all_gather_into_tensor(gathered.view(-1), shard_buf.view(-1))
+            ctx.allgather_framebuffer(shard_buf, gathered)
             resolve_shards(ctx, W, H, world, gathered, frame)
         else:
             scene.trace_device(cam, sky, W, H, frame, **kw)
@@ -321,7 +327,7 @@ def ours(args, cfg):
             traffic_note = tj.get("how")
         except Exception:
             traffic = None
-    launches_per_step = launches / max(1, args.steps) - (2 if world > 1 else 0)
+    launches_per_step = launches / max(1, args.steps) - (1 if world > 1 else 0)     # resolve_kernel follows the all-gather
     pipeline = "frame_kernel (megakernel, 1 launch)" if cfg["max_bounces"] == 0 else \
         "wavefront pipeline: wf_gen_primary, wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_resolve (%d launches)" % launches_per_step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("DUST_B200_LIB") or os.path.join(LIB_DIR, "libdust_b20
 DUST_OK = 0
 ERR_NAMES = {
     0: "DUST_OK", 1: "DUST_ERR_INVALID_ARGUMENT", 2: "DUST_ERR_NO_DEVICE", 3: "DUST_ERR_CUDA",
-    4: "DUST_ERR_UNSUPPORTED", 5: "DUST_ERR_OUT_OF_MEMORY",
+    4: "DUST_ERR_UNSUPPORTED", 5: "DUST_ERR_OUT_OF_MEMORY", 6: "DUST_ERR_COMM",
 }
 DUST_TRACE_WRITE_HITS = 1
 DUST_TRACE_STATS = 2
@@ -125,8 +125,13 @@ SYMBOLS = {
     "dust_trace_rays": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
     "dust_shard_layout": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "dust_resolve_shards": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "dust_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "dust_comm_init": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "dust_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "dust_allgather_framebuffer": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "dust_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(DustStats)]),
 }
+DUST_COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -143,7 +148,7 @@ def load() -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.dust_abi_version() != 2:
+    if lib.dust_abi_version() != 3:
         raise RuntimeError("libdust_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -4,6 +4,7 @@
 #include "wavefront.cuh"
 
 #include <cstdlib>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +31,9 @@ struct DustCtx {
     uint32_t *d_wf_counters = nullptr;
     int sms = 148;
     DustStats stats{};
+    // multi-GPU: NCCL communicator of the shard group (dust_comm_init); NCCL is dlopen'ed on first use
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
 };
 
 struct DustTree {
@@ -471,6 +475,7 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     if (!ctx) return DUST_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    dust_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
@@ -949,6 +954,106 @@ int32_t dust_resolve_shards(DustCtx *ctx, uint32_t width, uint32_t height, uint3
                                                  shard_count, (width + 31) / 32, tiles_per_shard);
     CU_TRY(ctx, cudaGetLastError());
     count_launch(ctx);
+    return DUST_OK;
+}
+
+// ---- multi-GPU exchange step: one ncclAllGather of the compact per-rank tile buffers ----
+// NCCL is bound at run time (dlopen "libnccl.so.2": the copy the host process already loaded, else the
+// system one), so single-GPU users of this library carry no NCCL dependency.  The declarations below
+// restate the public NCCL 2.x C API (nccl.h) for the five entry points used.
+
+namespace {
+struct NcclUniqueId { char internal[DUST_COMM_ID_BYTES]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi *nccl_api(std::string &why)
+{
+    static NcclApi api;
+    static bool tried = false;
+    static std::string err;
+    if (!tried) {
+        tried = true;
+        const char *override_path = std::getenv("DUST_NCCL_LIB");
+        api.lib = dlopen(override_path ? override_path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) err = std::string("dlopen libnccl.so.2: ") + dlerror();
+        else {
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
+                err = "libnccl.so.2 lacks a required symbol";
+                dlclose(api.lib);
+                api.lib = nullptr;
+            }
+        }
+    }
+    why = err;
+    return api.lib ? &api : nullptr;
+}
+#define NCCL_TRY(ctx, api, expr)                                                                  \
+    do {                                                                                          \
+        const int r_ = (expr);                                                                    \
+        if (r_ != 0) return fail(ctx, DUST_ERR_COMM, std::string(#expr) + ": " + (api)->GetErrorString(r_)); \
+    } while (0)
+}  // namespace
+
+int32_t dust_comm_unique_id(uint8_t *id_out)
+{
+    if (!id_out) return DUST_ERR_INVALID_ARGUMENT;
+    std::string why;
+    NcclApi *api = nccl_api(why);
+    if (!api) return DUST_ERR_COMM;
+    NcclUniqueId id;
+    if (api->GetUniqueId(&id) != 0) return DUST_ERR_COMM;
+    memcpy(id_out, id.internal, DUST_COMM_ID_BYTES);
+    return DUST_OK;
+}
+
+int32_t dust_comm_init(DustCtx *ctx, const uint8_t *id, int32_t rank, int32_t nranks)
+{
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return DUST_ERR_INVALID_ARGUMENT;
+    if (ctx->nccl_comm) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "dust_comm_init: this context already has a communicator");
+    std::string why;
+    NcclApi *api = nccl_api(why);
+    if (!api) return fail(ctx, DUST_ERR_COMM, why);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, DUST_COMM_ID_BYTES);
+    NCCL_TRY(ctx, api, api->CommInitRank(&ctx->nccl_comm, nranks, uid, rank));
+    ctx->comm_rank = rank; ctx->comm_size = nranks;
+    return DUST_OK;
+}
+
+int32_t dust_comm_destroy(DustCtx *ctx)
+{
+    if (!ctx) return DUST_ERR_INVALID_ARGUMENT;
+    if (!ctx->nccl_comm) return DUST_OK;
+    std::string why;
+    NcclApi *api = nccl_api(why);
+    if (!api) return fail(ctx, DUST_ERR_COMM, why);
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    NCCL_TRY(ctx, api, api->CommDestroy(ctx->nccl_comm));
+    ctx->nccl_comm = nullptr; ctx->comm_rank = 0; ctx->comm_size = 1;
+    return DUST_OK;
+}
+
+int32_t dust_allgather_framebuffer(DustCtx *ctx, const void *shard, uint64_t bytes_per_rank, void *gathered)
+{
+    if (!ctx || !shard || !gathered || !bytes_per_rank) return DUST_ERR_INVALID_ARGUMENT;
+    if (!ctx->nccl_comm) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "dust_allgather_framebuffer: call dust_comm_init first");
+    std::string why;
+    NcclApi *api = nccl_api(why);
+    if (!api) return fail(ctx, DUST_ERR_COMM, why);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    NCCL_TRY(ctx, api, api->AllGather(shard, gathered, (size_t)bytes_per_rank, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream));
     return DUST_OK;
 }
 

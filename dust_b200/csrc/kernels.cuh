@@ -14,8 +14,11 @@
 
 namespace dust {
 
+#ifndef DUST_FRAME_MIN_BLOCKS
+#define DUST_FRAME_MIN_BLOCKS 5          // frame_kernel: 96 registers, no spills
+#endif
 #ifndef DUST_MIN_BLOCKS
-#define DUST_MIN_BLOCKS 5
+#define DUST_MIN_BLOCKS 6                // wf_trace
 #endif
 
 struct FrameParams {
@@ -177,7 +180,7 @@ __device__ __forceinline__ uint32_t even_bits(uint32_t v)      // bits 0,2,4,6,8
 // Every thread runs ONE loop around ONE call of trace_scene: the path's next ray (primary, sun
 // shadow, bounce) is generated after the previous one is consumed.
 template <int NL, bool STATS>
-__global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) frame_kernel(const __grid_constant__ FrameParams p)
+__global__ void __launch_bounds__(DUST_THREADS, DUST_FRAME_MIN_BLOCKS) frame_kernel(const __grid_constant__ FrameParams p)
 {
     __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
     uint32_t *sm = s_scratch + threadIdx.x;

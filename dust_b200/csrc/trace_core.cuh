@@ -167,6 +167,8 @@ struct Walk {
     uint32_t mid_lo, mid_hi, mid_base;
     uint32_t inst, leaf_i;
     bool have_mid;                   // the 4^3 node of the current 16-cell is in registers
+    bool have_n16;                   // 4-level trees: n16_i / blk_lo / blk_hi describe the 16^3 node of the current 256-cell
+    uint32_t n16_i;
     bool four;                       // this instance has 4 levels
 };
 
@@ -206,6 +208,7 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     if (NL == 0) w.four = bw.w == 4u;
     if (NL == 3 || (NL == 0 && !w.four)) { const uint2 b = __ldg(w.blocks); w.blk_lo = b.x; w.blk_hi = b.y; }
     w.have_mid = false;
+    w.have_n16 = false;
     w.L4 = 0;
     return true;
 }
@@ -238,7 +241,9 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (tz <= t_next) { nz = pz_ ? cz + L4 : cz - 1; out |= (uint32_t)(nz - (int)(w.bnd2 & 0xFFFFu)) >= (w.bnd2 >> 16); }
         else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.z, t_next, w.o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
         // the cached 4^3 node survives a step that stays inside its 16-cell
-        w.have_mid = w.have_mid && (((uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz)) >> 2) == 0u);
+        const uint32_t moved = (uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz));
+        w.have_mid = w.have_mid && ((moved >> 2) == 0u);
+        if (NL != 3) w.have_n16 = w.have_n16 && ((moved >> 6) == 0u);       // ... and so does the 16^3 node inside its 256-cell
         w.jx = nx; w.jy = ny; w.jz = nz;
         w.L4 = 0;
         if (out) return WS_OUT;
@@ -247,22 +252,25 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
     const bool four = NL == 4 || (NL == 0 && w.four);
     if (!w.have_mid) {
         const DNode16 *node = w.n16;
-        uint32_t blo = w.blk_lo, bhi = w.blk_hi;
         if (four) {
-            const uint2 tb = __ldg(w.blocks);
-            if (STATS) st.mask_words++;
-            if (!bit64(tb.x, tb.y, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
-            const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
-            const uint4 q = __ldg(&node->word[tidx >> 6]);
-            if (STATS) st.mask_words++;
-            const uint32_t b = tidx & 63u;
-            if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
-            if (STATS) st.child_ptrs++;
-            const uint32_t ni = q.z + rank64(q.x, q.y, b);
-            node = w.n16 + ni;
-            const uint2 cb = __ldg(w.blocks + ni);
-            blo = cb.x; bhi = cb.y;
+            if (!w.have_n16) {
+                const uint2 tb = __ldg(w.blocks);
+                if (STATS) st.mask_words++;
+                if (!bit64(tb.x, tb.y, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
+                const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
+                const uint4 q = __ldg(&node->word[tidx >> 6]);
+                if (STATS) st.mask_words++;
+                const uint32_t b = tidx & 63u;
+                if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
+                if (STATS) st.child_ptrs++;
+                w.n16_i = q.z + rank64(q.x, q.y, b);
+                const uint2 cb = __ldg(w.blocks + w.n16_i);
+                w.blk_lo = cb.x; w.blk_hi = cb.y;
+                w.have_n16 = true;
+            } else if (STATS) { st.mask_words += 2; st.child_ptrs++; }
+            node = w.n16 + w.n16_i;
         }
+        const uint32_t blo = w.blk_lo, bhi = w.blk_hi;
         if (STATS) st.mask_words++;
         if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
         const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
@@ -320,7 +328,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     if (live) cull_begin(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc);
 
     Walk w;
-    w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
+    w.four = NL == 4; w.have_mid = false; w.have_n16 = false; w.n16_i = 0; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
     for (;;) {
         // ---- phase 1: cull
         while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc, st);

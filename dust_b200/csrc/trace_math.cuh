@@ -187,8 +187,13 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
     float my = ((float)py + (posy ? 1.0f : 0.0f)) * cy - by_;
     float mz = ((float)pz + (posz ? 1.0f : 0.0f)) * cz - bz_;
     const float dx = (1.0f * cx) * (posx ? 1.0f : -1.0f), dy = (1.0f * cy) * (posy ? 1.0f : -1.0f), dz = (1.0f * cz) * (posz ? 1.0f : -1.0f);   // :96
-    const int isx = posx ? 16 : -16, isy = posy ? 4 : -4, isz = posz ? 1 : -1;    // step, pre-shifted into the voxel id
-    // voxel id x<<4 | y<<2 | z with one guard bit above each 2-bit field: leaving 0..3 on any axis sets a guard
+    // The cell is carried as x << 6 | y << 3 | z: 3-bit fields whose top bit is a GUARD.  A step that leaves
+    // 0..3 on an axis sets a guard bit (+1 from 3 -> 4; -1 from 0 -> 7, borrowing from the field above,
+    // which can only turn that field's 4 into 3 or its 7 into 6: whenever any axis leaves, at least the
+    // lowest leaving field keeps its guard).  So "did any stepped axis leave" is ONE mask test, with no
+    // per-axis branches (they ran with ~3 of 32 lanes, profiles/r01_v4_wf_trace_pt_lines.txt).
+    const int isx = posx ? 64 : -64, isy = posy ? 8 : -8, isz = posz ? 1 : -1;
+    int cell = (px << 6) | (py << 3) | pz;
     int hit = (px << 4) | (py << 2) | pz;                               // :99
 #pragma unroll 1
     while (!bit64(grid_lo, grid_hi, (uint32_t)hit)) {                   // :101
@@ -198,10 +203,10 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
         const bool kz = (my >= mz) && (mx >= mz);
         hitDistance = fminf(fminf(mx, my), mz);                         // :106
         if (hitDistance + 0.001f >= t_max) return false;                // :107
+        cell += (kx ? isx : 0) + (ky ? isy : 0) + (kz ? isz : 0);       // :103-104, :112
         // deviation (2), see oracle: a tie-step that leaves 0..3 on any axis ends the walk
-        if (kx) { if ((hit >> 4) == (posx ? 3 : 0)) return false; hit += isx; }   // :103-104, :112
-        if (ky) { if (((hit >> 2) & 3) == (posy ? 3 : 0)) return false; hit += isy; }
-        if (kz) { if ((hit & 3) == (posz ? 3 : 0)) return false; hit += isz; }
+        if (cell & 0x124) return false;
+        hit = ((cell >> 2) & 0x30) | ((cell >> 1) & 0xC) | (cell & 3);
         mx += kx ? dx : 0.0f; my += ky ? dy : 0.0f; mz += kz ? dz : 0.0f;          // :110
     }
     t_out = hitDistance / 1.0f;                                         // :115

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
 }
 
 #ifndef DUST_PT_MIN_BLOCKS2
-#define DUST_PT_MIN_BLOCKS2 6
+#define DUST_PT_MIN_BLOCKS2 8                 // 64 registers: 8 CTAs / SM beat 6 with no spills that matter (A/B in profiles/r01_history.md)
 #endif
 
 enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
     int mode = W_NEXT, j = 0;                                          // j == WF_CANDS or key 0xFFFFFFFF: list exhausted
     bool exhausted = true;
     Walk w;
-    w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
+    w.four = NL == 4; w.have_mid = false; w.have_n16 = false; w.n16_i = 0; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
 
 #pragma unroll 1
     for (;;) {

@@ -53,6 +53,28 @@ class Context:
         check(self.h, self.lib.dust_get_stats(self.h, C.byref(s)), "dust_get_stats")
         return s.as_dict()
 
+    # ---- multi-GPU exchange step (dust_comm_* / dust_allgather_framebuffer) ---------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0 calls this and hands the 128 bytes to the other ranks over the host's own channel."""
+        buf = (C.c_uint8 * capi.DUST_COMM_ID_BYTES)()
+        check(None, capi.load().dust_comm_unique_id(buf), "dust_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        """Collective: every rank of the shard group calls it with the same id."""
+        assert len(uid) == capi.DUST_COMM_ID_BYTES
+        buf = (C.c_uint8 * capi.DUST_COMM_ID_BYTES).from_buffer_copy(uid)
+        check(self.h, self.lib.dust_comm_init(self.h, buf, rank, nranks), "dust_comm_init")
+
+    def comm_destroy(self):
+        check(self.h, self.lib.dust_comm_destroy(self.h), "dust_comm_destroy")
+
+    def allgather_framebuffer(self, shard, gathered):
+        """shard: this rank's compact tile buffer (CUDA tensor); gathered: nranks x the same, rank order."""
+        nbytes = shard.numel() * shard.element_size()
+        check(self.h, self.lib.dust_allgather_framebuffer(self.h, _ptr(shard), nbytes, _ptr(gathered)), "dust_allgather_framebuffer")
+
     def upload_tree(self, desc: capi.DustTreeDesc) -> "DeviceTree":
         return DeviceTree(self, desc)
 

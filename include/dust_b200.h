@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DUST_ABI_VERSION 2
+#define DUST_ABI_VERSION 3
 
 enum {
     DUST_OK = 0,
@@ -32,7 +32,8 @@ enum {
     DUST_ERR_NO_DEVICE = 2,
     DUST_ERR_CUDA = 3,
     DUST_ERR_UNSUPPORTED = 4,     /* e.g. a hierarchy other than (4,2,2) / (4,4,2,2) */
-    DUST_ERR_OUT_OF_MEMORY = 5
+    DUST_ERR_OUT_OF_MEMORY = 5,
+    DUST_ERR_COMM = 6             /* NCCL missing or a collective failed (dust_last_error_string has the NCCL text) */
 };
 
 typedef struct DustCtx DustCtx;
@@ -199,6 +200,19 @@ int32_t dust_shard_layout(uint32_t width, uint32_t height, uint32_t shard_count,
                           uint32_t *tiles_per_shard, uint64_t *pixels_per_shard);
 int32_t dust_resolve_shards(DustCtx *ctx, uint32_t width, uint32_t height, uint32_t shard_count,
                             const void *gathered, void *out);
+
+/* Multi-GPU exchange step (the reference renders on one GPU): one process and one DustCtx
+ * per GPU, every rank traces its shard (DustTraceConfig.shard_index / shard_count) into a compact device
+ * buffer, ONE all-gather over NVLink/NVSwitch (ncclAllGather on the context's stream) concatenates the
+ * shard buffers in rank order, dust_resolve_shards un-permutes.  Rank 0 obtains the 128-byte id with
+ * dust_comm_unique_id and hands it to the other ranks over the host's own channel; dust_comm_init is
+ * collective (all ranks call it).  NCCL is bound with dlopen("libnccl.so.2") at the first call. */
+#define DUST_COMM_ID_BYTES 128
+int32_t dust_comm_unique_id(uint8_t *id_out);
+int32_t dust_comm_init(DustCtx *ctx, const uint8_t *id, int32_t rank, int32_t nranks);
+int32_t dust_comm_destroy(DustCtx *ctx);
+/* shard, gathered: device pointers; gathered holds nranks * bytes_per_rank bytes */
+int32_t dust_allgather_framebuffer(DustCtx *ctx, const void *shard, uint64_t bytes_per_rank, void *gathered);
 
 int32_t dust_get_stats(DustCtx *ctx, DustStats *out);
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (dust_[a-z0-9_]+)", out))
     assert set(names) <= exported
-    assert lib.dust_abi_version() == 2
+    assert lib.dust_abi_version() == 3
 
 
 def test_ctypes_structs_match_header(tmp_path):
