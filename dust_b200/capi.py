@@ -25,7 +25,8 @@ DUST_TRACE_PIPELINE_MEGAKERNEL = 4
 DUST_TRACE_PIPELINE_WAVEFRONT = 8
 PIPELINE_FLAGS = {None: 0, "auto": 0, "megakernel": 4, "wavefront": 8}
 DUST_MEM_HOST, DUST_MEM_DEVICE = 0, 1
-DUST_FMT_RGBA32F, DUST_FMT_RGBA16F = 0, 1
+DUST_FMT_RGBA32F, DUST_FMT_RGBA16F, DUST_FMT_YCOCG16F = 0, 1, 2
+DUST_TRACE_DEMODULATE = 16
 
 
 class DustError(RuntimeError):
@@ -95,6 +96,14 @@ class DustFrame(C.Structure):
     ]
 
 
+class DustExposureParams(C.Structure):
+    _fields_ = [("min_log_luminance", C.c_float), ("log_luminance_range", C.c_float), ("time_coefficient", C.c_float)]
+
+
+class DustToneMapParams(C.Structure):
+    _fields_ = [("color_space_conversion", C.c_float * 9), ("output_transfer_function", C.c_uint32), ("dst_format", C.c_uint32)]
+
+
 class DustStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded", "kernel_launches")]
@@ -129,6 +138,14 @@ SYMBOLS = {
     "dust_comm_init": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "dust_comm_destroy": (C.c_int32, [C.c_void_p]),
     "dust_allgather_framebuffer": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "dust_exposure_create": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dust_exposure_destroy": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "dust_exposure_get": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "dust_exposure_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_float]),
+    "dust_auto_exposure": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.POINTER(DustExposureParams), C.POINTER(C.c_float)]),
+    "dust_tone_map": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.POINTER(DustToneMapParams), C.c_void_p]),
     "dust_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(DustStats)]),
 }
 DUST_COMM_ID_BYTES = 128

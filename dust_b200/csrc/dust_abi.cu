@@ -2,6 +2,7 @@
 // instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
 // launches sm_100a kernels or fails.
 #include "wavefront.cuh"
+#include "post.cuh"
 
 #include <cstdlib>
 #include <dlfcn.h>
@@ -49,6 +50,10 @@ struct DustTree {
     const uchar4 *palette_raw = nullptr;
     uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0;
     int32_t bmin[3] = { 0, 0, 0 }, bmax[3] = { 0, 0, 0 };   // occupied bounds in object voxels
+};
+
+struct DustExposure {
+    DHistogram *d = nullptr;
 };
 
 struct DustScene {
@@ -733,7 +738,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     const bool want_hits = (cfg.flags & DUST_TRACE_WRITE_HITS) != 0;
     if (want_hits && (cfg.shard_count != 1 || !frame->hit_instance || !frame->hit_leaf || !frame->hit_voxel || !frame->hit_t))
         return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "hit buffers need shard_count == 1 and all four arrays");
-    if (frame->radiance_format != DUST_FMT_RGBA32F && frame->radiance_format != DUST_FMT_RGBA16F)
+    if (frame->radiance_format != DUST_FMT_RGBA32F && frame->radiance_format != DUST_FMT_RGBA16F && frame->radiance_format != DUST_FMT_YCOCG16F)
         return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad radiance format");
     const DustGBuffer *gb = frame->gbuffer;
     if (gb && cfg.shard_count != 1) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "the G-buffer needs shard_count == 1");
@@ -764,6 +769,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
         for (int a = 0; a < 3; a++) p.sun_nee[a] = su[a] * sun_cone;
     }
     p.tiles_x = (cfg.width + 31) / 32; p.tiles_y = (cfg.height + 31) / 32; p.n_local_tiles = tiles_per_shard;
+    p.ycocg = frame->radiance_format == DUST_FMT_YCOCG16F;
 
     uint8_t *scratch = nullptr;
     size_t off_hi = 0, off_hl = 0, off_hv = 0, off_ht = 0, off_gb[5] = { 0, 0, 0, 0, 0 };
@@ -954,6 +960,110 @@ int32_t dust_resolve_shards(DustCtx *ctx, uint32_t width, uint32_t height, uint3
                                                  shard_count, (width + 31) / 32, tiles_per_shard);
     CU_TRY(ctx, cudaGetLastError());
     count_launch(ctx);
+    return DUST_OK;
+}
+
+// ---- post chain (post.cuh) ---------------------------------------------------------------------------
+
+int32_t dust_exposure_create(DustCtx *ctx, DustExposure **out)
+{
+    if (!ctx || !out) return DUST_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DustExposure *e = new (std::nothrow) DustExposure();
+    if (!e) return fail(ctx, DUST_ERR_OUT_OF_MEMORY, "host allocation failed");
+    if (cudaMalloc(&e->d, sizeof(DHistogram)) != cudaSuccess) { delete e; return fail(ctx, DUST_ERR_OUT_OF_MEMORY, "cudaMalloc(histogram)"); }
+    CU_TRY(ctx, cudaMemsetAsync(e->d, 0, sizeof(DHistogram), ctx->stream));          // fill_buffer(&mut buffer, 0), auto_exposure.rs:116-118
+    *out = e;
+    return DUST_OK;
+}
+
+int32_t dust_exposure_destroy(DustCtx *ctx, DustExposure *exposure)
+{
+    if (!ctx || !exposure) return DUST_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (exposure->d) cudaFree(exposure->d);
+    delete exposure;
+    return DUST_OK;
+}
+
+int32_t dust_exposure_get(DustCtx *ctx, const DustExposure *exposure, float *avg_out)
+{
+    if (!ctx || !exposure || !avg_out) return DUST_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpyAsync(avg_out, &exposure->d->avg, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DUST_OK;
+}
+
+int32_t dust_exposure_set(DustCtx *ctx, DustExposure *exposure, float avg)
+{
+    if (!ctx || !exposure) return DUST_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpyAsync(&exposure->d->avg, &avg, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DUST_OK;
+}
+
+int32_t dust_auto_exposure(DustCtx *ctx, DustExposure *exposure, const void *illuminance, uint32_t width, uint32_t height,
+                           uint32_t memory, const DustExposureParams *params, float *avg_out)
+{
+    if (!ctx || !exposure || !illuminance || !params || !width || !height) return DUST_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = (uint64_t)width * height;
+    const uint2 *img = static_cast<const uint2 *>(illuminance);
+    if (memory == DUST_MEM_HOST) {
+        const int32_t rc = ensure_scratch(ctx, n * 8);
+        if (rc != DUST_OK) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->scratch, illuminance, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        img = static_cast<const uint2 *>(ctx->scratch);
+    } else if (memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n / 2 + 255) / 256 + 1, (uint64_t)ctx->sms * 8);
+    exposure_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(img, n, params->min_log_luminance, 1.0f / params->log_luminance_range, exposure->d);
+    count_launch(ctx);
+    exposure_average_kernel<<<1, 256, 0, ctx->stream>>>(exposure->d, width * height, params->min_log_luminance, params->log_luminance_range,
+                                                        params->time_coefficient);
+    count_launch(ctx);
+    CU_TRY(ctx, cudaGetLastError());
+    if (avg_out) {
+        CU_TRY(ctx, cudaMemcpyAsync(avg_out, &exposure->d->avg, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return DUST_OK;
+}
+
+int32_t dust_tone_map(DustCtx *ctx, const DustExposure *exposure, const void *illuminance, const uint32_t *albedo,
+                      uint32_t width, uint32_t height, uint32_t memory, const DustToneMapParams *params, void *dst)
+{
+    if (!ctx || !exposure || !illuminance || !albedo || !params || !dst || !width || !height) return DUST_ERR_INVALID_ARGUMENT;
+    if (params->dst_format != DUST_FMT_RGBA32F && params->dst_format != DUST_FMT_RGBA16F) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad dst_format");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = (uint64_t)width * height;
+    const size_t dst_bytes = n * (params->dst_format == DUST_FMT_RGBA32F ? 16 : 8);
+    const uint2 *img = static_cast<const uint2 *>(illuminance);
+    const uint32_t *alb = albedo;
+    void *d_dst = dst;
+    if (memory == DUST_MEM_HOST) {
+        const size_t off_alb = align_up(n * 8, 256), off_dst = off_alb + align_up(n * 4, 256);
+        const int32_t rc = ensure_scratch(ctx, off_dst + dst_bytes);
+        if (rc != DUST_OK) return rc;
+        uint8_t *s = static_cast<uint8_t *>(ctx->scratch);
+        CU_TRY(ctx, cudaMemcpyAsync(s, illuminance, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(s + off_alb, albedo, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        img = reinterpret_cast<const uint2 *>(s); alb = reinterpret_cast<const uint32_t *>(s + off_alb); d_dst = s + off_dst;
+    } else if (memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    ToneMapParams tp;
+    memcpy(tp.csc, params->color_space_conversion, sizeof tp.csc);
+    tp.oetf = params->output_transfer_function; tp.dst_format = params->dst_format;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sms * 8);
+    tone_map_kernel<<<grid, 256, 0, ctx->stream>>>(img, alb, n, exposure->d, tp, d_dst);
+    count_launch(ctx);
+    CU_TRY(ctx, cudaGetLastError());
+    if (memory == DUST_MEM_HOST) {
+        CU_TRY(ctx, cudaMemcpyAsync(dst, d_dst, dst_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return DUST_OK;
 }
 

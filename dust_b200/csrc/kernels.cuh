@@ -33,6 +33,7 @@ struct FrameParams {
     uint32_t slot_log2;        // 2^slot_log2 threads share a pixel, each takes every 2^slot_log2-th sample
     float4 *radiance32;
     __half *radiance16;
+    uint32_t ycocg;            // radiance16 holds REBLUR_FrontEnd_PackRadianceAndNormHitDist's YCoCg (DUST_FMT_YCOCG16F)
     uint32_t *hit_instance, *hit_leaf;
     uint8_t *hit_voxel;
     float *hit_t;
@@ -89,6 +90,25 @@ __device__ __forceinline__ f3 surface_at(const DSceneView &sc, const Hit &h, f3 
     ro = mk3((t * rd.x + ro.x) + sn.x * 0.01f, (t * rd.y + ro.y) + sn.y * 0.01f, (t * rd.z + ro.z) + sn.z * 0.01f);
     if (STATS) st.hits_shaded++;
     return mk3(c.x, c.y, c.z);
+}
+
+// Pixel store shared by both pipelines: RGBA32F / RGBA16F ACEScg, or the `img_illuminance` encoding the
+// reference's post chain reads (headers/nrd.glsl:99-147: Y, Co, Cg; normHitDist is NRD-only and stored as 1).
+__device__ __forceinline__ void store_radiance(float4 *radiance32, __half *radiance16, uint32_t ycocg, uint32_t index, float r, float g, float b)
+{
+    if (radiance32) radiance32[index] = make_float4(r, g, b, 1.0f);
+    if (radiance16) {
+        if (ycocg) {                                                               // _NRD_LinearToYCoCg
+            const float Y = (r * 0.25f + g * 0.5f) + b * 0.25f;
+            const float Co = (r * 0.5f + g * 0.0f) + b * -0.5f;
+            const float Cg = (r * -0.25f + g * 0.5f) + b * -0.25f;
+            r = Y; g = Co; b = Cg;
+        }
+        const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, 1.0f);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&lo); pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(radiance16)[index] = pk;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ G-buffer
@@ -241,7 +261,10 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_FRAME_MIN_BLOCKS) frame_ker
                     uint32_t pidx = 0;
                     const f3 a = surface_at<STATS>(p.scene, h, ro, rd, sn, st, &pidx);
                     if (want_gb) gbuffer_store(p.gb, p.scene, pixel_index, true, h.t, h.inst, h.voxel, pidx, ro0, rd, sn);
-                    if (kind == RAY_PRIMARY) { T = a; v = 0; }                         // tone_map.comp:195-203
+                    if (kind == RAY_PRIMARY) {                                         // tone_map.comp:195-203 (the albedo factor;
+                        if (!(cfg.flags & DUST_TRACE_DEMODULATE)) T = a;               //  left to tone_map when demodulated)
+                        v = 0;
+                    }
                     else { T.x = T.x * a.x; T.y = T.y * a.y; T.z = T.z * a.z; v += 1; }   // final_gather.rchit:76-80
                     to_vertex = true;
                 } else need_sky = true;
@@ -291,14 +314,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_FRAME_MIN_BLOCKS) frame_ker
     if (have_pixel && slot == 0) {
         const uint32_t out_index = cfg.shard_count > 1 ? lt * 1024u + ly * 32u + lx : pixel_index;
         const float n = (float)cfg.spp;
-        const float4 outv = make_float4(acc.x / n, acc.y / n, acc.z / n, 1.0f);
-        if (p.radiance32) p.radiance32[out_index] = outv;
-        if (p.radiance16) {
-            __half2 a = __floats2half2_rn(outv.x, outv.y), b = __floats2half2_rn(outv.z, outv.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t *>(&a); pk.y = *reinterpret_cast<uint32_t *>(&b);
-            reinterpret_cast<uint2 *>(p.radiance16)[out_index] = pk;
-        }
+        store_radiance(p.radiance32, p.radiance16, p.ycocg, out_index, acc.x / n, acc.y / n, acc.z / n);
     }
     if (STATS) flush_counters(p.counters, st);
 }

@@ -158,8 +158,7 @@ struct Walk {
     f3 o, d, inv;                    // object-space ray, exact 1/d
     int jx, jy, jz;                  // current cell
     int L4;                          // != 0: the cell of that edge (leaf units) containing (jx,jy,jz) is empty / done: leave it first
-    float t_exit;
-    uint32_t bnd0, bnd1, bnd2;       // occupied bounds per axis: lo | size << 16
+    float t_exit, t_box;             // inclusive end of the walk (box exit or padded tmax); exit time of the occupied bounds
     const DNode16 *n16;
     const uint2 *blocks;
     const uint4 *mids, *leaves;
@@ -167,8 +166,6 @@ struct Walk {
     uint32_t mid_lo, mid_hi, mid_base;
     uint32_t inst, leaf_i;
     bool have_mid;                   // the 4^3 node of the current 16-cell is in registers
-    bool have_n16;                   // 4-level trees: n16_i / blk_lo / blk_hi describe the 16^3 node of the current 256-cell
-    uint32_t n16_i;
     bool four;                       // this instance has 4 levels
 };
 
@@ -185,7 +182,6 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     object_ray(in, ro, rd, w.o, w.d);
     w.inv = mk3(1.0f / w.d.x, 1.0f / w.d.y, 1.0f / w.d.z);
     const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(in.bounds));
-    w.bnd0 = bw.x; w.bnd1 = bw.y; w.bnd2 = bw.z;
     const int bx0 = (int)(bw.x & 0xFFFFu) << 2, by0 = (int)(bw.y & 0xFFFFu) << 2, bz0 = (int)(bw.z & 0xFFFFu) << 2;
     const int bx1 = bx0 + ((int)(bw.x >> 16) << 2), by1 = by0 + ((int)(bw.y >> 16) << 2), bz1 = bz0 + ((int)(bw.z >> 16) << 2);
     // plane times are (plane - o) * inv: difference first, plane*inv - o*inv would cancel (|o/d| >> t)
@@ -194,7 +190,8 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     const float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
     // walk a hair past tmax (acceptance stays exact): DESIGN.md "Traversal semantics"
     const float tmax_pad = cur + (fabsf(cur) * 3.814697265625e-06f + 9.5367431640625e-07f);
-    w.t_exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_pad));
+    w.t_box = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    w.t_exit = fminf(w.t_box, tmax_pad);
     if (!(t_enter <= w.t_exit) || bx1 <= bx0) return false;
     const int ix = __float2int_rd(__fmaf_rn(w.d.x, t_enter, w.o.x));
     const int iy = __float2int_rd(__fmaf_rn(w.d.y, t_enter, w.o.y));
@@ -208,7 +205,6 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     if (NL == 0) w.four = bw.w == 4u;
     if (NL == 3 || (NL == 0 && !w.four)) { const uint2 b = __ldg(w.blocks); w.blk_lo = b.x; w.blk_hi = b.y; }
     w.have_mid = false;
-    w.have_n16 = false;
     w.L4 = 0;
     return true;
 }
@@ -230,47 +226,45 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         const float ty = ((float)((py_ ? cy + L4 : cy) << 2) - w.o.y) * w.inv.y;
         const float tz = ((float)((pz_ ? cz + L4 : cz) << 2) - w.o.z) * w.inv.z;
         const float t_next = fminf(fminf(tx, ty), tz);
-        bool out = !(t_next <= w.t_exit);                             // inclusive
+        // inclusive end; a stepping axis that leaves the occupied bounds has t_next >= t_box (same float
+        // expressions as the bounds planes, see the CPU checker): ONE comparison, no per-axis range checks
+        if (!(t_next <= w.t_exit) || !(t_next < w.t_box)) { w.L4 = 0; return WS_OUT; }
         int nx = w.jx, ny = w.jy, nz = w.jz;
         // axes whose plane time ties the minimum step one cell; the others are re-derived from the ray at
         // t_next and clamped into the cell's own range — a no-op at leaf granularity when L4 == 1
-        if (tx <= t_next) { nx = px_ ? cx + L4 : cx - 1; out |= (uint32_t)(nx - (int)(w.bnd0 & 0xFFFFu)) >= (w.bnd0 >> 16); }
+        if (tx <= t_next) nx = px_ ? cx + L4 : cx - 1;
         else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.x, t_next, w.o.x)) >> 2; nx = min(max(ip, cx), cx + L4 - 1); }
-        if (ty <= t_next) { ny = py_ ? cy + L4 : cy - 1; out |= (uint32_t)(ny - (int)(w.bnd1 & 0xFFFFu)) >= (w.bnd1 >> 16); }
+        if (ty <= t_next) ny = py_ ? cy + L4 : cy - 1;
         else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.y, t_next, w.o.y)) >> 2; ny = min(max(ip, cy), cy + L4 - 1); }
-        if (tz <= t_next) { nz = pz_ ? cz + L4 : cz - 1; out |= (uint32_t)(nz - (int)(w.bnd2 & 0xFFFFu)) >= (w.bnd2 >> 16); }
+        if (tz <= t_next) nz = pz_ ? cz + L4 : cz - 1;
         else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.z, t_next, w.o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
         // the cached 4^3 node survives a step that stays inside its 16-cell
-        const uint32_t moved = (uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz));
-        w.have_mid = w.have_mid && ((moved >> 2) == 0u);
-        if (NL != 3) w.have_n16 = w.have_n16 && ((moved >> 6) == 0u);       // ... and so does the 16^3 node inside its 256-cell
+        w.have_mid = w.have_mid && (((uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz)) >> 2) == 0u);
         w.jx = nx; w.jy = ny; w.jz = nz;
         w.L4 = 0;
-        if (out) return WS_OUT;
     }
     const int jx = w.jx, jy = w.jy, jz = w.jz;
     const bool four = NL == 4 || (NL == 0 && w.four);
     if (!w.have_mid) {
         const DNode16 *node = w.n16;
+        uint32_t blo = w.blk_lo, bhi = w.blk_hi;
         if (four) {
-            if (!w.have_n16) {
-                const uint2 tb = __ldg(w.blocks);
-                if (STATS) st.mask_words++;
-                if (!bit64(tb.x, tb.y, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
-                const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
-                const uint4 q = __ldg(&node->word[tidx >> 6]);
-                if (STATS) st.mask_words++;
-                const uint32_t b = tidx & 63u;
-                if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
-                if (STATS) st.child_ptrs++;
-                w.n16_i = q.z + rank64(q.x, q.y, b);
-                const uint2 cb = __ldg(w.blocks + w.n16_i);
-                w.blk_lo = cb.x; w.blk_hi = cb.y;
-                w.have_n16 = true;
-            } else if (STATS) { st.mask_words += 2; st.child_ptrs++; }
-            node = w.n16 + w.n16_i;
+            // (keeping the 16^3 node of the current 256-cell in registers, like the 4^3 node below, was tried:
+            //  these words are L1 hits and the extra state cost more than the three loads — config 5 lost 9 %)
+            const uint2 tb = __ldg(w.blocks);
+            if (STATS) st.mask_words++;
+            if (!bit64(tb.x, tb.y, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
+            const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
+            const uint4 q = __ldg(&node->word[tidx >> 6]);
+            if (STATS) st.mask_words++;
+            const uint32_t b = tidx & 63u;
+            if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
+            if (STATS) st.child_ptrs++;
+            const uint32_t ni = q.z + rank64(q.x, q.y, b);
+            node = w.n16 + ni;
+            const uint2 cb = __ldg(w.blocks + ni);
+            blo = cb.x; bhi = cb.y;
         }
-        const uint32_t blo = w.blk_lo, bhi = w.blk_hi;
         if (STATS) st.mask_words++;
         if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
         const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
@@ -328,7 +322,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     if (live) cull_begin(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc);
 
     Walk w;
-    w.four = NL == 4; w.have_mid = false; w.have_n16 = false; w.n16_i = 0; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
+    w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
     for (;;) {
         // ---- phase 1: cull
         while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc, st);

@@ -27,12 +27,14 @@ __device__ __forceinline__ f3 normalize3(f3 v)
 __device__ __forceinline__ float signf(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-// bit `i` (0..63) of the 64-bit mask (lo, hi), and the number of set bits below it — 32-bit ops only
-__device__ __forceinline__ bool bit64(uint32_t lo, uint32_t hi, uint32_t i) { return (((i & 32u) ? hi : lo) >> (i & 31u)) & 1u; }
+// bit `i` (0..63) of the 64-bit mask (lo, hi): one 64-bit funnel shift (SHF.R.U64) + one LOP3
+__device__ __forceinline__ bool bit64(uint32_t lo, uint32_t hi, uint32_t i) { return (uint32_t)(u64_of(lo, hi) >> i) & 1u; }
+// number of set bits below bit `i`, which MUST itself be set (every caller has just tested it): shifting
+// bit i up to bit 63 leaves exactly the bits <= i, so the count is popc - 1 (2 SHF + 2 POPC + 1 IADD3,
+// where the select-by-word form took 14 instructions on the saturated ALU pipe, profiles/r01_history.md)
 __device__ __forceinline__ uint32_t rank64(uint32_t lo, uint32_t hi, uint32_t i)
 {
-    const uint32_t below = (1u << (i & 31u)) - 1u;
-    return (i & 32u) ? __popc(lo) + __popc(hi & below) : __popc(lo & below);
+    return (uint32_t)__popcll(u64_of(lo, hi) << (63u - i)) - 1u;
 }
 
 // headers/spatial_hash.glsl:105-111

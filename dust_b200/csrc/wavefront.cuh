@@ -189,11 +189,14 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
 #ifndef DUST_PT_MIN_BLOCKS2
 #define DUST_PT_MIN_BLOCKS2 8                 // 64 registers: 8 CTAs / SM beat 6 with no spills that matter (A/B in profiles/r01_history.md)
 #endif
+#ifndef DUST_PT_MIN_BLOCKS4
+#define DUST_PT_MIN_BLOCKS4 8                 // the same for 4-level / mixed scenes
+#endif
 
 enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
 
 template <int NL, bool STATS>
-__global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work)
+__global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : DUST_PT_MIN_BLOCKS4) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work)
 {
     __shared__ uint32_t s_cand[WF_CANDS * DUST_THREADS];
     const unsigned full = 0xffffffffu;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_PT_MIN_BLOCKS2) wf_trace_pt
     int mode = W_NEXT, j = 0;                                          // j == WF_CANDS or key 0xFFFFFFFF: list exhausted
     bool exhausted = true;
     Walk w;
-    w.four = NL == 4; w.have_mid = false; w.have_n16 = false; w.n16_i = 0; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
+    w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
 
 #pragma unroll 1
     for (;;) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
                 uint32_t pidx = 0;
                 const f3 al = surface_at<STATS>(p.f.scene, h, ro, rd, sn, st, &pidx);   // ro becomes the offset hit point
                 if (want_gb) gbuffer_store(p.f.gb, p.f.scene, py * cfg.width + px, true, h.t, h.inst, h.voxel, pidx, ro0, rd, sn);
-                if (p.depth == 0) T = al;                                               // tone_map.comp:195-203
+                if (p.depth == 0) { if (!(cfg.flags & DUST_TRACE_DEMODULATE)) T = al; }   // tone_map.comp:195-203
                 else { T.x = T.x * al.x; T.y = T.y * al.y; T.z = T.z * al.z; }          // final_gather.rchit:76-80
                 if (dot3(mk3(p.f.sky.direction[0], p.f.sky.direction[1], p.f.sky.direction[2]), sn) > 0.0f) {   // ambient_occlusion.rgen:33-50
                     if (STATS) st.shadow_rays++;
@@ -447,14 +450,7 @@ __global__ void __launch_bounds__(256) wf_resolve(const __grid_constant__ WfPara
     }
     if (!p.last_batch) { p.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f); return; }
     const float n = (float)p.f.cfg.spp;
-    const float4 outv = make_float4(acc.x / n, acc.y / n, acc.z / n, 1.0f);
-    if (p.f.radiance32) p.f.radiance32[oi] = outv;
-    if (p.f.radiance16) {
-        __half2 a = __floats2half2_rn(outv.x, outv.y), b = __floats2half2_rn(outv.z, outv.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t *>(&a); pk.y = *reinterpret_cast<uint32_t *>(&b);
-        reinterpret_cast<uint2 *>(p.f.radiance16)[oi] = pk;
-    }
+    store_radiance(p.f.radiance32, p.f.radiance16, p.f.ycocg, oi, acc.x / n, acc.y / n, acc.z / n);
 }
 
 }  // namespace dust

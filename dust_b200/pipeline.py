@@ -151,12 +151,14 @@ class Scene:
 
     # ---- dust_trace ------------------------------------------------------------------------------
     def trace(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0,
-              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None, pipeline=None, gbuffer=False):
+              shard_index=0, shard_count=1, hits=False, stats=False, fmt=DUST_FMT_RGBA32F, out=None, pipeline=None, gbuffer=False,
+              demodulate=False):
         """Host-buffer call: returns dict(radiance[H,W,4], hit_instance, hit_leaf, hit_voxel, hit_t).
         pipeline: None / "auto", "megakernel" or "wavefront" (DUST_TRACE_PIPELINE_*; same results)."""
         ctx, lib = self.ctx, self.ctx.lib
         cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count,
-                              (DUST_TRACE_WRITE_HITS if hits else 0) | (DUST_TRACE_STATS if stats else 0) | PIPELINE_FLAGS[pipeline])
+                              (DUST_TRACE_WRITE_HITS if hits else 0) | (DUST_TRACE_STATS if stats else 0) | PIPELINE_FLAGS[pipeline] |
+                              (capi.DUST_TRACE_DEMODULATE if demodulate else 0))
         res = {}
         if shard_count == 1:
             n_out, shape = width * height, (height, width, 4)
@@ -214,6 +216,56 @@ class Scene:
         ctx = self.ctx
         check(ctx.h, ctx.lib.dust_trace_rays(ctx.h, self.h, _ptr(rays), n, _ptr(hits), DUST_MEM_DEVICE,
                                              DUST_TRACE_STATS if stats else 0), "dust_trace_rays")
+
+
+class Exposure:
+    """The reference's Histogram buffer + the two post passes (dust_auto_exposure, dust_tone_map).
+    Images are numpy arrays (host) or torch CUDA tensors (device): illuminance [H,W,4] float16 in
+    DUST_FMT_YCOCG16F, albedo [H,W] uint32 (DustGBuffer.albedo)."""
+    IDENTITY = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+
+    def __init__(self, ctx: Context, min_log_luminance=-6.0, max_log_luminance=8.5, time_coefficient=0.2):
+        self.ctx = ctx
+        self.params = capi.DustExposureParams(min_log_luminance, max_log_luminance - min_log_luminance, time_coefficient)
+        h = C.c_void_p()
+        check(ctx.h, ctx.lib.dust_exposure_create(ctx.h, C.byref(h)), "dust_exposure_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.dust_exposure_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def avg(self) -> float:
+        v = C.c_float()
+        check(self.ctx.h, self.ctx.lib.dust_exposure_get(self.ctx.h, self.h, C.byref(v)), "dust_exposure_get")
+        return float(v.value)
+
+    @avg.setter
+    def avg(self, value: float):
+        check(self.ctx.h, self.ctx.lib.dust_exposure_set(self.ctx.h, self.h, float(value)), "dust_exposure_set")
+
+    @staticmethod
+    def _mem(buf):
+        return DUST_MEM_HOST if isinstance(buf, np.ndarray) else DUST_MEM_DEVICE
+
+    def update(self, illuminance, width, height, read_back=True):
+        """auto_exposure.comp + auto_exposure_avg.comp; returns the adapted luminance when read_back."""
+        v = C.c_float()
+        check(self.ctx.h, self.ctx.lib.dust_auto_exposure(self.ctx.h, self.h, _ptr(illuminance), width, height, self._mem(illuminance),
+                                                          C.byref(self.params), C.byref(v) if read_back else None), "dust_auto_exposure")
+        return float(v.value) if read_back else None
+
+    def tone_map(self, illuminance, albedo, width, height, dst, csc=IDENTITY, oetf=1):
+        fmt = DUST_FMT_RGBA32F if (dst.dtype == np.float32 if isinstance(dst, np.ndarray) else dst.element_size() == 4) else DUST_FMT_RGBA16F
+        tp = capi.DustToneMapParams((C.c_float * 9)(*csc), oetf, fmt)
+        check(self.ctx.h, self.ctx.lib.dust_tone_map(self.ctx.h, self.h, _ptr(illuminance), _ptr(albedo), width, height, self._mem(illuminance),
+                                                     C.byref(tp), _ptr(dst)), "dust_tone_map")
+        return dst
 
 
 def shard_layout(width, height, shard_count):

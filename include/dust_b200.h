@@ -101,7 +101,11 @@ enum {
     DUST_TRACE_STATS      = 2u,   /* count rays / visited words; read back with dust_get_stats */
     /* pipeline override (default: chosen per frame).  Results are bit-identical either way. */
     DUST_TRACE_PIPELINE_MEGAKERNEL = 4u,   /* one launch, a path stays in its thread */
-    DUST_TRACE_PIPELINE_WAVEFRONT  = 8u    /* rays re-ordered between path vertices (frames with bounces) */
+    DUST_TRACE_PIPELINE_WAVEFRONT  = 8u,   /* rays re-ordered between path vertices (frames with bounces) */
+    /* Leave the primary-hit albedo factor out of the radiance (the reference's img_illuminance holds the
+     * incoming light; tone_map.comp:192-203 multiplies DustGBuffer.albedo back in): radiance for
+     * dust_tone_map.  Default (flag clear): the product, i.e. tone_map's `mapped` before exposure. */
+    DUST_TRACE_DEMODULATE = 16u
 };
 
 /* Replaces the push constants + launch size of the four vkCmdTraceRaysKHR dispatches
@@ -117,7 +121,9 @@ typedef struct DustTraceConfig {
 } DustTraceConfig;
 
 enum { DUST_MEM_HOST = 0, DUST_MEM_DEVICE = 1 };
-enum { DUST_FMT_RGBA32F = 0, DUST_FMT_RGBA16F = 1 };
+/* radiance formats: ACEScg RGBA as float / half, or the reference's img_illuminance encoding
+ * REBLUR_FrontEnd_PackRadianceAndNormHitDist (headers/nrd.glsl:99-147): half (Y, Co, Cg, 1) */
+enum { DUST_FMT_RGBA32F = 0, DUST_FMT_RGBA16F = 1, DUST_FMT_YCOCG16F = 2 };
 
 /* Replaces the GBuffer images the reference writes (standard.rs:880-917).  With shard_count == 1
  * every array is row-major width*height.  With shard_count > 1 `radiance` is the compact
@@ -213,6 +219,35 @@ int32_t dust_comm_init(DustCtx *ctx, const uint8_t *id, int32_t rank, int32_t nr
 int32_t dust_comm_destroy(DustCtx *ctx);
 /* shard, gathered: device pointers; gathered holds nranks * bytes_per_rank bytes */
 int32_t dust_allgather_framebuffer(DustCtx *ctx, const void *shard, uint64_t bytes_per_rank, void *gathered);
+
+/* ---- post chain: the two compute passes the reference runs on the traced frame ----
+ * DustExposure = the reference's Histogram buffer {uint histogram[256]; float avg;} (auto_exposure.playout),
+ * zero-filled at creation like auto_exposure.rs:116-118.  dust_auto_exposure = auto_exposure.comp +
+ * auto_exposure_avg.comp on an illuminance image in DUST_FMT_YCOCG16F (AutoExposurePipeline::render,
+ * crates/render/src/pipeline/auto_exposure.rs:96-224); dust_tone_map = tone_map.comp (ToneMappingPipeline::render,
+ * crates/render/src/pipeline/tone_mapping.rs).  `memory` says where the images live; `avg_out` (may be NULL) is a
+ * host float that receives the adapted luminance — passing it makes the call synchronous. */
+typedef struct DustExposure DustExposure;
+typedef struct DustExposureParams {     /* ExposureSettings, auto_exposure.rs:229-247 (defaults -6.0, 8.5 - -6.0, 0.2) */
+    float min_log_luminance;
+    float log_luminance_range;          /* max_log_luminance - min_log_luminance */
+    float time_coefficient;
+} DustExposureParams;
+typedef struct DustToneMapParams {
+    float color_space_conversion[9];    /* COLOR_SPACE_CONVERSION_0..8 (tone_map.comp:15-23), column-major mat3 */
+    uint32_t output_transfer_function;  /* OUTPUT_TRANSFER_FUNCTION 0..8 (tone_map.comp:12, 98-167) */
+    uint32_t dst_format;                /* DUST_FMT_RGBA32F or DUST_FMT_RGBA16F */
+} DustToneMapParams;
+int32_t dust_exposure_create(DustCtx *ctx, DustExposure **out);
+int32_t dust_exposure_destroy(DustCtx *ctx, DustExposure *exposure);
+/* read / seed the adapted luminance (Histogram.avg); both synchronise the context's stream */
+int32_t dust_exposure_get(DustCtx *ctx, const DustExposure *exposure, float *avg_out);
+int32_t dust_exposure_set(DustCtx *ctx, DustExposure *exposure, float avg);
+int32_t dust_auto_exposure(DustCtx *ctx, DustExposure *exposure, const void *illuminance, uint32_t width, uint32_t height,
+                           uint32_t memory, const DustExposureParams *params, float *avg_out);
+/* albedo: DustGBuffer.albedo (A2R10G10B10_UNORM_PACK32); dst: width*height pixels of dst_format */
+int32_t dust_tone_map(DustCtx *ctx, const DustExposure *exposure, const void *illuminance, const uint32_t *albedo,
+                      uint32_t width, uint32_t height, uint32_t memory, const DustToneMapParams *params, void *dst);
 
 int32_t dust_get_stats(DustCtx *ctx, DustStats *out);
 

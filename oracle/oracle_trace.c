@@ -323,7 +323,8 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
      * walk enters at tmax + 1 ulp.  Acceptance itself stays exact (tmin <= t <= tmax); the pad only
      * makes the result independent of how far tmax was already shrunk by other instances. */
     float tmax_pad = tmax + (fabsf(tmax) * 3.814697265625e-06f + 9.5367431640625e-07f);
-    float t_exit = fminf(fminf(hi[0], hi[1]), fminf(hi[2], tmax_pad));
+    float t_box = fminf(fminf(hi[0], hi[1]), hi[2]);
+    float t_exit = fminf(t_box, tmax_pad);
     if (!(t_enter <= t_exit) || bmax[0] <= bmin[0]) return 0;
     int32_t iv[3];
     for (int a = 0; a < 3; a++) {
@@ -379,10 +380,16 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
         /* inclusive: a cell entered exactly at tmax may still hold a hit at t == tmax (accepted by
          * reportIntersectionEXT); keeps the closest-hit result independent of instance order */
         if (!(t_next <= t_exit)) return 0;
+        /* Leaving the occupied bounds: a stepping axis whose plane is a bounds plane (or lies beyond it,
+         * for a cell that sticks out of the bounds) has exactly / at least that plane's time, and the
+         * stepping axes carry the minimum, so "some stepping axis leaves [bmin, bmax)" implies
+         * t_next >= t_box — the same float expressions on both sides.  The walk therefore ends on this ONE
+         * comparison (no per-axis range checks), and since non-stepping axes stay inside their cell, the
+         * coordinates can never leave the tree's domain either. */
+        if (!(t_next < t_box)) return 0;
         for (int a = 0; a < 3; a++) {
             if (tx[a] <= t_next) {
                 iv[a] = d[a] > 0.0f ? cmin[a] + L : cmin[a] - 1;
-                if (iv[a] < bmin[a] || iv[a] >= bmax[a]) return 0;
             } else {
                 int32_t ip = (int32_t)floorf(fmaf(d[a], t_next, o[a]));
                 iv[a] = ip < cmin[a] ? cmin[a] : (ip > cmin[a] + L - 1 ? cmin[a] + L - 1 : ip);
@@ -608,7 +615,7 @@ static void shade_pixel(const Frame *F, uint32_t px, uint32_t py, OStats *st)
             }
             if (smp == 0 && F->gb) gbuffer_hit(F, pixel_index, &h, &sf, o, d);
             float T[3];                             /* throughput, starts at the primary albedo (tone_map.comp:195-203) */
-            for (int a = 0; a < 3; a++) T[a] = o_srgb_to_linear(sf.albedo[a]);
+            for (int a = 0; a < 3; a++) T[a] = (cfg->flags & O_TRACE_DEMODULATE) ? 1.0f : o_srgb_to_linear(sf.albedo[a]);
             for (uint32_t v = 0;; v++) {
                 /* sun next-event estimation: ambient_occlusion.rgen:33-50, nee.rmiss:11-22 */
                 if (dot3(F->sky->direction, sf.n) > 0.0f) {

@@ -54,7 +54,9 @@ typedef struct OTraceConfig {
     uint32_t max_bounces;
     uint32_t seed, frame_index;
     uint32_t y0, y1;             /* rows rendered: [y0, y1) */
+    uint32_t flags;              /* O_TRACE_* */
 } OTraceConfig;
+#define O_TRACE_DEMODULATE 1u    /* radiance without the primary-hit albedo factor (img_illuminance; tone_map.comp:192-203 multiplies it back) */
 
 typedef struct OStats {
     uint64_t primary_rays, bounce_rays, shadow_rays;

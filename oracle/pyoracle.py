@@ -50,7 +50,16 @@ class OCamera(C.Structure):
 
 
 class OTraceConfig(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("width", "height", "spp", "max_bounces", "seed", "frame_index", "y0", "y1")]
+    _fields_ = [(n, C.c_uint32) for n in ("width", "height", "spp", "max_bounces", "seed", "frame_index", "y0", "y1", "flags")]
+O_TRACE_DEMODULATE = 1
+
+
+class OExposureParams(C.Structure):
+    _fields_ = [("min_log_lum", C.c_float), ("log_lum_range", C.c_float), ("time_coeff", C.c_float)]
+
+
+class OHistogram(C.Structure):
+    _fields_ = [("histogram", C.c_uint32 * 256), ("avg", C.c_float)]
 
 
 class OStats(C.Structure):
@@ -122,6 +131,11 @@ def lib() -> C.CDLL:
         "o_camera_ray": (None, [C.POINTER(OCamera), u32, u32, u32, u32, f32, f32, pf32, pf32]),
         "o_pcg": (u32, [u32]), "o_cossin_2pi": (None, [f32, pf32, pf32]),
         "o_rotate_by_normal": (None, [pf32, pf32, pf32]), "o_world2obj": (None, [pf32, pf32]),
+        "o_half_to_float": (f32, [C.c_uint16]), "o_float_to_half": (C.c_uint16, [f32]), "o_post_log2": (f32, [f32]),
+        "o_color_to_bin": (u32, [pf32, C.POINTER(OExposureParams)]),
+        "o_exposure_histogram": (None, [vp, u32, u32, C.POINTER(OExposureParams), C.POINTER(OHistogram)]),
+        "o_exposure_average": (None, [C.POINTER(OHistogram), u32, u32, C.POINTER(OExposureParams)]),
+        "o_tone_map": (None, [vp, vp, u32, u32, f32, pf32, u32, vp]),
         "o_dense_from_tree": (vp, [vp]), "o_dense_free": (None, [vp]),
         "o_dense_march": (i32, [vp, C.POINTER(f64), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
     }
@@ -345,13 +359,13 @@ class Scene:
         lib().o_scene_set_previous(self._h, a.ctypes.data)
 
     def render(self, camera, sky, width, height, spp=1, max_bounces=0, seed=0, frame_index=0, y0=0, y1=None,
-               hits=True, threads=None, rows=None, gbuffer=False):
+               hits=True, threads=None, rows=None, gbuffer=False, demodulate=False):
         """rows: optional list of rows rendered in ONE call (the other rows of the returned frame stay zero).
         gbuffer: also return the G-buffer images of the sample-0 primary hit (motion as float16, like the image)."""
         cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
         sk = sky if isinstance(sky, OSky) else as_struct(OSky, sky)
         y1 = height if y1 is None else y1
-        cfg = OTraceConfig(width, height, spp, max_bounces, seed, frame_index, y0, y1)
+        cfg = OTraceConfig(width, height, spp, max_bounces, seed, frame_index, y0, y1, O_TRACE_DEMODULATE if demodulate else 0)
         rad = np.zeros((height, width, 4), np.float32)
         res = {"radiance": rad}
         hp = [None] * 4
@@ -399,6 +413,45 @@ class Scene:
         st = OStats()
         lib().o_trace_rays(self._h, rays.ctypes.data, len(rays), hits.ctypes.data, C.byref(st), threads or os.cpu_count() or 1)
         return hits, st.as_dict()
+
+
+# ---- post chain (oracle_post.c) ----------------------------------------------------------------------
+
+def pack_illuminance(radiance):
+    """REBLUR_FrontEnd_PackRadianceAndNormHitDist of an ACEScg float32 frame -> [H,W,4] float16 (Y, Co, Cg, 1):
+    the DUST_FMT_YCOCG16F image (headers/nrd.glsl:99-147; same float expression order as the kernel)."""
+    r, g, b = (np.asarray(radiance[..., k], np.float32) for k in range(3))
+    f = np.float32
+    out = np.empty(radiance.shape[:-1] + (4,), np.float32)
+    out[..., 0] = (r * f(0.25) + g * f(0.5)) + b * f(0.25)
+    out[..., 1] = (r * f(0.5) + g * f(0.0)) + b * f(-0.5)
+    out[..., 2] = (r * f(-0.25) + g * f(0.5)) + b * f(-0.25)
+    out[..., 3] = 1.0
+    with np.errstate(over="ignore"):
+        return out.astype(np.float16)
+
+
+def exposure_update(illuminance16, avg, min_log_lum=-6.0, log_lum_range=14.5, time_coeff=0.2):
+    """auto_exposure.comp + auto_exposure_avg.comp on a [H,W,4] float16 image; returns (histogram[256], new avg)."""
+    img = np.ascontiguousarray(illuminance16, dtype=np.float16)
+    h, w = img.shape[:2]
+    p = OExposureParams(min_log_lum, log_lum_range, time_coeff)
+    hist = OHistogram()
+    hist.avg = avg
+    lib().o_exposure_histogram(img.ctypes.data, w, h, C.byref(p), C.byref(hist))
+    bins = np.array(hist.histogram[:], np.uint32)
+    lib().o_exposure_average(C.byref(hist), w, h, C.byref(p))
+    return bins, float(hist.avg)
+
+
+def tone_map(illuminance16, albedo, avg, csc=(1, 0, 0, 0, 1, 0, 0, 0, 1), oetf=1):
+    img = np.ascontiguousarray(illuminance16, dtype=np.float16)
+    alb = np.ascontiguousarray(albedo, dtype=np.uint32)
+    h, w = img.shape[:2]
+    dst = np.empty((h, w, 4), np.float32)
+    m = (C.c_float * 9)(*[float(v) for v in csc])
+    lib().o_tone_map(img.ctypes.data, alb.ctypes.data, w, h, avg, m, oetf, dst.ctypes.data)
+    return dst
 
 
 def leaf_dda(origin, direction, grid, tmin=0.0):
