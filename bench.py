@@ -437,6 +437,24 @@ def rays_config(args, cfg):
     peak, peak_src = measured_peak()
     achieved = alg / (ms * 1e-3) / 1e9
     hit_frac = float((d_hits[:, 1] != -1).float().mean().item())
+    # ---- CPU baseline beside it: the oracle port on all host threads over the first rays of the same batch,
+    # and (it is the checker, after all) a bit-for-bit comparison of those rays with the GPU's answers
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        desc = dom.describe()
+        osc = po.Scene([(ident, po.TreeView(desc)._h, dom.materials, dom.palette)])
+        n_cal = min(n, 100_000)
+        t0 = time.perf_counter()
+        osc.trace_rays(rays[:n_cal])
+        rate = n_cal / max(time.perf_counter() - t0, 1e-6)
+        n_cpu = int(max(n_cal, min(n, 12.0 * rate)))
+        t0 = time.perf_counter()
+        o_hits, _ = osc.trace_rays(rays[:n_cpu])
+        dt = time.perf_counter() - t0
+        same = bool(np.array_equal(o_hits.view(np.uint32).reshape(-1, 4), d_hits[:n_cpu].cpu().numpy().view(np.uint32)))
+        cpu = {"value": n_cpu / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"first {n_cpu} rays of the same batch, {dt:.1f} s", "gpu_hits_bit_exact_on_sample": same}
     line = {
         "metric": "Mrays/s, random-origin ray batch on the synthetic 4096^3 VDB", "value": world * n / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -447,7 +465,7 @@ def rays_config(args, cfg):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "wf_trace_pt<4> (persistent lanes, %d launch(es))" % (launches // args.steps), "kernel_ms": ms,
                      "algorithmic_bytes_per_launch": alg, "bytes_per_ray": alg / n, "peak_source": peak_src},
-        "cpu_baseline": None,
+        "cpu_baseline": cpu,
         "e2e": {"value": n_e2e / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n_e2e * 32, "d2h_bytes_per_step": n_e2e * 16,
                 "api": "dust_trace_rays(DUST_MEM_HOST), %d rays per call" % n_e2e},
         "gpu_launches": int(launches), "clocks": clk,

@@ -220,4 +220,61 @@ private:
     uint32_t frame_index_ = 0;
 };
 
+// ExposureSettings (crates/render/src/pipeline/auto_exposure.rs:229-247) and the two post passes with
+// the reference's names.  AutoExposurePipeline owns the Histogram buffer the way the reference keeps
+// it in a shared state (auto_exposure.rs:108-118); ToneMappingPipeline reads it (tone_mapping.rs).
+struct ExposureSettings {
+    float min_log_luminance = -6.0f, max_log_luminance = 8.5f;
+    float time_coefficient = 0.2f;
+    float default_value = 0.0f, current = 0.0f;
+};
+
+class AutoExposurePipeline {
+public:
+    explicit AutoExposurePipeline(DustCtx *ctx) : ctx_(ctx) { status_ = dust_exposure_create(ctx, &buffer_); }
+    ~AutoExposurePipeline() { if (buffer_) dust_exposure_destroy(ctx_, buffer_); }
+    AutoExposurePipeline(const AutoExposurePipeline &) = delete;
+    AutoExposurePipeline &operator=(const AutoExposurePipeline &) = delete;
+    // illuminance: device image in DUST_FMT_YCOCG16F; enqueues both passes, returns the buffer (like the
+    // reference's RenderRes<SharedDeviceState<ResidentBuffer>>) or nullptr on error
+    DustExposure *render(const void *illuminance_image, uint32_t width, uint32_t height, const ExposureSettings &settings)
+    {
+        if (!buffer_) return nullptr;
+        const DustExposureParams p{ settings.min_log_luminance, settings.max_log_luminance - settings.min_log_luminance, settings.time_coefficient };
+        status_ = dust_auto_exposure(ctx_, buffer_, illuminance_image, width, height, DUST_MEM_DEVICE, &p, nullptr);
+        return status_ == DUST_OK ? buffer_ : nullptr;
+    }
+    int32_t last_status() const { return status_; }
+
+private:
+    DustCtx *ctx_;
+    DustExposure *buffer_ = nullptr;
+    int32_t status_ = DUST_OK;
+};
+
+class ToneMappingPipeline {
+public:
+    // color_space_conversion / transfer function: the specialisation constants the reference derives from
+    // the swapchain's colour space (tone_map.comp:12-23)
+    ToneMappingPipeline(DustCtx *ctx, const float color_space_conversion[9], uint32_t output_transfer_function) : ctx_(ctx)
+    {
+        for (int i = 0; i < 9; ++i) params_.color_space_conversion[i] = color_space_conversion[i];
+        params_.output_transfer_function = output_transfer_function;
+        params_.dst_format = DUST_FMT_RGBA16F;
+    }
+    bool render(const void *src_illuminance, const uint32_t *albedo, void *dst, uint32_t dst_format, uint32_t width, uint32_t height,
+                const DustExposure *exposure)
+    {
+        params_.dst_format = dst_format;
+        status_ = dust_tone_map(ctx_, exposure, src_illuminance, albedo, width, height, DUST_MEM_DEVICE, &params_, dst);
+        return status_ == DUST_OK;
+    }
+    int32_t last_status() const { return status_; }
+
+private:
+    DustCtx *ctx_;
+    DustToneMapParams params_{};
+    int32_t status_ = DUST_OK;
+};
+
 }  // namespace dust::render
