@@ -161,6 +161,10 @@ struct Walk {
     float t_exit, t_box;             // inclusive end of the walk (box exit or padded tmax); exit time of the occupied bounds
     const DNode16 *n16;
     const uint2 *blocks;
+#ifdef DUST_TMA_TOP
+    const uint4 *topw;               // 64 words of the root 16^3 node: global, or the CTA's TMA-staged shared copy (generic loads)
+    const uint2 *topb;               // its block mask (4-level trees)
+#endif
     const uint4 *mids, *leaves;
     uint32_t blk_lo, blk_hi;         // block mask of the 16^3 node above the mids (kept in registers for 3-level trees)
     uint32_t mid_lo, mid_hi, mid_base;
@@ -202,6 +206,9 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     w.mids = reinterpret_cast<const uint4 *>(p01.y);
     w.leaves = in.leaves;
     w.blocks = in.blocks;
+#ifdef DUST_TMA_TOP
+    w.topw = w.n16->word; w.topb = w.blocks;
+#endif
     if (NL == 0) w.four = bw.w == 4u;
     if (NL == 3 || (NL == 0 && !w.four)) { const uint2 b = __ldg(w.blocks); w.blk_lo = b.x; w.blk_hi = b.y; }
     w.have_mid = false;
@@ -251,11 +258,19 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (four) {
             // (keeping the 16^3 node of the current 256-cell in registers, like the 4^3 node below, was tried:
             //  these words are L1 hits and the extra state cost more than the three loads — config 5 lost 9 %)
+#ifdef DUST_TMA_TOP
+            const uint2 tb = *w.topb;
+#else
             const uint2 tb = __ldg(w.blocks);
+#endif
             if (STATS) st.mask_words++;
             if (!bit64(tb.x, tb.y, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
             const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
+#ifdef DUST_TMA_TOP
+            const uint4 q = w.topw[tidx >> 6];
+#else
             const uint4 q = __ldg(&node->word[tidx >> 6]);
+#endif
             if (STATS) st.mask_words++;
             const uint32_t b = tidx & 63u;
             if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
@@ -269,7 +284,11 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
         const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
         if (STATS) st.mask_words++;
+#ifdef DUST_TMA_TOP
+        const uint4 q = four ? __ldg(&node->word[ridx >> 6]) : w.topw[ridx >> 6];
+#else
         const uint4 q = __ldg(&node->word[ridx >> 6]);
+#endif
         const uint32_t b = ridx & 63u;
         if (!bit64(q.x, q.y, b)) { w.L4 = 4; return WS_WALK; }
         const uint4 mid = __ldg(&w.mids[q.z + rank64(q.x, q.y, b)]);

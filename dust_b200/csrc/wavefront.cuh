@@ -218,6 +218,32 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
     Walk w;
     w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
 
+#ifdef DUST_TMA_TOP
+    // Experiment (profiles/r01_history.md): single-instance scenes stage the root 16^3 node (64 x 16 B) and its
+    // block mask in shared memory with one TMA bulk copy per CTA; the walk then reads them with generic loads.
+    __shared__ __align__(128) uint4 s_top[64];
+    __shared__ __align__(16) uint2 s_topb[2];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const bool staged = sc.n_inst == 1;
+    if (staged) {
+        const DInstance &in0 = sc.inst[0];
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(1024u + 16u));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(s_top)), "l"(in0.n16), "r"(1024u), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(s_topb)), "l"(in0.blocks), "r"(16u), "r"(bar) : "memory");
+        }
+        __syncthreads();
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
+#endif
+
 #pragma unroll 1
     for (;;) {
         const uint32_t packed = __reduce_add_sync(full, mode < W_DEAD ? (1u << (8 * mode)) : 0u);
@@ -260,7 +286,12 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                     ++j;
                     if (j == WF_CANDS) exhausted = true;
                     if (key == 0xFFFFFFFFu || __uint_as_float(key & ~id_mask) > cur) exhausted = true;   // end of list / sorted: nothing further can beat the best hit
-                    else if (walk_enter<NL, STATS>(sc, w, key & id_mask, ro, rd, tmin, cur, st)) { mode = W_WALK; entered = true; }
+                    else if (walk_enter<NL, STATS>(sc, w, key & id_mask, ro, rd, tmin, cur, st)) {
+                        mode = W_WALK; entered = true;
+#ifdef DUST_TMA_TOP
+                        if (staged) { w.topw = s_top; w.topb = s_topb; }
+#endif
+                    }
                 }
                 need = !entered && exhausted;
             }
