@@ -273,10 +273,16 @@ def ours(args, cfg):
             ev[k][2].record()
         ev[k][1].record()
     torch.cuda.synchronize()
+    launches = ctx.stats()["kernel_launches"] - launches0
+    # K short steps can end before nvidia-smi's first 100 ms tick: keep the same load running (untimed) until
+    # the sampler has seen at least ~0.8 s of it, so the clocks line describes the load that was timed
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.8:
+        step()
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clk = clocks.stop()
-    launches = ctx.stats()["kernel_launches"] - launches0
     step_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
     kern_ms = sum(a.elapsed_time(c) for a, _, c in ev) / args.steps      # the trace kernel alone (same stream)
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
@@ -412,10 +418,14 @@ def rays_config(args, cfg):
         scene.trace_rays_device(d_rays, d_hits, n)
         ev[k][1].record()
     torch.cuda.synchronize()
+    launches = ctx.stats()["kernel_launches"] - launches0
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.8:                       # see ours(): enough nvidia-smi samples under the same load
+        scene.trace_rays_device(d_rays, d_hits, n)
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clk = clocks.stop()
-    launches = ctx.stats()["kernel_launches"] - launches0
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -443,7 +453,8 @@ def rays_config(args, cfg):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as po
         desc = dom.describe()
-        osc = po.Scene([(ident, po.TreeView(desc)._h, dom.materials, dom.palette)])
+        otree = po.TreeView(desc)                                   # a view of the same host tree (kept alive with the scene)
+        osc = po.Scene([(ident, otree._h, dom.materials, dom.palette)])
         n_cal = min(n, 100_000)
         t0 = time.perf_counter()
         osc.trace_rays(rays[:n_cal])
