@@ -211,7 +211,7 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
         hit = ((cell >> 2) & 0x30) | ((cell >> 1) & 0xC) | (cell & 3);
         mx += kx ? dx : 0.0f; my += ky ? dy : 0.0f; mz += kz ? dz : 0.0f;          // :110
     }
-    t_out = hitDistance / 1.0f;                                         // :115
+    t_out = hitDistance / 1.0f + 0.0f;                                  // :115; + 0.0f: canonical +0 (see the CPU checker)
     voxel = (uint32_t)hit;
     return true;
 }

@@ -266,7 +266,9 @@ int o_leaf_dda(const float origin[3], const float dir[3], uint64_t grid, float r
         if ((pos[0] | pos[1] | pos[2]) & ~3) return 0;
         hit = ((uint32_t)pos[0] << 4) | ((uint32_t)pos[1] << 2) | (uint32_t)pos[2];          /* :112 */
     }
-    *t_out = hitDistance / 1.0f;                                        /* :115 */
+    /* :115.  "+ 0.0f": a ray that starts inside a set voxel exactly on a leaf plane reports max(-0, +0), whose
+     * sign IEEE leaves open (glibc's fmaxf and PTX max.f32 disagree); -0 + +0 = +0 makes t canonical. */
+    *t_out = hitDistance / 1.0f + 0.0f;
     *voxel_out = hit;
     return 1;
 }

@@ -220,6 +220,28 @@ def test_ray_batch_small_domain(oracle, host, ctx):
     assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
 
 
+def test_ray_batch_origins_on_lattice_planes(oracle, host, ctx):
+    """Rays that start ON voxel / leaf / node planes (integer origins, tmin = 0), many of them inside set voxels:
+    t = 0 hits must come out as the canonical +0.0 on both sides (max(-0, +0) is not defined by IEEE), and
+    plane-time ties at the very first step must not change a result."""
+    from dust_b200 import scenes
+    from dust_b200.pipeline import Scene
+    dom = host.SynthDomain(seed=7, fill=0.05, domain_leaves=64)
+    desc = dom.describe()
+    scene = Scene(ctx, [(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), ctx.upload_tree(desc))])
+    rays = scenes.ray_batch(400_000, dom.extent, seed=9)
+    rays["o"] = np.round(rays["o"])                                   # every origin on the voxel lattice
+    rays["o"][::2] = np.round(rays["o"][::2] / 4) * 4                 # every other one on the leaf lattice
+    rays["d"][::5, 1] = 0.0                                           # and some axis-parallel / zero components
+    g = scene.trace_rays(rays)
+    otree = oracle.TreeView(desc)
+    o, _ = oracle.Scene([(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), otree._h, dom.materials, dom.palette)]).trace_rays(rays)
+    zero = (o["instance"] != 0xFFFFFFFF) & (o["t"] == 0.0)
+    assert zero.sum() > 1000
+    assert (o["t"][zero].view(np.uint32) == 0).all()                  # +0.0, never -0.0
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+
+
 def test_ray_batch_many_instances(castle_small, host, monkeypatch):
     """dust_trace_rays on a multi-instance scene: pre-culled candidate lists + persistent lanes (and the
     one-thread-per-ray kernel, DUST_RAYS_PLAIN) against the oracle's linear instance loop, bit for bit."""
