@@ -128,6 +128,7 @@ SYMBOLS = {
     "dust_tree_device_bytes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dust_scene_create": (C.c_int32, [C.c_void_p, C.POINTER(DustInstance), C.c_uint32, C.POINTER(C.c_void_p)]),
     "dust_scene_destroy": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "dust_scene_update_transforms": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "dust_scene_set_previous_transforms": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "dust_trace": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(DustCamera), C.POINTER(DustSky),
                                C.POINTER(DustTraceConfig), C.POINTER(DustFrame)]),

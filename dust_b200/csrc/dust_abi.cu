@@ -21,6 +21,7 @@ struct DustCtx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = { nullptr, nullptr };   // dust_trace_rays(DUST_MEM_HOST): copy / compute overlap across chunks
     std::string err;
     // scratch for DUST_MEM_HOST frames / ray batches
     void *scratch = nullptr;
@@ -62,6 +63,8 @@ struct DustScene {
     float4 *d_prev = nullptr;        // last frame's object -> world rows (3 per instance)
     DSceneView view{};               // device pointers + root box, passed to the kernels by value
     uint32_t n_inst = 0, n_bvh = 0, max_levels = 3, min_levels = 3;
+    std::vector<const DustTree *> trees;   // per instance, for dust_scene_update_transforms
+    std::vector<float> o2w;                // current object -> world rows (12 per instance)
 };
 
 namespace {
@@ -485,6 +488,7 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
     if (ctx->d_wf_counters) cudaFree(ctx->d_wf_counters);
+    for (int k = 0; k < 2; k++) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DUST_OK;
@@ -613,18 +617,18 @@ int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out)
     return DUST_OK;
 }
 
-int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t n, DustScene **out)
+// Instance records, padded world boxes and the SAH BVH over them for `n` (tree, transform) pairs.
+static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *trees, const float *o2w, std::vector<DInstance> &inst,
+                            std::vector<DBvhNode> &nodes, Box &root_box, int &root_ref, uint32_t &max_levels, uint32_t &min_levels)
 {
-    if (!ctx || !out || (n && !instances)) return DUST_ERR_INVALID_ARGUMENT;
-    *out = nullptr;
-    std::vector<DInstance> inst(n);
+    inst.assign(n, DInstance{});
     std::vector<Box> boxes(n);
-    uint32_t max_levels = 3, min_levels = 4;
+    max_levels = 3; min_levels = 4;
     for (uint32_t k = 0; k < n; k++) {
-        const DustTree *t = instances[k].tree;
+        const DustTree *t = trees[k];
         if (!t) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "instance without a tree");
         DInstance &d = inst[k];
-        const float *m = instances[k].obj2world;
+        const float *m = o2w + 12 * (size_t)k;
         world2obj(m, d.w2o);
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
         d.n_levels = t->n_levels;
@@ -653,9 +657,10 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         boxes[k] = b;
     }
     if (n > (1u << 20)) return fail(ctx, DUST_ERR_UNSUPPORTED, "more than 2^20 instances");
-    std::vector<DBvhNode> nodes;
-    Box root_box{};
-    int root_ref = -1, depth = 0;
+    nodes.clear();
+    root_box = Box{};
+    root_ref = -1;
+    int depth = 0;
     if (n) {
         std::vector<uint32_t> ids(n);
         for (uint32_t k = 0; k < n; k++) ids[k] = k;
@@ -663,18 +668,42 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         root_ref = build_bvh(nodes, ids, boxes, 0, n, root_box, 0, depth);
         if (depth > DUST_MAX_BVH_DEPTH) return fail(ctx, DUST_ERR_UNSUPPORTED, "instance BVH deeper than the traversal stack");
     }
+    return DUST_OK;
+}
+
+static void scene_set_view(DustScene *s, const Box &root_box, int root_ref)
+{
+    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh; s->view.prev_o2w = s->d_prev;
+    for (int a = 0; a < 3; a++) { s->view.root_lo[a] = root_box.lo[a]; s->view.root_hi[a] = root_box.hi[a]; }
+    s->view.root_ref = root_ref; s->view.n_inst = s->n_inst;
+    s->view.id_bits = 8;                                   // candidate key = entry t (high bits) | instance (low id_bits)
+    while ((1u << s->view.id_bits) < s->n_inst) s->view.id_bits++;
+}
+
+int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t n, DustScene **out)
+{
+    if (!ctx || !out || (n && !instances)) return DUST_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::vector<const DustTree *> trees(n);
+    std::vector<float> o2w(12 * (size_t)n);
+    for (uint32_t k = 0; k < n; k++) { trees[k] = instances[k].tree; memcpy(&o2w[12 * (size_t)k], instances[k].obj2world, 12 * sizeof(float)); }
+    std::vector<DInstance> inst;
+    std::vector<DBvhNode> nodes;
+    Box root_box{};
+    int root_ref = -1;
+    uint32_t max_levels = 3, min_levels = 4;
+    const int32_t rc = scene_arrays(ctx, n, trees.data(), o2w.data(), inst, nodes, root_box, root_ref, max_levels, min_levels);
+    if (rc != DUST_OK) return rc;
     DustScene *s = new (std::nothrow) DustScene();
     if (!s) return DUST_ERR_OUT_OF_MEMORY;
     s->n_inst = n; s->n_bvh = (uint32_t)nodes.size(); s->max_levels = max_levels; s->min_levels = std::min(min_levels, max_levels);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (n) {
         cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * std::max<size_t>(nodes.size(), 1));
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * (size_t)n);           // a binary tree over n leaves has n - 1 nodes
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream);
-        std::vector<float> prev(12 * (size_t)n);
-        for (uint32_t k = 0; k < n; k++) memcpy(&prev[12 * (size_t)k], instances[k].obj2world, 12 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&s->d_prev, sizeof(float) * 12 * n);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_prev, prev.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_prev, o2w.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess && !nodes.empty()) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
@@ -685,12 +714,34 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
             return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e));
         }
     }
-    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh; s->view.prev_o2w = s->d_prev;
-    for (int a = 0; a < 3; a++) { s->view.root_lo[a] = root_box.lo[a]; s->view.root_hi[a] = root_box.hi[a]; }
-    s->view.root_ref = root_ref; s->view.n_inst = n;
-    s->view.id_bits = 8;                                   // candidate key = entry t (high bits) | instance (low id_bits)
-    while ((1u << s->view.id_bits) < n) s->view.id_bits++;
+    s->trees = std::move(trees);
+    s->o2w = std::move(o2w);
+    scene_set_view(s, root_box, root_ref);
     *out = s;
+    return DUST_OK;
+}
+
+int32_t dust_scene_update_transforms(DustCtx *ctx, DustScene *scene, const float *obj2world, uint32_t n)
+{
+    if (!ctx || !scene || (n && !obj2world)) return DUST_ERR_INVALID_ARGUMENT;
+    if (n != scene->n_inst) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "one transform per instance");
+    if (!n) return DUST_OK;
+    std::vector<DInstance> inst;
+    std::vector<DBvhNode> nodes;
+    Box root_box{};
+    int root_ref = -1;
+    uint32_t max_levels = 3, min_levels = 4;
+    const int32_t rc = scene_arrays(ctx, n, scene->trees.data(), obj2world, inst, nodes, root_box, root_ref, max_levels, min_levels);
+    if (rc != DUST_OK) return rc;                                        // the scene is unchanged on error
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // this frame's transforms become "last frame" for DustGBuffer.motion (PreviousFrameGlobalTransform, standard.rs:845-854)
+    CU_TRY(ctx, cudaMemcpyAsync(scene->d_prev, scene->o2w.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(scene->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!nodes.empty()) CU_TRY(ctx, cudaMemcpyAsync(scene->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));                     // stream-ordered after the frames in flight; host arrays die at return
+    memcpy(scene->o2w.data(), obj2world, sizeof(float) * 12 * n);
+    scene->n_bvh = (uint32_t)nodes.size();
+    scene_set_view(scene, root_box, root_ref);
     return DUST_OK;
 }
 
@@ -862,24 +913,60 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     return DUST_OK;
 }
 
+// One chunk (<= 16 Mi rays) of a ray batch on `stream`: wf_cull (multi-instance scenes) + wf_trace_pt + the overflow pass.
+// `counters`: 4 words (overflow count, pad, 64-bit work counter); `cand`: cn * 36 bytes of scratch when need_cull.
+static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const DustRay *d_rays, DustHit *d_hits, uint32_t cn, cudaStream_t stream,
+                                    uint32_t *counters, uint8_t *cand, bool need_cull, bool plain, bool stats, int nl)
+{
+    WfParams p;
+    memset(&p, 0, sizeof p);
+    p.f.scene = scene->view;
+    p.f.counters = ctx->d_counters;
+    p.n_paths = cn;
+    p.hits_out = d_hits;
+    WfQueue q;
+    q.a = reinterpret_cast<float4 *>(const_cast<DustRay *>(d_rays)); q.b = q.a + 1; q.path = nullptr; q.stride = 2;
+    const uint32_t grid = (cn + DUST_THREADS - 1) / DUST_THREADS;
+    uint32_t *ovf_count = counters;
+    unsigned long long *work = reinterpret_cast<unsigned long long *>(counters + 2);
+    auto trace = [&](const uint32_t *count, const uint32_t *list) {
+        if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); }
+        else if (nl == 4) { if (stats) wf_trace<4, true><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); else wf_trace<4, false><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); }
+        else { if (stats) wf_trace<0, true><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); else wf_trace<0, false><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); }
+        count_launch(ctx);
+    };
+    if (plain) { trace(nullptr, nullptr); return cudaGetLastError(); }
+    cudaError_t le = cudaMemsetAsync(counters, 0, 16, stream);
+    if (le != cudaSuccess) return le;
+    if (need_cull) {
+        p.cand = reinterpret_cast<uint4 *>(cand);
+        p.overflow = reinterpret_cast<uint32_t *>(cand + align_up((size_t)cn * 32, 256));
+        if (stats) wf_cull<true><<<grid, DUST_THREADS, 0, stream>>>(p, q, nullptr, ovf_count);
+        else wf_cull<false><<<grid, DUST_THREADS, 0, stream>>>(p, q, nullptr, ovf_count);
+        count_launch(ctx);
+    }
+    auto launch = [&](auto kernel) {
+        int per_sm = 0;
+        le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
+        const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
+        kernel<<<pgrid, DUST_THREADS, 0, stream>>>(p, q, nullptr, work);
+    };
+    if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
+    else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
+    else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
+    count_launch(ctx);
+    if (need_cull) trace(ovf_count, p.overflow);                       // rays whose candidate list overflowed
+    return le != cudaSuccess ? le : cudaGetLastError();
+}
+
 int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *rays, uint64_t n, DustHit *hits,
                         uint32_t memory, uint32_t flags)
 {
     if (!ctx || !scene || (n && (!rays || !hits))) return DUST_ERR_INVALID_ARGUMENT;
     if (n == 0) return DUST_OK;
+    if (memory != DUST_MEM_HOST && memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const DustRay *d_rays = rays;
-    DustHit *d_hits = hits;
-    uint8_t *scratch = nullptr;
-    const size_t ray_bytes = align_up((size_t)n * sizeof(DustRay), 256);
-    if (memory == DUST_MEM_HOST) {
-        int32_t rc = ensure_scratch(ctx, ray_bytes + (size_t)n * sizeof(DustHit));
-        if (rc != DUST_OK) return rc;
-        scratch = static_cast<uint8_t *>(ctx->scratch);
-        CU_TRY(ctx, cudaMemcpyAsync(scratch, rays, (size_t)n * sizeof(DustRay), cudaMemcpyHostToDevice, ctx->stream));
-        d_rays = reinterpret_cast<const DustRay *>(scratch);
-        d_hits = reinterpret_cast<DustHit *>(scratch + ray_bytes);
-    } else if (memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    const bool host = memory == DUST_MEM_HOST;
     const bool stats = (flags & DUST_TRACE_STATS) != 0;
     if (stats) CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DCounters), ctx->stream));
     const int nl = scene->n_inst == 0 || scene->min_levels == scene->max_levels ? (scene->n_inst ? (int)scene->max_levels : 3) : 0;
@@ -889,62 +976,55 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     // (wf_trace_pt), fed by pre-culled candidate lists (wf_cull) when the scene has more than one instance.
     const bool plain = std::getenv("DUST_RAYS_PLAIN") != nullptr;                         // A/B only: one thread per ray
     const bool need_cull = !plain && scene->n_inst > 1;
-    const uint64_t chunk_max = need_cull ? (16ull << 20) : (1ull << 30);
-    if (need_cull) {
-        const size_t need = align_up((size_t)std::min<uint64_t>(n, chunk_max) * 32, 256) + (size_t)std::min<uint64_t>(n, chunk_max) * 4;
-        if (need > ctx->wf_scratch_bytes) {
-            if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
-            CU_TRY(ctx, cudaMalloc(&ctx->wf_scratch, need));
-            ctx->wf_scratch_bytes = need;
-        }
+    // Device buffers: chunks of <= 16 Mi rays, back to back on the context's stream.  Host buffers: chunks of 2 Mi
+    // rays ping-pong over two side streams, so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the
+    // kernels of chunk k (both copy engines + the SMs busy; needs pinned host memory to overlap, works without).
+    uint64_t chunk_max = host ? (2ull << 20) : (need_cull ? (16ull << 20) : (1ull << 30));
+    if (const char *e = std::getenv("DUST_RAYS_CHUNK")) chunk_max = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));   // tests: force several chunks
+    const int n_slots = host ? 2 : 1;
+    const size_t cand_slot = need_cull ? align_up(align_up((size_t)std::min<uint64_t>(n, chunk_max) * 32, 256) + (size_t)std::min<uint64_t>(n, chunk_max) * 4, 256) : 0;
+    if (cand_slot * n_slots > ctx->wf_scratch_bytes) {
+        if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
+        CU_TRY(ctx, cudaMalloc(&ctx->wf_scratch, cand_slot * n_slots));
+        ctx->wf_scratch_bytes = cand_slot * n_slots;
+    }
+    const DustRay *d_rays = rays;
+    DustHit *d_hits = hits;
+    cudaEvent_t ev = nullptr;
+    if (host) {
+        const size_t ray_bytes = align_up((size_t)n * sizeof(DustRay), 256);
+        const int32_t rc = ensure_scratch(ctx, ray_bytes + (size_t)n * sizeof(DustHit));
+        if (rc != DUST_OK) return rc;
+        d_rays = reinterpret_cast<const DustRay *>(ctx->scratch);
+        d_hits = reinterpret_cast<DustHit *>(static_cast<uint8_t *>(ctx->scratch) + ray_bytes);
+        for (int k = 0; k < 2; k++)
+            if (!ctx->side[k]) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU_TRY(ctx, cudaEventRecord(ev, ctx->stream));                                     // side streams start after the work already queued
+        for (int k = 0; k < 2; k++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->side[k], ev, 0));
     }
     cudaError_t le = cudaSuccess;
-    for (uint64_t first = 0; first < n; first += chunk_max) {
+    uint32_t slot = 0;
+    for (uint64_t first = 0; first < n && le == cudaSuccess; first += chunk_max, slot ^= 1u) {
         const uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_max, n - first);
-        WfParams p;
-        memset(&p, 0, sizeof p);
-        p.f.scene = scene->view;
-        p.f.counters = ctx->d_counters;
-        p.n_paths = cn;
-        p.hits_out = d_hits + first;
-        WfQueue q;
-        q.a = reinterpret_cast<float4 *>(const_cast<DustRay *>(d_rays + first)); q.b = q.a + 1; q.path = nullptr; q.stride = 2;
-        const uint32_t grid = (cn + DUST_THREADS - 1) / DUST_THREADS;
-        uint32_t *ovf_count = ctx->d_wf_counters;
-        unsigned long long *work = reinterpret_cast<unsigned long long *>(ctx->d_wf_counters + 2);
-        auto trace = [&](const uint32_t *count, const uint32_t *list) {
-            if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
-            else if (nl == 4) { if (stats) wf_trace<4, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<4, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
-            else { if (stats) wf_trace<0, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<0, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
-            count_launch(ctx);
-        };
-        if (plain) { trace(nullptr, nullptr); continue; }
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_wf_counters, 0, 16, ctx->stream));
-        if (need_cull) {
-            p.cand = static_cast<uint4 *>(ctx->wf_scratch);
-            p.overflow = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ctx->wf_scratch) + align_up((size_t)std::min<uint64_t>(n, chunk_max) * 32, 256));
-            if (stats) wf_cull<true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, nullptr, ovf_count);
-            else wf_cull<false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, nullptr, ovf_count);
-            count_launch(ctx);
+        cudaStream_t st = host ? ctx->side[slot] : ctx->stream;
+        const uint32_t sl = host ? slot : 0u;
+        if (host) le = cudaMemcpyAsync(const_cast<DustRay *>(d_rays) + first, rays + first, (size_t)cn * sizeof(DustRay), cudaMemcpyHostToDevice, st);
+        if (le == cudaSuccess)
+            le = launch_ray_chunk(ctx, scene, d_rays + first, d_hits + first, cn, st, ctx->d_wf_counters + 4 * sl,
+                                  static_cast<uint8_t *>(ctx->wf_scratch) + cand_slot * sl, need_cull, plain, stats, nl);
+        if (host && le == cudaSuccess) le = cudaMemcpyAsync(hits + first, d_hits + first, (size_t)cn * sizeof(DustHit), cudaMemcpyDeviceToHost, st);
+    }
+    if (host) {
+        for (int k = 0; k < 2; k++) {                                                      // join the side streams back into the context's stream
+            if (cudaEventRecord(ev, ctx->side[k]) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, ev, 0);
+            cudaStreamSynchronize(ctx->side[k]);
         }
-        auto launch = [&](auto kernel) {
-            int per_sm = 0;
-            le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
-            const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
-            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, nullptr, work);
-        };
-        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
-        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
-        else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
-        count_launch(ctx);
-        if (need_cull) trace(ovf_count, p.overflow);                   // rays whose candidate list overflowed
+        cudaEventDestroy(ev);
     }
     CU_TRY(ctx, le);
     CU_TRY(ctx, cudaGetLastError());
-    if (memory == DUST_MEM_HOST) {
-        CU_TRY(ctx, cudaMemcpyAsync(hits, scratch + ray_bytes, (size_t)n * sizeof(DustHit), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (host) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (stats) return fetch_counters(ctx);
     return DUST_OK;
 }

@@ -135,6 +135,13 @@ class Scene:
         self.h = h
         self.n_instances = len(instances)
 
+    def update_transforms(self, obj2world):
+        """New object->world matrices [n_instances, 12] for the same trees (moving instances); the old ones become
+        last frame's for DustGBuffer.motion."""
+        a = np.ascontiguousarray(np.asarray(obj2world, dtype=np.float32).reshape(-1, 12))
+        check(self.ctx.h, self.ctx.lib.dust_scene_update_transforms(self.ctx.h, self.h, a.ctypes.data, len(a)),
+              "dust_scene_update_transforms")
+
     def set_previous_transforms(self, obj2world_prev):
         """Last frame's object->world matrices, [n_instances, 12] (DustGBuffer.motion, hit.rchit:90-94)."""
         a = np.ascontiguousarray(np.asarray(obj2world_prev, dtype=np.float32).reshape(-1, 12))
@@ -203,10 +210,12 @@ class Scene:
         check(ctx.h, lib.dust_trace(ctx.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr)), "dust_trace")
 
     # ---- dust_trace_rays -------------------------------------------------------------------------
-    def trace_rays(self, rays: np.ndarray, stats=False) -> np.ndarray:
+    def trace_rays(self, rays: np.ndarray, stats=False, out=None) -> np.ndarray:
+        """Host-buffer call.  Copies and kernels of consecutive 2 Mi-ray chunks overlap when `rays` / `out` are pinned."""
         rays = np.ascontiguousarray(rays)
         assert rays.dtype == RAY_DTYPE
-        hits = np.empty(len(rays), dtype=HIT_DTYPE)
+        hits = out if out is not None else np.empty(len(rays), dtype=HIT_DTYPE)
+        assert hits.dtype == HIT_DTYPE and len(hits) == len(rays) and hits.flags.c_contiguous
         ctx = self.ctx
         check(ctx.h, ctx.lib.dust_trace_rays(ctx.h, self.h, _ptr(rays), len(rays), _ptr(hits), DUST_MEM_HOST,
                                              DUST_TRACE_STATS if stats else 0), "dust_trace_rays")

@@ -189,6 +189,11 @@ int32_t dust_scene_destroy(DustCtx *ctx, DustScene *scene);
 /* Last frame's object->world matrices (n x 12 floats, row-major 3x4), the `instances[]` buffer of
  * hit.rchit:92 (PreviousFrameGlobalTransform, standard.rs:845-854); used only for DustGBuffer.motion.
  * Until called, last frame == this frame. */
+/* Moving instances (examples/castle.rs:287-292 moves the teapot every frame; tlas_system rebuilds the TLAS from
+ * the entities' GlobalTransforms each frame, tlas.rs:79-132): new object->world matrices (n x 12 floats) for the
+ * SAME trees.  Instance records and the instance BVH are rebuilt on the host and re-uploaded, stream-ordered
+ * after the frames in flight; the transforms in force until now become "last frame" for DustGBuffer.motion. */
+int32_t dust_scene_update_transforms(DustCtx *ctx, DustScene *scene, const float *obj2world, uint32_t n);
 int32_t dust_scene_set_previous_transforms(DustCtx *ctx, DustScene *scene, const float *obj2world_prev, uint32_t n);
 
 /* Replaces StandardPipeline::render (standard.rs:228-810) for the primary + bounce passes. */

@@ -132,6 +132,39 @@ def test_gbuffer_bit_exact(castle_small, host, pipeline):
     assert np.abs(o["gbuffer"]["motion"].astype(np.float32)).max() > 0.3
 
 
+def test_moving_instances_update_transforms(castle_small, host, oracle):
+    """dust_scene_update_transforms (the moving teapot of examples/castle.rs:287-292): instance records and the
+    instance BVH are rebuilt for new matrices; hits equal an oracle scene built with those matrices, and the motion
+    vectors point back to the transforms that were in force before the update."""
+    from dust_b200 import scenes
+    W, H = 192, 108
+    cam = host.camera_look_at(width=W, height=H, **{k: v for k, v in scenes.CASTLE_CAMERA.items()})
+    sky = host.sunlight_bake(direction=host.castle_sun_direction(0.0))
+    old = np.stack([m for _, m in castle_small.ovox.instances]).astype(np.float32).reshape(-1, 12)
+    new = old.copy()
+    rng = np.random.default_rng(11)
+    new[:, 3::4] += np.round(rng.normal(scale=6.0, size=(len(new), 3))).astype(np.float32)      # every instance moves a few voxels
+    oscene = oracle.Scene([(new[i], castle_small.omodels[m].tree._h, castle_small.omodels[m].materials, castle_small.ovox.palette)
+                           for i, (m, _) in enumerate(castle_small.ovox.instances)])
+    oscene.set_previous_transforms(old)
+    scene = castle_small.loaded.scene
+    scene.update_transforms(new)
+    try:
+        g = scene.trace(cam, sky, W, H, spp=2, max_bounces=1, seed=4, hits=True, gbuffer=True)
+        o = oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=4, gbuffer=True)
+    finally:
+        scene.update_transforms(old)
+        scene.set_previous_transforms(old)
+    _assert_hits_equal(g, o)
+    _assert_radiance_close(g, o)
+    assert np.array_equal(g["gbuffer"]["motion"].view(np.uint16), o["gbuffer"]["motion"].view(np.uint16))
+    assert np.abs(o["gbuffer"]["motion"].astype(np.float32)).max() > 1.0
+    # and the scene is back where it was
+    g0 = scene.trace(cam, sky, W, H, hits=True)
+    o0 = castle_small.oscene.render(cam, sky, W, H)
+    _assert_hits_equal(g0, o0)
+
+
 def test_visit_counters_against_oracle(teapot, host):
     """Ray / hit counts are properties of the paths and must match the oracle exactly.  The visit
     counters W, P are properties of the ALGORITHM: the kernel culls with the padded
@@ -257,6 +290,10 @@ def test_ray_batch_many_instances(castle_small, host, monkeypatch):
     monkeypatch.setenv("DUST_RAYS_PLAIN", "1")
     g2 = castle_small.loaded.scene.trace_rays(rays)
     assert np.array_equal(g2.view(np.uint32), o.view(np.uint32))
+    monkeypatch.delenv("DUST_RAYS_PLAIN")
+    monkeypatch.setenv("DUST_RAYS_CHUNK", "20000")           # host path: 8 chunks ping-pong over the two side streams (ragged last chunk)
+    g3 = castle_small.loaded.scene.trace_rays(rays)
+    assert np.array_equal(g3.view(np.uint32), o.view(np.uint32))
 
 
 def test_empty_scene_and_errors(host, ctx):
