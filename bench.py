@@ -205,8 +205,13 @@ def ours(args, cfg):
     cam = host.camera_look_at(width=W, height=H, **camkw)
     ctx = Context(local)
     t0 = time.perf_counter()
-    loaded = load_vox(ctx, data)
+    loaded = load_vox(ctx, data)                                   # trees built on the host (mirror of the Rust crates), then uploaded
     upload_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    loaded_dev = load_vox(ctx, data, device_build=True)            # same trees built on the device from the voxel lists
+    ctx.synchronize()
+    device_build_s = time.perf_counter() - t0
+    del loaded_dev
     scene = loaded.scene
     ctx.use_torch_stream()
     if world > 1:
@@ -363,7 +368,8 @@ def ours(args, cfg):
         "config": workload_config(cfg, label, args, spp),
         "rays_per_step": rays_per_step, "shadow_rays_per_step": tot[2],
         "scene_stats": {"voxels": loaded.num_voxels, "leaves": loaded.num_leaves, "instances": len(loaded.instances),
-                        "device_tree_bytes": loaded.device_bytes, "upload_s": upload_s},
+                        "device_tree_bytes": loaded.device_bytes, "upload_s": upload_s,
+                        "device_build_s": device_build_s},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dust_trace(DUST_MEM_HOST, RGBA16F) -> pinned host frame"},

@@ -96,6 +96,13 @@ class DustFrame(C.Structure):
     ]
 
 
+class DustTreeLayout(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("_pad", C.c_uint32)] + \
+               [(n, C.c_uint64) for n in ("n_nodes16", "n_mids", "n_leaves", "n_materials", "off_nodes16", "off_blocks", "off_mids", "off_leaves",
+                                          "off_palette_linear", "off_palette", "off_materials", "total_bytes")] + \
+               [("bounds_min", C.c_int32 * 3), ("bounds_max", C.c_int32 * 3)]
+
+
 class DustExposureParams(C.Structure):
     _fields_ = [("min_log_luminance", C.c_float), ("log_luminance_range", C.c_float), ("time_coefficient", C.c_float)]
 
@@ -123,6 +130,9 @@ SYMBOLS = {
     "dust_ctx_synchronize": (C.c_int32, [C.c_void_p]),
     "dust_last_error_string": (C.c_char_p, [C.c_void_p]),
     "dust_tree_upload": (C.c_int32, [C.c_void_p, C.POINTER(DustTreeDesc), C.POINTER(C.c_void_p)]),
+    "dust_tree_build_voxels": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "dust_tree_layout": (C.c_int32, [C.c_void_p, C.POINTER(DustTreeLayout)]),
+    "dust_tree_download": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "dust_tree_destroy": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "dust_tree_leaf_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dust_tree_device_bytes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),

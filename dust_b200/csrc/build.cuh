@@ -1,0 +1,144 @@
+// sm_100a device code, part 6: building a model's tree ON THE DEVICE from its voxel list.
+// Replaces, for one .vox model, the serial host chain VoxLoader::load_model (crates/vox/src/loader.rs:238-308:
+// per-voxel Tree::set_value + ModelIndexCollector, collector.rs:2-87) + VoxGeometry::from_tree + the re-layout of
+// dust_tree_upload, and produces the SAME device blob section by section (tests compare them bytewise).
+//
+//   vb_scatter    one thread per voxel: axis swizzle (loader.rs:248-253), block_counts[block] += 1 and
+//                 grid[block * 64 + bit] = max((order + 1) << 9 | (i + 1))   (the last voxel of a cell wins, like
+//                 the collector's overwrite; duplicates count twice in block_counts, like the collector)
+//   vb_scan       single-CTA exclusive scans over the 64^3 blocks (collector order: material_ptr and material
+//                 write positions; tree order: leaf slots) and the 16^3 mid nodes
+//   vb_leaves     one thread per 4^3 block in TREE order (root child index, then mid child index =
+//                 Tree::iter_leaf order): occupancy mask from the grid, popcount, flag
+//   vb_emit_*     leaf / mid / 16^3-node words, block mask, compacted material bytes, occupied bounds
+//
+// Integer work throughout; every array is dense over the 256^3 domain (64^3 = 262 144 blocks), so the kernels are
+// streaming passes over 128 MB (grid) + a few MB: HBM-bound, ~100 us per model instead of seconds on the host.
+#pragma once
+#include "device_layout.h"
+#include <stdint.h>
+
+namespace dust {
+
+constexpr uint32_t VB_BLOCKS = 64u * 64u * 64u;      // 4^3-voxel blocks (= leaf slots) of a 256^3 model
+constexpr uint32_t VB_MIDS = 16u * 16u * 16u;        // 4^3-leaf mid nodes
+
+struct VbCounts { uint32_t n_leaves, n_mids, n_materials, pad; int32_t bmin[3], bmax[3]; };
+
+// collector block index (x>>2) + (y>>2) * 64 + (z>>2) * 4096  <->  tree-order key (mid index << 6 | leaf-in-mid index)
+__device__ __forceinline__ uint32_t vb_block_of_key(uint32_t key)
+{
+    const uint32_t mid = key >> 6, li = key & 63u;
+    const uint32_t bx = ((mid >> 8) << 2) | (li >> 4), by = (((mid >> 4) & 15u) << 2) | ((li >> 2) & 3u), bz = ((mid & 15u) << 2) | (li & 3u);
+    return bx + by * 64u + bz * 4096u;
+}
+
+__global__ void __launch_bounds__(256) vb_scatter(const uchar4 *__restrict__ voxels, uint32_t n, uint32_t size_y,
+                                                  unsigned long long *__restrict__ grid, uint32_t *__restrict__ block_counts)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const uchar4 v = __ldg(&voxels[i]);
+    const uint32_t x = v.x, y = v.z, z = (size_y - (uint32_t)v.y - 1u) & 255u;           // loader.rs:248-253
+    const uint32_t block = (x >> 2) + (y >> 2) * 64u + (z >> 2) * 4096u;                 // collector.rs:25-27
+    const uint32_t bit = (z & 3u) | ((y & 3u) << 2) | ((x & 3u) << 4);                   // collector.rs:31 == leaf.rs:81-83
+    atomicAdd(&block_counts[block], 1u);
+    atomicMax(&grid[(size_t)block * 64u + bit], ((unsigned long long)(i + 1u) << 9) | ((unsigned long long)v.w + 1ull));
+}
+
+// occupancy of every block, in tree order
+__global__ void __launch_bounds__(256) vb_leaves(const unsigned long long *__restrict__ grid, unsigned long long *__restrict__ leaf_mask,
+                                                 uint32_t *__restrict__ flag_tree, uint32_t *__restrict__ pop_block)
+{
+    const uint32_t key = blockIdx.x * 256u + threadIdx.x;                                // < VB_BLOCKS
+    const uint32_t block = vb_block_of_key(key);
+    const ulonglong2 *g = reinterpret_cast<const ulonglong2 *>(grid + (size_t)block * 64u);
+    unsigned long long m = 0;
+#pragma unroll 8
+    for (uint32_t k = 0; k < 32; k++) {
+        const ulonglong2 two = __ldg(&g[k]);
+        m |= (unsigned long long)(two.x != 0ull) << (2 * k);
+        m |= (unsigned long long)(two.y != 0ull) << (2 * k + 1);
+    }
+    leaf_mask[key] = m;
+    flag_tree[key] = m != 0ull;
+    pop_block[block] = (uint32_t)__popcll(m);
+}
+
+// exclusive scan of `n` (multiple of 1024) uint32 in place, one CTA of 1024 threads; *total = sum
+__global__ void __launch_bounds__(1024) vb_scan(uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ total)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t per = n / 1024u, first = threadIdx.x * per;
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < per; k++) s += a[first + k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t ofs = 1; ofs < 1024u; ofs <<= 1) {                                    // Hillis-Steele over the 1024 partial sums
+        const uint32_t v = threadIdx.x >= ofs ? part[threadIdx.x - ofs] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (uint32_t k = 0; k < per; k++) { const uint32_t v = a[first + k]; a[first + k] = run; run += v; }
+    if (total && threadIdx.x == 1023u) *total = part[1023];
+}
+
+// per mid node (tree order): child mask from the leaf flags
+__global__ void __launch_bounds__(256) vb_mid_masks(const uint32_t *__restrict__ flag_tree, unsigned long long *__restrict__ mid_mask, uint32_t *__restrict__ mid_flag)
+{
+    const uint32_t mid = blockIdx.x * 256u + threadIdx.x;                                // < VB_MIDS
+    unsigned long long m = 0;
+    for (uint32_t li = 0; li < 64; li++) m |= (unsigned long long)(flag_tree[mid * 64u + li] != 0u) << li;
+    mid_mask[mid] = m;
+    mid_flag[mid] = m != 0ull;
+}
+
+// leaf words {occupancy lo, hi, material_ptr, 0} at their slot; materials compacted in collector order; bounds
+__global__ void __launch_bounds__(256) vb_emit_leaves(const unsigned long long *__restrict__ grid, const unsigned long long *__restrict__ leaf_mask,
+                                                      const uint32_t *__restrict__ leaf_slot, const uint32_t *__restrict__ mat_ptr,
+                                                      const uint32_t *__restrict__ mat_pos, uint4 *__restrict__ leaves, uint8_t *__restrict__ materials,
+                                                      VbCounts *__restrict__ counts)
+{
+    const uint32_t key = blockIdx.x * 256u + threadIdx.x;
+    const unsigned long long m = leaf_mask[key];
+    if (!m) return;
+    const uint32_t block = vb_block_of_key(key);
+    leaves[leaf_slot[key]] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), mat_ptr[block], 0u);
+    uint32_t pos = mat_pos[block];
+    for (unsigned long long b = m; b; b &= b - 1)                                        // ascending bit order (collector.rs:47-60)
+        materials[pos++] = (uint8_t)((grid[(size_t)block * 64u + (uint32_t)(__ffsll((long long)b) - 1)] & 511ull) - 1ull);
+    const int32_t lo[3] = { (int32_t)(block & 63u) * 4, (int32_t)((block >> 6) & 63u) * 4, (int32_t)(block >> 12) * 4 };
+    for (int a = 0; a < 3; a++) { atomicMin(&counts->bmin[a], lo[a]); atomicMax(&counts->bmax[a], lo[a] + 4); }
+}
+
+__global__ void __launch_bounds__(256) vb_emit_mids(const unsigned long long *__restrict__ mid_mask, const uint32_t *__restrict__ mid_slot,
+                                                    const uint32_t *__restrict__ leaf_slot, uint4 *__restrict__ mids)
+{
+    const uint32_t mid = blockIdx.x * 256u + threadIdx.x;
+    const unsigned long long m = mid_mask[mid];
+    if (m) mids[mid_slot[mid]] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), leaf_slot[mid * 64u], 0u);   // slot of its first leaf
+}
+
+// the root 16^3 node (64 words) and its block mask: one CTA of 64 threads
+__global__ void __launch_bounds__(64) vb_emit_root(const uint32_t *__restrict__ mid_flag, const uint32_t *__restrict__ mid_slot,
+                                                   DNode16 *__restrict__ n16, uint2 *__restrict__ blocks)
+{
+    __shared__ unsigned long long words[64];
+    const uint32_t w = threadIdx.x;
+    unsigned long long m = 0;
+    for (uint32_t b = 0; b < 64; b++) m |= (unsigned long long)(mid_flag[w * 64u + b] != 0u) << b;
+    words[w] = m;
+    n16->word[w] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), mid_slot[w * 64u], 0u);
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long bm = 0;                                                       // same rule as dust_tree_upload
+        for (uint32_t k = 0; k < 64; k++)
+            for (uint32_t bz = 0; bz < 4; bz++)
+                if (words[k] & (0x000F000F000F000Full << (4 * bz))) bm |= 1ull << (((k >> 4) << 4) | ((k & 3) << 2) | bz);
+        blocks[0] = make_uint2((uint32_t)bm, (uint32_t)(bm >> 32));
+    }
+}
+
+}  // namespace dust

@@ -3,6 +3,7 @@
 // launches sm_100a kernels or fails.
 #include "wavefront.cuh"
 #include "post.cuh"
+#include "build.cuh"
 
 #include <cstdlib>
 #include <dlfcn.h>
@@ -49,7 +50,7 @@ struct DustTree {
     const uint8_t *materials = nullptr;
     const float4 *palette_lin = nullptr;
     const uchar4 *palette_raw = nullptr;
-    uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0;
+    uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0, n_materials = 0;
     int32_t bmin[3] = { 0, 0, 0 }, bmax[3] = { 0, 0, 0 };   // occupied bounds in object voxels
 };
 
@@ -451,6 +452,46 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     return DUST_OK;
 }
 
+// offsets of the sections of a tree blob: [n16 | blocks | mids | leaves | palette_lin | palette_raw | materials], 256-byte aligned
+struct BlobLayout { size_t n16, blocks, mids, leaves, pal, praw, mat, total; };
+BlobLayout blob_layout(size_t n_n16, size_t n_mids, size_t n_leaves, size_t n_materials)
+{
+    BlobLayout L;
+    L.n16 = 0;
+    L.blocks = align_up(L.n16 + n_n16 * sizeof(DNode16), 256);
+    L.mids = align_up(L.blocks + n_n16 * sizeof(uint2), 256);
+    L.leaves = align_up(L.mids + n_mids * sizeof(uint4), 256);
+    L.pal = align_up(L.leaves + n_leaves * sizeof(uint4), 256);
+    L.praw = align_up(L.pal + 256 * sizeof(float4), 256);
+    L.mat = align_up(L.praw + 1024, 256);
+    L.total = align_up(L.mat + n_materials + 16, 256);
+    return L;
+}
+
+void tree_set_pointers(DustTree *t, const BlobLayout &L)
+{
+    uint8_t *base = static_cast<uint8_t *>(t->blob);
+    t->blob_bytes = L.total;
+    t->n16 = reinterpret_cast<const DNode16 *>(base + L.n16);
+    t->blocks = reinterpret_cast<const uint2 *>(base + L.blocks);
+    t->mids = reinterpret_cast<const uint4 *>(base + L.mids);
+    t->leaves = reinterpret_cast<const uint4 *>(base + L.leaves);
+    t->palette_lin = reinterpret_cast<const float4 *>(base + L.pal);
+    t->palette_raw = reinterpret_cast<const uchar4 *>(base + L.praw);
+    t->materials = base + L.mat;
+}
+
+void palette_tables(const uint8_t *palette, float4 pal[256], uint8_t praw[1024])
+{
+    memset(pal, 0, 256 * sizeof(float4));
+    for (int i = 0; i < 255; i++) {
+        const uint8_t *c = palette + 4 * i;
+        pal[i] = make_float4(srgb_to_linear((float)c[0] / 255.0f), srgb_to_linear((float)c[1] / 255.0f), srgb_to_linear((float)c[2] / 255.0f), 0.0f);
+    }
+    memset(praw, 0, 1024);
+    memcpy(praw, palette, 255 * 4);
+}
+
 }  // namespace
 
 extern "C" {
@@ -528,11 +569,8 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     if (desc->n_materials && !desc->materials) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "materials is NULL");
 
     float4 pal[256];
-    memset(pal, 0, sizeof pal);
-    for (int i = 0; i < 255; i++) {
-        const uint8_t *c = desc->palette + 4 * i;
-        pal[i] = make_float4(srgb_to_linear((float)c[0] / 255.0f), srgb_to_linear((float)c[1] / 255.0f), srgb_to_linear((float)c[2] / 255.0f), 0.0f);
-    }
+    uint8_t praw[1024];
+    palette_tables(desc->palette, pal, praw);
 
     // block masks: bit bx<<4|by<<2|bz of node n = "some child bit set in the 4x4x4 block (bx,by,bz) of its 16^3 children"
     std::vector<uint2> blocks(r.n16.size());
@@ -546,15 +584,9 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
         blocks[n] = make_uint2((uint32_t)bm, (uint32_t)(bm >> 32));
     }
 
-    // one allocation: [n16 | blocks | mids | leaves | palette_lin | materials], each 256-byte aligned
-    const size_t off_n16 = 0;
-    const size_t off_blocks = align_up(off_n16 + r.n16.size() * sizeof(DNode16), 256);
-    const size_t off_mids = align_up(off_blocks + blocks.size() * sizeof(uint2), 256);
-    const size_t off_leaves = align_up(off_mids + r.mids.size() * sizeof(uint4), 256);
-    const size_t off_pal = align_up(off_leaves + r.leaves.size() * sizeof(uint4), 256);
-    const size_t off_praw = align_up(off_pal + sizeof pal, 256);
-    const size_t off_mat = align_up(off_praw + 1024, 256);
-    const size_t total = align_up(off_mat + (size_t)desc->n_materials + 16, 256);
+    // one allocation: [n16 | blocks | mids | leaves | palette_lin | palette_raw | materials], each 256-byte aligned
+    const BlobLayout L = blob_layout(r.n16.size(), r.mids.size(), r.leaves.size(), (size_t)desc->n_materials);
+    const size_t off_n16 = L.n16, off_blocks = L.blocks, off_mids = L.mids, off_leaves = L.leaves, off_pal = L.pal, off_praw = L.praw, off_mat = L.mat, total = L.total;
 
     DustTree *t = new (std::nothrow) DustTree();
     if (!t) return DUST_ERR_OUT_OF_MEMORY;
@@ -570,9 +602,6 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     if (e == cudaSuccess) e = put(off_mids, r.mids.data(), r.mids.size() * sizeof(uint4));
     if (e == cudaSuccess) e = put(off_leaves, r.leaves.data(), r.leaves.size() * sizeof(uint4));
     if (e == cudaSuccess) e = put(off_pal, pal, sizeof pal);
-    uint8_t praw[1024];
-    memset(praw, 0, sizeof praw);
-    memcpy(praw, desc->palette, 255 * 4);
     if (e == cudaSuccess) e = put(off_praw, praw, sizeof praw);
     if (e == cudaSuccess) e = put(off_mat, desc->materials, (size_t)desc->n_materials);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);     // host vectors die at return
@@ -586,10 +615,109 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     t->palette_lin = reinterpret_cast<const float4 *>(base + off_pal);
     t->palette_raw = reinterpret_cast<const uchar4 *>(base + off_praw);
     t->materials = base + off_mat;
-    t->n_leaves = r.leaves.size(); t->n_mids = r.mids.size(); t->n_n16 = r.n16.size();
+    t->n_leaves = r.leaves.size(); t->n_mids = r.mids.size(); t->n_n16 = r.n16.size(); t->n_materials = desc->n_materials;
     if (r.leaves.empty()) { for (int a = 0; a < 3; a++) { t->bmin[a] = 0; t->bmax[a] = 0; } }
     else for (int a = 0; a < 3; a++) { t->bmin[a] = r.bmin[a]; t->bmax[a] = r.bmax[a]; }
     *out = t;
+    return DUST_OK;
+}
+
+// ---- device-side build (build.cuh) ---------------------------------------------------------------------
+
+int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n, const uint32_t *size, const uint8_t *palette,
+                               uint32_t memory, DustTree **out)
+{
+    if (!ctx || !out || !size || !palette || (n && !voxels)) return DUST_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (size[0] > 256 || size[1] > 256 || size[2] > 256) return fail(ctx, DUST_ERR_UNSUPPORTED, "model larger than 256^3 (loader.rs:365)");
+    if (n > (1ull << 31)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "too many voxels");
+    if (memory != DUST_MEM_HOST && memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // scratch: [grid u64 x 16 Mi | block_counts -> mat_ptr | pop_block -> mat_pos | flag_tree -> leaf_slot | leaf_mask | mid_mask | mid_flag | mid_slot | counts | voxels]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_grid = take((size_t)VB_BLOCKS * 64 * 8), o_cnt = take(VB_BLOCKS * 4), o_pop = take(VB_BLOCKS * 4), o_flag = take(VB_BLOCKS * 4);
+    const size_t o_lmask = take(VB_BLOCKS * 8), o_mmask = take(VB_MIDS * 8), o_mflag = take(VB_MIDS * 4), o_mslot = take(VB_MIDS * 4);
+    const size_t o_counts = take(sizeof(VbCounts)), o_vox = take(memory == DUST_MEM_HOST ? (size_t)n * 4 : 0);
+    const int32_t rc = ensure_scratch(ctx, off);
+    if (rc != DUST_OK) return rc;
+    uint8_t *sc = static_cast<uint8_t *>(ctx->scratch);
+    unsigned long long *grid = reinterpret_cast<unsigned long long *>(sc + o_grid), *lmask = reinterpret_cast<unsigned long long *>(sc + o_lmask),
+                       *mmask = reinterpret_cast<unsigned long long *>(sc + o_mmask);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + o_cnt), *pop = reinterpret_cast<uint32_t *>(sc + o_pop), *flag = reinterpret_cast<uint32_t *>(sc + o_flag),
+             *mflag = reinterpret_cast<uint32_t *>(sc + o_mflag), *mslot = reinterpret_cast<uint32_t *>(sc + o_mslot);
+    VbCounts *d_counts = reinterpret_cast<VbCounts *>(sc + o_counts);
+    const uchar4 *d_vox = reinterpret_cast<const uchar4 *>(voxels);
+    cudaStream_t st = ctx->stream;
+    if (memory == DUST_MEM_HOST && n) {
+        CU_TRY(ctx, cudaMemcpyAsync(sc + o_vox, voxels, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        d_vox = reinterpret_cast<const uchar4 *>(sc + o_vox);
+    }
+    CU_TRY(ctx, cudaMemsetAsync(sc + o_grid, 0, o_pop - o_grid, st));                      // grid + block_counts
+    VbCounts h_counts;
+    memset(&h_counts, 0, sizeof h_counts);
+    for (int a = 0; a < 3; a++) { h_counts.bmin[a] = INT32_MAX; h_counts.bmax[a] = INT32_MIN; }
+    CU_TRY(ctx, cudaMemcpyAsync(d_counts, &h_counts, sizeof h_counts, cudaMemcpyHostToDevice, st));
+    if (n) { vb_scatter<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(d_vox, (uint32_t)n, size[1], grid, cnt); count_launch(ctx); }
+    vb_leaves<<<VB_BLOCKS / 256, 256, 0, st>>>(grid, lmask, flag, pop); count_launch(ctx);
+    vb_mid_masks<<<VB_MIDS / 256, 256, 0, st>>>(flag, mmask, mflag); count_launch(ctx);
+    CU_TRY(ctx, cudaMemcpyAsync(mslot, mflag, VB_MIDS * 4, cudaMemcpyDeviceToDevice, st));
+    vb_scan<<<1, 1024, 0, st>>>(cnt, VB_BLOCKS, nullptr); count_launch(ctx);               // material_ptr (collector.rs:76-82)
+    vb_scan<<<1, 1024, 0, st>>>(pop, VB_BLOCKS, &d_counts->n_materials); count_launch(ctx);  // where each block's bytes go
+    vb_scan<<<1, 1024, 0, st>>>(flag, VB_BLOCKS, &d_counts->n_leaves); count_launch(ctx);  // leaf slots, Tree::iter_leaf order
+    vb_scan<<<1, 1024, 0, st>>>(mslot, VB_MIDS, &d_counts->n_mids); count_launch(ctx);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(&h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));                                                // sizes of the blob
+
+    const BlobLayout L = blob_layout(1, h_counts.n_mids, h_counts.n_leaves, h_counts.n_materials);
+    DustTree *t = new (std::nothrow) DustTree();
+    if (!t) return DUST_ERR_OUT_OF_MEMORY;
+    cudaError_t e = cudaMalloc(&t->blob, L.total);
+    if (e != cudaSuccess) { delete t; return fail(ctx, DUST_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+    tree_set_pointers(t, L);
+    uint8_t *base = static_cast<uint8_t *>(t->blob);
+    float4 pal[256];
+    uint8_t praw[1024];
+    palette_tables(palette, pal, praw);
+    e = cudaMemcpyAsync(base + L.pal, pal, sizeof pal, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(base + L.praw, praw, sizeof praw, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        vb_emit_leaves<<<VB_BLOCKS / 256, 256, 0, st>>>(grid, lmask, flag, cnt, pop, reinterpret_cast<uint4 *>(base + L.leaves), base + L.mat, d_counts);
+        vb_emit_mids<<<VB_MIDS / 256, 256, 0, st>>>(mmask, mslot, flag, reinterpret_cast<uint4 *>(base + L.mids));
+        vb_emit_root<<<1, 64, 0, st>>>(mflag, mslot, reinterpret_cast<DNode16 *>(base + L.n16), reinterpret_cast<uint2 *>(base + L.blocks));
+        count_launch(ctx); count_launch(ctx); count_launch(ctx);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);                                   // bounds; pal / praw die at return
+    if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e)); }
+    t->n_levels = 3;
+    t->n_leaves = h_counts.n_leaves; t->n_mids = h_counts.n_mids; t->n_n16 = 1; t->n_materials = h_counts.n_materials;
+    for (int a = 0; a < 3; a++) { t->bmin[a] = h_counts.n_leaves ? h_counts.bmin[a] : 0; t->bmax[a] = h_counts.n_leaves ? h_counts.bmax[a] : 0; }
+    *out = t;
+    return DUST_OK;
+}
+
+int32_t dust_tree_layout(const DustTree *tree, DustTreeLayout *out)
+{
+    if (!tree || !out) return DUST_ERR_INVALID_ARGUMENT;
+    const BlobLayout L = blob_layout(tree->n_n16, tree->n_mids, tree->n_leaves, tree->n_materials);
+    out->n_levels = tree->n_levels;
+    out->n_nodes16 = tree->n_n16; out->n_mids = tree->n_mids; out->n_leaves = tree->n_leaves; out->n_materials = tree->n_materials;
+    out->off_nodes16 = L.n16; out->off_blocks = L.blocks; out->off_mids = L.mids; out->off_leaves = L.leaves;
+    out->off_palette_linear = L.pal; out->off_palette = L.praw; out->off_materials = L.mat; out->total_bytes = L.total;
+    for (int a = 0; a < 3; a++) { out->bounds_min[a] = tree->bmin[a]; out->bounds_max[a] = tree->bmax[a]; }
+    return DUST_OK;
+}
+
+int32_t dust_tree_download(DustCtx *ctx, const DustTree *tree, void *dst, uint64_t capacity)
+{
+    if (!ctx || !tree || !dst) return DUST_ERR_INVALID_ARGUMENT;
+    if (capacity < tree->blob_bytes) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "dust_tree_download: buffer smaller than DustTreeLayout.total_bytes");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpyAsync(dst, tree->blob, tree->blob_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return DUST_OK;
 }
 

@@ -135,6 +135,13 @@ void dh_vox_model_info(const void *v, uint32_t model, uint32_t *size3, uint64_t 
     std::memcpy(size3, m.size, sizeof m.size);
     *n_voxels = m.voxels.size();
 }
+// the model's dot_vox voxels as parsed ({x, y, z, i} bytes): input of dust_tree_build_voxels
+const uint8_t *dh_vox_model_voxels(const void *v, uint32_t model)
+{
+    const auto &m = static_cast<const DhVox *>(v)->file->models[model];
+    static_assert(sizeof(dust::vox::Voxel) == 4, "Voxel is 4 bytes");
+    return m.voxels.empty() ? nullptr : reinterpret_cast<const uint8_t *>(m.voxels.data());
+}
 void dh_to_transform(const int32_t *t, uint8_t rot, const uint32_t *size, float *out)
 {
     const auto a = dust::vox::VoxFile::to_transform(t, rot, size);

@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         "dh_vox_instance": (None, [vp, u32, C.POINTER(u32), C.POINTER(f32)]),
         "dh_vox_palette": (vp, [vp]),
         "dh_vox_model_info": (None, [vp, u32, C.POINTER(u32), C.POINTER(u64)]),
+        "dh_vox_model_voxels": (vp, [vp, u32]),
         "dh_to_transform": (None, [C.POINTER(i32), C.c_uint8, C.POINTER(u32), C.POINTER(f32)]),
         "dh_vox_load_model": (vp, [vp, u32]),
         "dh_model_free": (None, [vp]),
@@ -285,6 +286,14 @@ class VoxFile:
         n = C.c_uint64()
         lib().dh_vox_model_info(self._h, model_id, size, C.byref(n))
         return tuple(size), int(n.value)
+
+    def model_voxels(self, model_id) -> np.ndarray:
+        """The model's dot_vox voxels as parsed: [n, 4] uint8 (x, y, z, i) — a view into the parsed file."""
+        _, n = self.model_info(model_id)
+        if not n:
+            return np.zeros((0, 4), np.uint8)
+        p = lib().dh_vox_model_voxels(self._h, model_id)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n, 4))
 
     def load_model(self, model_id) -> VoxModel:
         h = lib().dh_vox_load_model(self._h, model_id)

@@ -83,11 +83,52 @@ class Context:
 
 
 class DeviceTree:
-    def __init__(self, ctx: Context, desc: capi.DustTreeDesc):
+    def __init__(self, ctx: Context, desc: capi.DustTreeDesc = None, _handle=None):
         self.ctx = ctx
+        if _handle is not None:
+            self.h = _handle
+            return
         h = C.c_void_p()
         check(ctx.h, ctx.lib.dust_tree_upload(ctx.h, C.byref(desc), C.byref(h)), "dust_tree_upload")
         self.h = h
+
+    @classmethod
+    def build_voxels(cls, ctx: Context, voxels, size, palette) -> "DeviceTree":
+        """dust_tree_build_voxels: the tree of one .vox model built on the device from its voxel list
+        ([n, 4] uint8 x, y, z, i as parsed; numpy = host memory, torch CUDA tensor = device memory)."""
+        n = int(voxels.shape[0])
+        if isinstance(voxels, np.ndarray):
+            voxels = np.ascontiguousarray(voxels, dtype=np.uint8)
+            mem = DUST_MEM_HOST
+        else:
+            mem = DUST_MEM_DEVICE
+        pal = np.ascontiguousarray(np.asarray(palette, dtype=np.uint8).reshape(-1)[:255 * 4])
+        h = C.c_void_p()
+        check(ctx.h, ctx.lib.dust_tree_build_voxels(ctx.h, _ptr(voxels) if n else None, n, (C.c_uint32 * 3)(*[int(v) for v in size]),
+                                                   pal.ctypes.data, mem, C.byref(h)), "dust_tree_build_voxels")
+        return cls(ctx, _handle=h)
+
+    def layout(self) -> capi.DustTreeLayout:
+        out = capi.DustTreeLayout()
+        check(self.ctx.h, self.ctx.lib.dust_tree_layout(self.h, C.byref(out)), "dust_tree_layout")
+        return out
+
+    def download(self) -> dict:
+        """The device blob, section by section (numpy copies): nodes16 [n,64,4] u32, blocks [n,2] u32, mids / leaves [n,4] u32,
+        palette_linear [256,4] f32, palette [256,4] u8, materials [n] u8."""
+        L = self.layout()
+        buf = np.empty(int(L.total_bytes), np.uint8)
+        check(self.ctx.h, self.ctx.lib.dust_tree_download(self.ctx.h, self.h, buf.ctypes.data, buf.size), "dust_tree_download")
+        def sec(off, count, dtype, shape):
+            nbytes = int(count) * np.dtype(dtype).itemsize
+            return buf[int(off):int(off) + nbytes].view(dtype).reshape(shape).copy()
+        return {
+            "nodes16": sec(L.off_nodes16, L.n_nodes16 * 256, np.uint32, (-1, 64, 4)), "blocks": sec(L.off_blocks, L.n_nodes16 * 2, np.uint32, (-1, 2)),
+            "mids": sec(L.off_mids, L.n_mids * 4, np.uint32, (-1, 4)), "leaves": sec(L.off_leaves, L.n_leaves * 4, np.uint32, (-1, 4)),
+            "palette_linear": sec(L.off_palette_linear, 1024, np.float32, (256, 4)), "palette": sec(L.off_palette, 1024, np.uint8, (256, 4)),
+            "materials": sec(L.off_materials, L.n_materials, np.uint8, (-1,)),
+            "bounds": (tuple(L.bounds_min), tuple(L.bounds_max)),
+        }
 
     @property
     def leaf_count(self) -> int:

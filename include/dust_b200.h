@@ -179,6 +179,23 @@ const char *dust_last_error_string(const DustCtx *ctx);
 /* Replaces VoxGeometry::from_tree + the material/palette uploads (geometry.rs:55-179,
  * loader.rs:208-236, 274-288): the tree is re-laid-out for the GPU and uploaded once. */
 int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out);
+/* Device-side build of ONE .vox model: replaces VoxLoader::load_model's per-voxel
+ * Tree::set_value + ModelIndexCollector (loader.rs:238-308, collector.rs:2-87) + VoxGeometry::from_tree +
+ * dust_tree_upload by a handful of kernels over the voxel list.  `voxels` = the model's dot_vox voxels as the loader
+ * sees them (.vox axes, i = palette entry), `size` = dot_vox model size {x, y, z} (each <= 256), `palette` = 255 x
+ * RGBA8.  The result is section for section the blob dust_tree_upload produces for the same model (hierarchy!(4,2,2)). */
+typedef struct DustVoxel { uint8_t x, y, z, i; } DustVoxel;
+int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n, const uint32_t *size, const uint8_t *palette,
+                               uint32_t memory, DustTree **out);
+/* Inspection: section offsets / counts of a tree's device blob, and a copy of it (tests compare both build paths). */
+typedef struct DustTreeLayout {
+    uint32_t n_levels, _pad;
+    uint64_t n_nodes16, n_mids, n_leaves, n_materials;
+    uint64_t off_nodes16, off_blocks, off_mids, off_leaves, off_palette_linear, off_palette, off_materials, total_bytes;
+    int32_t bounds_min[3], bounds_max[3];     /* occupied bounds in object voxels (multiples of 4) */
+} DustTreeLayout;
+int32_t dust_tree_layout(const DustTree *tree, DustTreeLayout *out);
+int32_t dust_tree_download(DustCtx *ctx, const DustTree *tree, void *dst, uint64_t capacity);
 int32_t dust_tree_destroy(DustCtx *ctx, DustTree *tree);
 int32_t dust_tree_leaf_count(const DustTree *tree, uint64_t *out);
 int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out);
