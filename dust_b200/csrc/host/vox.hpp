@@ -288,4 +288,18 @@ inline std::unique_ptr<VoxGeometry> load_model(const VoxFile &file, uint32_t mod
     return g;
 }
 
+// The device-side alternative to load_model + dust_tree_upload: only the parse stays on the host, the tree of the
+// model is built by dust_tree_build_voxels from its voxel list (same device blob, tests/test_device_build.py).
+inline DustTree *build_model_on_device(DustCtx *ctx, const VoxFile &file, uint32_t model_id, std::string &err)
+{
+    if (model_id >= file.models.size()) { err = "model id out of range"; return nullptr; }
+    const Model &model = file.models[model_id];
+    static_assert(sizeof(Voxel) == sizeof(DustVoxel), "Voxel == DustVoxel");
+    DustTree *tree = nullptr;
+    const int32_t rc = dust_tree_build_voxels(ctx, reinterpret_cast<const DustVoxel *>(model.voxels.data()), model.voxels.size(), model.size,
+                                              file.palette[0].data(), DUST_MEM_HOST, &tree);
+    if (rc != DUST_OK) { err = dust_last_error_string(ctx); return nullptr; }
+    return tree;
+}
+
 }  // namespace dust::vox
