@@ -372,7 +372,7 @@ def ours(args, cfg):
                         "device_build_s": device_build_s},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "dust_trace(DUST_MEM_HOST, RGBA16F) -> pinned host frame"},
+                "api": "dust_trace(DUST_MEM_HOST, RGBA16F) -> pinned host frame" + ("" if world == 1 else " (every rank downloads its own shard; no gather on this path)")},
         "gpu_launches": int(launches), "clocks": clk,
     }
     print(json.dumps(line), flush=True)

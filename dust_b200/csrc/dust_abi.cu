@@ -362,10 +362,10 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     const uint64_t n_paths = (uint64_t)n_slots * batch_spp;
     if (n_paths >= (1ull << 31)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "frame too large for one wavefront batch");
 
-    // carve the scratch: [ps0 ps1 ps2 | 3 queues (a, b, path) | hits | acc | vis | cand | overflow]
+    // carve the scratch: [ps0 ps1 | 3 queues (a, b, path) | hits | acc | vis | cand | overflow]
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_ps0 = take(n_paths * 16), o_ps1 = take(n_paths * 16), o_ps2 = take(n_paths * 16);
+    const size_t o_ps0 = take(n_paths * 16), o_ps1 = take(n_paths * 16);
     size_t o_q[3][3];
     for (int q = 0; q < 3; q++) { o_q[q][0] = take(n_paths * 16); o_q[q][1] = take(n_paths * 16); o_q[q][2] = take(n_paths * 4); }
     const size_t o_hits = take(n_paths * 16), o_acc = take((size_t)n_slots * 16), o_vis = take(n_paths);
@@ -382,7 +382,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     memset(&p, 0, sizeof p);
     p.f = fp;
     p.n_slots = n_slots;
-    p.ps0 = reinterpret_cast<float4 *>(base + o_ps0); p.ps1 = reinterpret_cast<float4 *>(base + o_ps1); p.ps2 = reinterpret_cast<float4 *>(base + o_ps2);
+    p.ps0 = reinterpret_cast<float4 *>(base + o_ps0); p.ps1 = reinterpret_cast<float4 *>(base + o_ps1);
     WfQueue *qs[3] = { &p.qc, &p.qs, &p.qn };
     for (int q = 0; q < 3; q++) {
         qs[q]->a = reinterpret_cast<float4 *>(base + o_q[q][0]); qs[q]->b = reinterpret_cast<float4 *>(base + o_q[q][1]);
@@ -432,13 +432,15 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         const uint32_t grid128 = (p.n_paths + DUST_THREADS - 1) / DUST_THREADS, grid256 = (p.n_paths + 255) / 256;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_wf_counters, 0, kWfCounterWords * sizeof(uint32_t), ctx->stream));
         p.qc = q_even; p.qn = q_odd;
-        wf_gen_primary<<<grid256, 256, 0, ctx->stream>>>(p);
-        count_launch(ctx);
+        // the depth-0 queue is implicit (slot i = camera ray of path i, recomputed by its consumers) unless it goes to the persistent tracer
+        const bool implicit0 = pt_depth > 0;
+        if (!implicit0) { wf_gen_primary<<<grid256, 256, 0, ctx->stream>>>(p); count_launch(ctx); }
         for (uint32_t depth = 0; depth <= cfg.max_bounces; depth++) {
             p.depth = depth;
             p.qc = depth & 1 ? q_odd : q_even; p.qn = depth & 1 ? q_even : q_odd;
+            if (depth == 0 && implicit0) { p.qc.a = nullptr; p.qc.b = nullptr; p.qc.path = nullptr; p.qc.stride = 0; }
             // queue sizes live on the device: launch for the largest possible queue, surplus CTAs exit at once
-            const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : p.counts + 3;
+            const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : (implicit0 ? nullptr : p.counts + 3);
             if (depth >= pt_depth) trace_pt(p.qc, n_closest, 2 * depth, grid128); else trace(p.qc, n_closest, nullptr, grid128);
             if (stats) wf_shade<true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_shade<false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p);
             count_launch(ctx);

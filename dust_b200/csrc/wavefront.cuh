@@ -32,7 +32,8 @@ struct WfQueue {
     float4 *a;          // origin.xyz, tmin   of ray i at a[i * stride]
     float4 *b;          // direction.xyz, tmax           b[i * stride]
     uint32_t *path;     // path index; bit 31: any-hit (shadow) ray.  NULL: closest-hit rays, path = i (ray batches)
-    uint32_t stride;    // 1: separate arrays; 2: interleaved DustRay records (a = rays, b = rays + 1)
+    uint32_t stride;    // 1: separate arrays; 2: interleaved DustRay records (a = rays, b = rays + 1);
+                        // 0: no arrays at all — slot i is the camera ray of path i (wf_primary_ray), the depth-0 queue of a frame
 };
 
 struct WfParams {
@@ -42,7 +43,7 @@ struct WfParams {
     uint32_t batch_spp, batch_first;  // samples per pixel in this batch, index of its first sample
     uint32_t depth;                   // vertex index of the closest queue being traced / shaded
     uint32_t last_batch;
-    float4 *ps0, *ps1, *ps2;          // path state: (T, s1) (L, flags) (pending sun term, -)
+    float4 *ps0, *ps1;                // path state: (T, s1) (L, n.l of the pending sun term or 0)
     WfQueue qc, qs, qn;               // closest queue of this depth, shadow queue, closest queue of the next depth
     uint4 *hits;                      // per closest-queue slot: t, instance | voxel << 20, leaf, leaf origin
     DustHit *hits_out;                // != NULL (dust_trace_rays): write the caller's DustHit records instead
@@ -54,7 +55,6 @@ struct WfParams {
 };
 
 #define WF_CANDS 8                    // pre-culled candidates per ray; rays touching more instances take the slow path
-#define WF_PEND 1u                    // ps1.w flag: a sun term is pending on vis[path]
 
 __device__ __forceinline__ uint32_t wf_in_count(const WfParams &p)
 {
@@ -73,27 +73,38 @@ __device__ __forceinline__ bool wf_pixel(const FrameParams &f, uint32_t slot, ui
     return tile_y < f.tiles_y && px < f.cfg.width && py < f.cfg.height;
 }
 
+// Camera ray of path i (primary.rgen:9-21) and the path's PRNG stream; paths of pixels outside the frame get a ray
+// with tmax < tmin, which traces nothing.  Computed where it is needed (wf_trace, wf_shade) instead of being
+// written to and re-read from a queue: 100 B per path of HBM traffic less than a generated depth-0 queue.
+__device__ __forceinline__ bool wf_primary_ray(const WfParams &p, uint32_t i, float4 &a, float4 &b, uint32_t &s1, uint32_t &smp,
+                                               uint32_t &px, uint32_t &py, uint32_t &oi)
+{
+    const DustTraceConfig &cfg = p.f.cfg;
+    const uint32_t slot = i / p.batch_spp;
+    smp = p.batch_first + (i - slot * p.batch_spp);
+    a = make_float4(0.0f, 0.0f, 0.0f, 1.0f); b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    s1 = 0;
+    if (!wf_pixel(p.f, slot, px, py, oi)) return false;
+    const uint32_t s0 = pcg((py * cfg.width + px) ^ pcg(cfg.seed + 0x9E3779B9u * cfg.frame_index));
+    s1 = pcg(s0 + smp);
+    float jx = 0.5f, jy = 0.5f;
+    if (smp > 0) { jx = u01(pcg(s1 + 0u)); jy = u01(pcg(s1 + 1u)); }
+    f3 ro, rd;
+    camera_ray(p.f.cam, cfg.width, cfg.height, px, py, jx, jy, ro, rd);
+    a = make_float4(ro.x, ro.y, ro.z, p.f.cam.near);
+    b = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
+    return true;
+}
+
+// materialises the depth-0 queue (only when that queue goes to the persistent tracer: DUST_WF_PT_DEPTH=0, A/B runs)
 __global__ void __launch_bounds__(256) wf_gen_primary(const __grid_constant__ WfParams p)
 {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= p.n_paths) return;
-    const DustTraceConfig &cfg = p.f.cfg;
-    const uint32_t slot = i / p.batch_spp, smp = p.batch_first + (i - slot * p.batch_spp);
-    uint32_t px, py, oi;
-    float4 a = make_float4(0.0f, 0.0f, 0.0f, 1.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);     // tmax < tmin: traces nothing
-    uint32_t s1 = 0;
-    if (wf_pixel(p.f, slot, px, py, oi)) {
-        const uint32_t s0 = pcg((py * cfg.width + px) ^ pcg(cfg.seed + 0x9E3779B9u * cfg.frame_index));
-        s1 = pcg(s0 + smp);
-        float jx = 0.5f, jy = 0.5f;
-        if (smp > 0) { jx = u01(pcg(s1 + 0u)); jy = u01(pcg(s1 + 1u)); }
-        f3 ro, rd;
-        camera_ray(p.f.cam, cfg.width, cfg.height, px, py, jx, jy, ro, rd);                   // primary.rgen:9-21
-        a = make_float4(ro.x, ro.y, ro.z, p.f.cam.near);
-        b = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
-    }
+    float4 a, b;
+    uint32_t s1, smp, px, py, oi;
+    wf_primary_ray(p, i, a, b, s1, smp, px, py, oi);
     p.qc.a[i] = a; p.qc.b[i] = b; p.qc.path[i] = i;
-    p.ps0[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(s1));
     if (i == 0) p.counts[3] = p.n_paths;                               // size of the depth-0 closest queue, for kernels that read it from memory
 }
 
@@ -122,12 +133,15 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
     const uint32_t i = live && list ? __ldg(&list[k]) : k;
     float4 a = make_float4(0.0f, 0.0f, 0.0f, 1.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     uint32_t pw = 0;
-    if (live) { a = __ldg(&q.a[(size_t)i * q.stride]); b = __ldg(&q.b[(size_t)i * q.stride]); pw = q.path ? __ldg(&q.path[i]) : i; }
+    if (live) {
+        if (q.stride == 0u) { uint32_t s1, smp, px, py, oi; wf_primary_ray(p, i, a, b, s1, smp, px, py, oi); pw = i; }
+        else { a = __ldg(&q.a[(size_t)i * q.stride]); b = __ldg(&q.b[(size_t)i * q.stride]); pw = q.path ? __ldg(&q.path[i]) : i; }
+    }
     Counters st = {};
     Hit h;
     trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st);
     if (live) {
-        if (STATS && !q.path) st.primary_rays++;
+        if (STATS && q.stride == 2u) st.primary_rays++;
         if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = h.hit ? 1 : 0;
         else wf_store_hit(p, i, h.hit, h.t, h.inst, h.leaf, h.pos, h.voxel);
     }
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
             const unsigned want = __ballot_sync(full, need);
             if (want) {
                 if (need && have_ray) {
-                    if (STATS && !q.path) st.primary_rays++;
+                    if (STATS && q.stride == 2u) st.primary_rays++;
                     if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = hit ? 1 : 0;
                     else wf_store_hit(p, ri, hit, cur, b_inst, b_leaf, b_pos, b_vox);
                 }
@@ -356,27 +370,30 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
     bool emit_shadow = false, emit_bounce = false;
     f3 ro = mk3(0.0f, 0.0f, 0.0f), rd = mk3(0.0f, 0.0f, 0.0f);
     if (live) {
-        path = __ldg(&p.qc.path[i]);
-        const float4 a = __ldg(&p.qc.a[i]), b = __ldg(&p.qc.b[i]);
-        const uint4 hw = __ldg(&p.hits[i]);
-        const float4 s0 = p.ps0[path];
-        f3 T = mk3(s0.x, s0.y, s0.z), L = mk3(0.0f, 0.0f, 0.0f);
-        const uint32_t s1 = __float_as_uint(s0.w);
-        ro = mk3(a.x, a.y, a.z); rd = mk3(b.x, b.y, b.z);
-        uint32_t px = 0, py = 0, oi = 0;
+        float4 a, b;
+        f3 T = mk3(1.0f, 1.0f, 1.0f), L = mk3(0.0f, 0.0f, 0.0f);
+        uint32_t s1 = 0, px = 0, py = 0, oi = 0, smp = 1;
         bool valid = true;
-        uint32_t smp = 1;
-        if (p.depth == 0) {
-            const uint32_t slot = path / p.batch_spp;
-            smp = p.batch_first + (path - slot * p.batch_spp);
-            valid = wf_pixel(p.f, slot, px, py, oi);
+        if (p.depth == 0 && p.qc.stride == 0u) {                        // the depth-0 queue is implicit: path i, camera ray recomputed
+            path = i;
+            valid = wf_primary_ray(p, i, a, b, s1, smp, px, py, oi);
         } else {
-            const float4 s1v = p.ps1[path], s2v = p.ps2[path];
-            L = mk3(s1v.x, s1v.y, s1v.z);
-            if ((__float_as_uint(s1v.w) & WF_PEND) && !p.vis[path]) { L.x += s2v.x; L.y += s2v.y; L.z += s2v.z; }   // nee.rmiss:11-22
+            path = __ldg(&p.qc.path[i]);
+            a = __ldg(&p.qc.a[i]); b = __ldg(&p.qc.b[i]);
+            if (p.depth == 0) { float4 a2, b2; valid = wf_primary_ray(p, path, a2, b2, s1, smp, px, py, oi); }
+            else {
+                const float4 s0 = p.ps0[path], s1v = p.ps1[path];
+                T = mk3(s0.x, s0.y, s0.z); s1 = __float_as_uint(s0.w);
+                L = mk3(s1v.x, s1v.y, s1v.z);
+                if (s1v.w > 0.0f && !p.vis[path]) {                      // nee.rmiss:11-22: the previous vertex's sun term, with that vertex's throughput
+                    const f3 ts = acescg2srgb(mk3(p.f.sun_nee[0] * s1v.w, p.f.sun_nee[1] * s1v.w, p.f.sun_nee[2] * s1v.w));
+                    L.x += T.x * ts.x; L.y += T.y * ts.y; L.z += T.z * ts.z;
+                }
+            }
         }
-        uint32_t flags = 0;
-        f3 pend = mk3(0.0f, 0.0f, 0.0f);
+        const uint4 hw = __ldg(&p.hits[i]);
+        ro = mk3(a.x, a.y, a.z); rd = mk3(b.x, b.y, b.z);
+        float pend_ndl = 0.0f;                                           // n.l of this vertex's sun term while its shadow ray is in flight
         if (valid) {
             const bool hit = hw.y != 0xFFFFFFFFu;
             if (STATS) { if (p.depth == 0) st.primary_rays++; else st.bounce_rays++; }
@@ -399,10 +416,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
                 else { T.x = T.x * al.x; T.y = T.y * al.y; T.z = T.z * al.z; }          // final_gather.rchit:76-80
                 if (dot3(mk3(p.f.sky.direction[0], p.f.sky.direction[1], p.f.sky.direction[2]), sn) > 0.0f) {   // ambient_occlusion.rgen:33-50
                     if (STATS) st.shadow_rays++;
-                    const float ndl = dot3(sn, mk3(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2]));
-                    const f3 ts = acescg2srgb(mk3(p.f.sun_nee[0] * ndl, p.f.sun_nee[1] * ndl, p.f.sun_nee[2] * ndl));
-                    pend = mk3(T.x * ts.x, T.y * ts.y, T.z * ts.z);
-                    flags |= WF_PEND;
+                    pend_ndl = dot3(sn, mk3(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2]));
                     emit_shadow = true;
                 }
                 if (p.depth < cfg.max_bounces) {
@@ -427,8 +441,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__
             }
         }
         p.ps0[path] = make_float4(T.x, T.y, T.z, __uint_as_float(s1));
-        p.ps1[path] = make_float4(L.x, L.y, L.z, __uint_as_float(flags));
-        p.ps2[path] = make_float4(pend.x, pend.y, pend.z, 0.0f);
+        p.ps1[path] = make_float4(L.x, L.y, L.z, pend_ndl);
     }
     // ---- compact the emitted rays into the queues: one atomic per warp and queue
     {
@@ -475,7 +488,11 @@ __global__ void __launch_bounds__(256) wf_resolve(const __grid_constant__ WfPara
         const uint32_t path = slot * p.batch_spp + s;
         const float4 s1v = p.ps1[path];
         f3 L = mk3(s1v.x, s1v.y, s1v.z);
-        if ((__float_as_uint(s1v.w) & WF_PEND) && !p.vis[path]) { const float4 s2v = p.ps2[path]; L.x += s2v.x; L.y += s2v.y; L.z += s2v.z; }
+        if (s1v.w > 0.0f && !p.vis[path]) {
+            const float4 s0 = p.ps0[path];
+            const f3 ts = acescg2srgb(mk3(p.f.sun_nee[0] * s1v.w, p.f.sun_nee[1] * s1v.w, p.f.sun_nee[2] * s1v.w));
+            L.x += s0.x * ts.x; L.y += s0.y * ts.y; L.z += s0.z * ts.z;
+        }
         const f3 Lc = srgb2acescg(L);
         acc.x += Lc.x; acc.y += Lc.y; acc.z += Lc.z;
     }
