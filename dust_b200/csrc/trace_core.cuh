@@ -39,7 +39,10 @@ struct Counters {
 #endif
 #define DUST_MAX_BVH_DEPTH (DUST_SCRATCH_WORDS - 4)
 #ifndef DUST_WALK_REPS
-#define DUST_WALK_REPS 2                       // cells a lane may walk per voted WALK operation
+#define DUST_WALK_REPS 2                       // cells a lane may walk per voted WALK operation (persistent tracer)
+#endif
+#ifndef DUST_WALK_REPS_TS
+#define DUST_WALK_REPS_TS 3                    // the same inside trace_scene (one thread per ray: coherent queues)
 #endif
 
 enum : int { M_NEXT = 0, M_WALK = 1, M_LEAF = 2, M_DONE = 3 };
@@ -350,11 +353,10 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
         // the warp votes and executes the ONE operation most lanes wait for (ties to the cheaper one).
         int mode = nc > 0 ? M_NEXT : M_DONE, j = 0;
         for (;;) {
-            const unsigned m_next = __ballot_sync(full, mode == M_NEXT);
-            const unsigned m_walk = __ballot_sync(full, mode == M_WALK);
-            const unsigned m_leaf = __ballot_sync(full, mode == M_LEAF);
-            if ((m_next | m_walk | m_leaf) == 0) break;
-            const int n_next = __popc(m_next), n_walk = __popc(m_walk), n_leaf = __popc(m_leaf);
+            // one REDUX of three packed 8-bit counters instead of three ballots + popcounts
+            const uint32_t packed = __reduce_add_sync(full, mode < M_DONE ? (1u << (8 * mode)) : 0u);
+            if (packed == 0u) break;
+            const int n_next = (int)(packed & 255u), n_walk = (int)((packed >> 8) & 255u), n_leaf = (int)(packed >> 16);
             int op = M_WALK, cnt = n_walk;
             if (n_next > cnt) { op = M_NEXT; cnt = n_next; }
             if (n_leaf > cnt) { op = M_LEAF; cnt = n_leaf; }
@@ -365,7 +367,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
             }
             if (op == M_WALK) {
 #pragma unroll 1
-                for (int rep = 0; rep < DUST_WALK_REPS; rep++)             // several cells per vote: WALK -> WALK is the common transition
+                for (int rep = 0; rep < DUST_WALK_REPS_TS; rep++)             // several cells per vote: WALK -> WALK is the common transition
                     if (mode == M_WALK) {
                         const int r = walk_step<NL, STATS>(w, st);
                         mode = r == WS_LEAF ? M_LEAF : (r == WS_OUT ? M_NEXT : M_WALK);
