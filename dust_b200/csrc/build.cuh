@@ -6,7 +6,7 @@
 //   vb_scatter    one thread per voxel: axis swizzle (loader.rs:248-253), block_counts[block] += 1 and
 //                 grid[block * 64 + bit] = max((order + 1) << 9 | (i + 1))   (the last voxel of a cell wins, like
 //                 the collector's overwrite; duplicates count twice in block_counts, like the collector)
-//   vb_scan       single-CTA exclusive scans over the 64^3 blocks (collector order: material_ptr and material
+//   vb_scan_*     exclusive scans (two coalesced launches each) over the 64^3 blocks (collector order: material_ptr and material
 //                 write positions; tree order: leaf slots) and the 16^3 mid nodes
 //   vb_leaves     one thread per 4^3 block in TREE order (root child index, then mid child index =
 //                 Tree::iter_leaf order): occupancy mask from the grid, popcount, flag
@@ -65,24 +65,52 @@ __global__ void __launch_bounds__(256) vb_leaves(const unsigned long long *__res
     pop_block[block] = (uint32_t)__popcll(m);
 }
 
-// exclusive scan of `n` (multiple of 1024) uint32 in place, one CTA of 1024 threads; *total = sum
-__global__ void __launch_bounds__(1024) vb_scan(uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ total)
+// ---- exclusive scan of n = 1024 * gridDim.x uint32 in place (n <= 1024 * 1024): two launches, coalesced.
+//   vb_scan_partials   CTA b: sum of its 1024 elements -> partial[b]
+//   vb_scan_apply      CTA b: offset = sum of partial[0 .. b) (re-derived by every CTA: <= 1024 values), then a block-wide
+//                      exclusive scan of its own 1024 elements; the last CTA also writes the grand total
+__device__ __forceinline__ uint32_t vb_block_scan(uint32_t v, uint32_t *warp_sums, uint32_t &block_total)   // 1024 threads; returns the exclusive prefix
 {
-    __shared__ uint32_t part[1024];
-    const uint32_t per = n / 1024u, first = threadIdx.x * per;
-    uint32_t s = 0;
-    for (uint32_t k = 0; k < per; k++) s += a[first + k];
-    part[threadIdx.x] = s;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, ofs); if (lane >= (unsigned)ofs) inc += t; }
+    if (lane == 31u) warp_sums[warp] = inc;
     __syncthreads();
-    for (uint32_t ofs = 1; ofs < 1024u; ofs <<= 1) {                                    // Hillis-Steele over the 1024 partial sums
-        const uint32_t v = threadIdx.x >= ofs ? part[threadIdx.x - ofs] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, ofs); if (lane >= (unsigned)ofs) w += t; }
+        warp_sums[lane] = w;                                                             // inclusive over warps
     }
-    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
-    for (uint32_t k = 0; k < per; k++) { const uint32_t v = a[first + k]; a[first + k] = run; run += v; }
-    if (total && threadIdx.x == 1023u) *total = part[1023];
+    __syncthreads();
+    block_total = warp_sums[31];
+    const uint32_t before = warp ? warp_sums[warp - 1] : 0u;
+    __syncthreads();
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) vb_scan_partials(const uint32_t *__restrict__ a, uint32_t *__restrict__ partial)
+{
+    __shared__ uint32_t ws[32];
+    uint32_t total;
+    vb_block_scan(a[(size_t)blockIdx.x * 1024u + threadIdx.x], ws, total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) vb_scan_apply(uint32_t *__restrict__ a, const uint32_t *__restrict__ partial, uint32_t *__restrict__ total_out)
+{
+    __shared__ uint32_t ws[32];
+    uint32_t ptotal, total;
+    const uint32_t pv = threadIdx.x < gridDim.x ? partial[threadIdx.x] : 0u;
+    const uint32_t pex = vb_block_scan(pv, ws, ptotal);                                  // exclusive prefix of the CTA sums
+    __shared__ uint32_t offset;
+    if (threadIdx.x == blockIdx.x) offset = pex;
+    __syncthreads();
+    const size_t i = (size_t)blockIdx.x * 1024u + threadIdx.x;
+    const uint32_t ex = vb_block_scan(a[i], ws, total);
+    a[i] = offset + ex;
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = ptotal;
 }
 
 // per mid node (tree order): child mask from the leaf flags

@@ -369,7 +369,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     size_t o_q[3][3];
     for (int q = 0; q < 3; q++) { o_q[q][0] = take(n_paths * 16); o_q[q][1] = take(n_paths * 16); o_q[q][2] = take(n_paths * 4); }
     const size_t o_hits = take(n_paths * 16), o_acc = take((size_t)n_slots * 16), o_vis = take(n_paths);
-    const size_t o_cand = take(n_paths * 32), o_ovf = take(n_paths * 4);
+    const size_t o_cand = take(n_paths * 4 * WF_CANDS), o_ovf = take(n_paths * 4);
     if (off > ctx->wf_scratch_bytes) {
         if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
         CU_TRY(ctx, cudaMalloc(&ctx->wf_scratch, off));
@@ -640,7 +640,7 @@ int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n
     auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_grid = take((size_t)VB_BLOCKS * 64 * 8), o_cnt = take(VB_BLOCKS * 4), o_pop = take(VB_BLOCKS * 4), o_flag = take(VB_BLOCKS * 4);
     const size_t o_lmask = take(VB_BLOCKS * 8), o_mmask = take(VB_MIDS * 8), o_mflag = take(VB_MIDS * 4), o_mslot = take(VB_MIDS * 4);
-    const size_t o_counts = take(sizeof(VbCounts)), o_vox = take(memory == DUST_MEM_HOST ? (size_t)n * 4 : 0);
+    const size_t o_counts = take(sizeof(VbCounts)), o_partial = take(1024 * 4), o_vox = take(memory == DUST_MEM_HOST ? (size_t)n * 4 : 0);
     const int32_t rc = ensure_scratch(ctx, off);
     if (rc != DUST_OK) return rc;
     uint8_t *sc = static_cast<uint8_t *>(ctx->scratch);
@@ -649,6 +649,7 @@ int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + o_cnt), *pop = reinterpret_cast<uint32_t *>(sc + o_pop), *flag = reinterpret_cast<uint32_t *>(sc + o_flag),
              *mflag = reinterpret_cast<uint32_t *>(sc + o_mflag), *mslot = reinterpret_cast<uint32_t *>(sc + o_mslot);
     VbCounts *d_counts = reinterpret_cast<VbCounts *>(sc + o_counts);
+    uint32_t *partial = reinterpret_cast<uint32_t *>(sc + o_partial);
     const uchar4 *d_vox = reinterpret_cast<const uchar4 *>(voxels);
     cudaStream_t st = ctx->stream;
     if (memory == DUST_MEM_HOST && n) {
@@ -664,10 +665,15 @@ int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n
     vb_leaves<<<VB_BLOCKS / 256, 256, 0, st>>>(grid, lmask, flag, pop); count_launch(ctx);
     vb_mid_masks<<<VB_MIDS / 256, 256, 0, st>>>(flag, mmask, mflag); count_launch(ctx);
     CU_TRY(ctx, cudaMemcpyAsync(mslot, mflag, VB_MIDS * 4, cudaMemcpyDeviceToDevice, st));
-    vb_scan<<<1, 1024, 0, st>>>(cnt, VB_BLOCKS, nullptr); count_launch(ctx);               // material_ptr (collector.rs:76-82)
-    vb_scan<<<1, 1024, 0, st>>>(pop, VB_BLOCKS, &d_counts->n_materials); count_launch(ctx);  // where each block's bytes go
-    vb_scan<<<1, 1024, 0, st>>>(flag, VB_BLOCKS, &d_counts->n_leaves); count_launch(ctx);  // leaf slots, Tree::iter_leaf order
-    vb_scan<<<1, 1024, 0, st>>>(mslot, VB_MIDS, &d_counts->n_mids); count_launch(ctx);
+    auto scan = [&](uint32_t *a, uint32_t n_elems, uint32_t *total) {
+        vb_scan_partials<<<n_elems / 1024, 1024, 0, st>>>(a, partial);
+        vb_scan_apply<<<n_elems / 1024, 1024, 0, st>>>(a, partial, total);
+        count_launch(ctx); count_launch(ctx);
+    };
+    scan(cnt, VB_BLOCKS, nullptr);                                                         // material_ptr (collector.rs:76-82)
+    scan(pop, VB_BLOCKS, &d_counts->n_materials);                                          // where each block's bytes go
+    scan(flag, VB_BLOCKS, &d_counts->n_leaves);                                            // leaf slots, Tree::iter_leaf order
+    scan(mslot, VB_MIDS, &d_counts->n_mids);
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaMemcpyAsync(&h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));                                                // sizes of the blob
@@ -1044,7 +1050,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
 }
 
 // One chunk (<= 16 Mi rays) of a ray batch on `stream`: wf_cull (multi-instance scenes) + wf_trace_pt + the overflow pass.
-// `counters`: 4 words (overflow count, pad, 64-bit work counter); `cand`: cn * 36 bytes of scratch when need_cull.
+// `counters`: 4 words (overflow count, pad, 64-bit work counter); `cand`: cn * (4 * WF_CANDS + 4) bytes of scratch when need_cull.
 static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const DustRay *d_rays, DustHit *d_hits, uint32_t cn, cudaStream_t stream,
                                     uint32_t *counters, uint8_t *cand, bool need_cull, bool plain, bool stats, int nl)
 {
@@ -1070,7 +1076,7 @@ static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const 
     if (le != cudaSuccess) return le;
     if (need_cull) {
         p.cand = reinterpret_cast<uint4 *>(cand);
-        p.overflow = reinterpret_cast<uint32_t *>(cand + align_up((size_t)cn * 32, 256));
+        p.overflow = reinterpret_cast<uint32_t *>(cand + align_up((size_t)cn * 4 * WF_CANDS, 256));
         if (stats) wf_cull<true><<<grid, DUST_THREADS, 0, stream>>>(p, q, nullptr, ovf_count);
         else wf_cull<false><<<grid, DUST_THREADS, 0, stream>>>(p, q, nullptr, ovf_count);
         count_launch(ctx);
@@ -1112,7 +1118,7 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     uint64_t chunk_max = host ? (2ull << 20) : (need_cull ? (16ull << 20) : (1ull << 30));
     if (const char *e = std::getenv("DUST_RAYS_CHUNK")) chunk_max = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));   // tests: force several chunks
     const int n_slots = host ? 2 : 1;
-    const size_t cand_slot = need_cull ? align_up(align_up((size_t)std::min<uint64_t>(n, chunk_max) * 32, 256) + (size_t)std::min<uint64_t>(n, chunk_max) * 4, 256) : 0;
+    const size_t cand_slot = need_cull ? align_up(align_up((size_t)std::min<uint64_t>(n, chunk_max) * 4 * WF_CANDS, 256) + (size_t)std::min<uint64_t>(n, chunk_max) * 4, 256) : 0;
     if (cand_slot * n_slots > ctx->wf_scratch_bytes) {
         if (ctx->wf_scratch) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->wf_scratch)); ctx->wf_scratch = nullptr; ctx->wf_scratch_bytes = 0; }
         CU_TRY(ctx, cudaMalloc(&ctx->wf_scratch, cand_slot * n_slots));

@@ -48,13 +48,16 @@ struct WfParams {
     uint4 *hits;                      // per closest-queue slot: t, instance | voxel << 20, leaf, leaf origin
     DustHit *hits_out;                // != NULL (dust_trace_rays): write the caller's DustHit records instead
     uint8_t *vis;                     // per path: 1 = its pending shadow ray was occluded
-    uint4 *cand;                      // per queue slot: 2 x uint4 = up to WF_CANDS sorted candidate keys (wf_cull)
+    uint4 *cand;                      // per queue slot: WF_CANDS / 4 x uint4 = up to WF_CANDS sorted candidate keys (wf_cull)
     uint32_t *overflow;               // queue slots whose candidate list did not fit: traced by wf_trace with the full cull
     uint32_t *counts;                 // per depth: [4v+1] shadow rays, [4v+2] bounce rays (= next closest queue); [3] = n_paths
     float4 *acc;                      // per pixel slot, carried across batches
 };
 
-#define WF_CANDS 8                    // pre-culled candidates per ray; rays touching more instances take the slow path
+#ifndef WF_CANDS
+#define WF_CANDS 8                    // pre-culled candidates per ray (multiple of 4); rays touching more instances take the slow path
+#endif
+#define WF_CVECS (WF_CANDS / 4)
 
 __device__ __forceinline__ uint32_t wf_in_count(const WfParams &p)
 {
@@ -186,9 +189,9 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
         uint32_t c[WF_CANDS];
 #pragma unroll
         for (int k = 0; k < WF_CANDS; k++) c[k] = (!over && k < nc) ? sm[k * DUST_THREADS] : 0xFFFFFFFFu;
-        p.cand[2 * (size_t)i] = make_uint4(c[0], c[1], c[2], c[3]);
-        p.cand[2 * (size_t)i + 1] = make_uint4(c[4], c[5], c[6], c[7]);
-        if (over) p.cand[2 * (size_t)i].x = 0xFFFFFFFEu;               // marker: not pre-culled
+        if (over) c[0] = 0xFFFFFFFEu;                                  // marker: not pre-culled
+#pragma unroll
+        for (int v = 0; v < WF_CVECS; v++) p.cand[WF_CVECS * (size_t)i + v] = make_uint4(c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]);
     }
     const unsigned m = __ballot_sync(full, over);
     if (m) {
@@ -328,19 +331,28 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                     else {
                         ri = (uint32_t)idx;
                         const float4 a = __ldg(&q.a[(size_t)ri * q.stride]), b = __ldg(&q.b[(size_t)ri * q.stride]);
-                        uint4 c0, c1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                        if (p.cand) { c0 = __ldg(&p.cand[2 * (size_t)ri]); c1 = __ldg(&p.cand[2 * (size_t)ri + 1]); }
-                        else {
+                        uint4 c0, cv[WF_CVECS];
+#pragma unroll
+                        for (int v = 0; v < WF_CVECS; v++) cv[v] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                        if (p.cand) {
+#pragma unroll
+                            for (int v = 0; v < WF_CVECS; v++) cv[v] = __ldg(&p.cand[WF_CVECS * (size_t)ri + v]);
+                            c0 = cv[0];
+                        } else {
                             // single-instance scene (no wf_cull pass): the candidate list is the scene box test
                             const float te = sc.n_inst ? box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2],
                                                                    mk3(a.x, a.y, a.z), cull_inverse(mk3(b.x, b.y, b.z)), a.w, b.w) : CUDART_INF_F;
                             c0 = make_uint4(te != CUDART_INF_F ? cand_key(te, 0u, id_mask) : 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                            cv[0] = c0;
                         }
                         if (c0.x != 0xFFFFFFFEu) {                                     // else: overflow ray, wf_trace does it
                             pw = q.path ? __ldg(&q.path[ri]) : ri;
                             ro = mk3(a.x, a.y, a.z); tmin = a.w; rd = mk3(b.x, b.y, b.z); cur = b.w;
-                            sm[0 * DUST_THREADS] = c0.x; sm[1 * DUST_THREADS] = c0.y; sm[2 * DUST_THREADS] = c0.z; sm[3 * DUST_THREADS] = c0.w;
-                            sm[4 * DUST_THREADS] = c1.x; sm[5 * DUST_THREADS] = c1.y; sm[6 * DUST_THREADS] = c1.z; sm[7 * DUST_THREADS] = c1.w;
+#pragma unroll
+                            for (int v = 0; v < WF_CVECS; v++) {
+                                sm[(4 * v + 0) * DUST_THREADS] = cv[v].x; sm[(4 * v + 1) * DUST_THREADS] = cv[v].y;
+                                sm[(4 * v + 2) * DUST_THREADS] = cv[v].z; sm[(4 * v + 3) * DUST_THREADS] = cv[v].w;
+                            }
                             hit = false; b_inst = 0xFFFFFFFFu;
                             j = 0; exhausted = false;
                             have_ray = true;
