@@ -45,10 +45,13 @@ def test_ctypes_structs_match_header(tmp_path):
         "DustFrame": ["radiance", "hit_instance", "hit_leaf", "hit_voxel", "hit_t", "memory", "radiance_format", "gbuffer"],
         "DustGBuffer": ["albedo", "depth", "normal", "motion", "voxel_id"],
         "DustStats": ["primary_rays", "mask_words", "kernel_launches"],
+        "DustExposureParams": ["min_log_luminance", "log_luminance_range", "time_coefficient"],
+        "DustToneMapParams": ["color_space_conversion", "output_transfer_function", "dst_format"],
+        "DustTreeLayout": ["n_levels", "n_nodes16", "n_materials", "off_nodes16", "off_materials", "total_bytes", "bounds_min", "bounds_max"],
     }
     body = "".join(f'printf("{s} %zu\\n", sizeof({s}));\n' + "".join(
         f'printf("{s}.{f} %zu\\n", offsetof({s}, {f}));\n' for f in fs) for s, fs in fields.items())
-    body += 'printf("DustRay %zu\\nDustHit %zu\\n", sizeof(DustRay), sizeof(DustHit));\n'
+    body += 'printf("DustRay %zu\\nDustHit %zu\\nDustVoxel %zu\\n", sizeof(DustRay), sizeof(DustHit), sizeof(DustVoxel));\n'
     src = tmp_path / "layout.c"
     src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "dust_b200.h"\nint main(void){{\n{body}return 0;}}\n')
     exe = tmp_path / "layout"
@@ -59,7 +62,7 @@ def test_ctypes_structs_match_header(tmp_path):
         assert int(got[s]) == C.sizeof(cls), s
         for f in fs:
             assert int(got[f"{s}.{f}"]) == getattr(cls, f).offset, (s, f)
-    assert got["DustRay"] == "32" and got["DustHit"] == "16"
+    assert got["DustRay"] == "32" and got["DustHit"] == "16" and got["DustVoxel"] == "4"
     assert C.sizeof(capi.DustCamera) == 192 and C.sizeof(capi.DustSky) == 224
 
 
@@ -91,6 +94,13 @@ def test_no_device_means_error_not_fallback():
     assert lib.dust_ctx_create(0, None) == 1
     assert lib.dust_trace(None, None, None, None, None, None) == 1
     assert lib.dust_last_error_string(None) == b"null context"
+    # every entry point added since ABI v2 validates its arguments before touching a device
+    assert lib.dust_comm_init(None, None, 0, 1) == 1 and lib.dust_comm_destroy(None) == 1 and lib.dust_comm_unique_id(None) == 1
+    assert lib.dust_allgather_framebuffer(None, None, 0, None) == 1
+    assert lib.dust_exposure_create(None, None) == 1 and lib.dust_auto_exposure(None, None, None, 0, 0, 0, None, None) == 1
+    assert lib.dust_tone_map(None, None, None, None, 0, 0, 0, None, None) == 1
+    assert lib.dust_tree_build_voxels(None, None, 0, None, None, 0, None) == 1 and lib.dust_tree_layout(None, None) == 1
+    assert lib.dust_scene_update_transforms(None, None, None, 0) == 1
 
 
 def test_product_never_references_the_oracle():

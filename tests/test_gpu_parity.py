@@ -233,6 +233,30 @@ def test_sharded_frame_equals_whole_frame(castle_small, host, ctx, shards, pipel
     assert np.array_equal(out.cpu().numpy(), whole)
 
 
+def test_comm_allgather_single_rank(ctx):
+    """dust_comm_* / dust_allgather_framebuffer with a one-rank communicator: exercises the run-time NCCL binding
+    (dlopen, unique id, ncclCommInitRank, ncclAllGather on the context's stream) on one GPU."""
+    import torch
+    from dust_b200.pipeline import Context, shard_layout
+    uid = Context.comm_unique_id()
+    assert len(uid) == 128 and any(uid)
+    ctx.comm_init(uid, 0, 1)
+    try:
+        _, per = shard_layout(200, 120, 1)
+        ctx.use_torch_stream()
+        shard = torch.rand((per, 4), dtype=torch.float32, device="cuda")
+        gathered = torch.zeros((1, per, 4), dtype=torch.float32, device="cuda")
+        ctx.allgather_framebuffer(shard, gathered)
+        torch.cuda.synchronize()
+        assert torch.equal(gathered[0], shard)
+        with pytest.raises(Exception):
+            ctx.comm_init(uid, 0, 1)                        # one communicator per context
+    finally:
+        ctx.set_stream(None)
+        ctx.comm_destroy()
+    ctx.comm_destroy()                                      # idempotent
+
+
 def test_ray_batch_small_domain(oracle, host, ctx):
     """BASELINE config 5 in miniature: hierarchy!(4,4,2,2), sphere-union leaf fill, random rays."""
     from dust_b200 import scenes
