@@ -290,6 +290,21 @@ def ours(args, cfg):
     clk = clocks.stop()
     step_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
     kern_ms = sum(a.elapsed_time(c) for a, _, c in ev) / args.steps      # the trace kernel alone (same stream)
+
+    # ---- per-kernel view of the same call, live (not under a profiler): DUST_TRACE_TIMING drops an event behind every launch;
+    # one STATS pass gives what each launch added to the visit counters, K timed passes give the device time of each launch
+    tgt = shard_buf if world > 1 else frame
+    skw = dict(shard_index=rank, shard_count=world) if world > 1 else {}
+    scene.trace_device(cam, sky, W, H, tgt, stats=True, timing=True, **skw, **kw)
+    per_launch = ctx.launch_info()
+    for rec in per_launch:
+        rec["ms"] = 0.0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        scene.trace_device(cam, sky, W, H, tgt, timing=True, **skw, **kw)
+        for rec, t_rec in zip(per_launch, ctx.launch_info()):
+            assert rec["kernel"] == t_rec["kernel"]
+            rec["ms"] += t_rec["ms"] / args.steps
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,7 +356,17 @@ def ours(args, cfg):
     launches_per_step = launches / max(1, args.steps) - (1 if world > 1 else 0)     # resolve_kernel follows the all-gather
     pipeline = "frame_kernel (megakernel, 1 launch)" if cfg["max_bounces"] == 0 else \
         "wavefront pipeline: wf_gen_primary, wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_resolve (%d launches)" % launches_per_step
+    kernels, total_ms = [], sum(r["ms"] for r in per_launch) or 1.0
+    for r in per_launch:
+        b = 8 * r["mask_words"] + 4 * r["child_ptrs"] + 5 * r["hits_shaded"] + (16 * my_pixels if r["kernel"] in ("wf_resolve", "frame_kernel") else 0)
+        kernels.append({"kernel": r["kernel"], "ms": round(r["ms"], 4), "share": round(r["ms"] / total_ms, 4), "algorithmic_bytes": b,
+                        "achieved_GBps": round(b / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 else None,
+                        "rays": r["primary_rays"] + r["bounce_rays"] + r["shadow_rays"]})
+    dom = max(kernels, key=lambda k_: k_["ms"]) if kernels else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "dominant_kernel": None if dom is None else dict(dom, frac=(dom["achieved_GBps"] or 0.0) / peak,
+                                                                 note="device time between the CUDA events behind consecutive launches of a live dust_trace call (DUST_TRACE_TIMING), mean of the timed steps; bytes = 8 W + 4 P + 5 H of that launch"),
+                "kernels": kernels,
                 "kernel": "dust_trace = " + pipeline, "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_ray": alg_bytes / max(1.0, float(rank_counts[0].item() + rank_counts[1].item())), "peak_source": peak_src,
                 "traffic_source": traffic_note,

@@ -27,6 +27,7 @@ PIPELINE_FLAGS = {None: 0, "auto": 0, "megakernel": 4, "wavefront": 8}
 DUST_MEM_HOST, DUST_MEM_DEVICE = 0, 1
 DUST_FMT_RGBA32F, DUST_FMT_RGBA16F, DUST_FMT_YCOCG16F = 0, 1, 2
 DUST_TRACE_DEMODULATE = 16
+DUST_TRACE_TIMING = 32
 
 
 class DustError(RuntimeError):
@@ -103,6 +104,11 @@ class DustTreeLayout(C.Structure):
                [("bounds_min", C.c_int32 * 3), ("bounds_max", C.c_int32 * 3)]
 
 
+class DustLaunchInfo(C.Structure):
+    _fields_ = [("kernel", C.c_char * 24), ("ms", C.c_float), ("_pad", C.c_uint32)] + \
+               [(n, C.c_uint64) for n in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded")]
+
+
 class DustExposureParams(C.Structure):
     _fields_ = [("min_log_luminance", C.c_float), ("log_luminance_range", C.c_float), ("time_coefficient", C.c_float)]
 
@@ -158,6 +164,7 @@ SYMBOLS = {
     "dust_tone_map": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.POINTER(DustToneMapParams), C.c_void_p]),
     "dust_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(DustStats)]),
+    "dust_get_launch_info": (C.c_int32, [C.c_void_p, C.POINTER(DustLaunchInfo), C.c_uint32, C.POINTER(C.c_uint32)]),
 }
 DUST_COMM_ID_BYTES = 128
 

@@ -34,6 +34,14 @@ struct DustCtx {
     uint32_t *d_wf_counters = nullptr;
     int sms = 148;
     DustStats stats{};
+    // DUST_TRACE_TIMING: one event after every launch of the last dust_trace call (+ a counter snapshot with DUST_TRACE_STATS)
+    struct LaunchRec { const char *name; cudaEvent_t ev; };
+    bool timing_on = false;
+    cudaEvent_t ev_begin = nullptr;
+    std::vector<LaunchRec> launch_recs;
+    std::vector<cudaEvent_t> ev_pool;
+    DCounters *h_snaps = nullptr;            // pinned, kMaxLaunchRecs entries
+    bool snaps_valid = false;
     // multi-GPU: NCCL communicator of the shard group (dust_comm_init); NCCL is dlopen'ed on first use
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_size = 1;
@@ -328,7 +336,21 @@ void sun_radiance_host(const DustSky &sky, float ar2, const float dir[3], float 
     for (int r = 0; r < 3; r++) out[r] = (m[r] * xyz[0] + m[3 + r] * xyz[1]) + m[6 + r] * xyz[2];
 }
 
-void count_launch(DustCtx *ctx) { ctx->stats.kernel_launches++; }
+constexpr size_t kMaxLaunchRecs = 512;
+
+// called after every kernel launch; with DUST_TRACE_TIMING it also drops an event behind the launch (launches of one call are
+// back to back on one stream, so consecutive events bracket one kernel) and, in a STATS pass, snapshots the counters
+void count_launch(DustCtx *ctx, const char *name = nullptr)
+{
+    ctx->stats.kernel_launches++;
+    if (!ctx->timing_on || !name || ctx->launch_recs.size() >= kMaxLaunchRecs) return;
+    cudaEvent_t ev = nullptr;
+    if (ctx->launch_recs.size() < ctx->ev_pool.size()) ev = ctx->ev_pool[ctx->launch_recs.size()];
+    else { if (cudaEventCreate(&ev) != cudaSuccess) return; ctx->ev_pool.push_back(ev); }
+    if (ctx->snaps_valid) cudaMemcpyAsync(&ctx->h_snaps[ctx->launch_recs.size()], ctx->d_counters, sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaEventRecord(ev, ctx->stream);
+    ctx->launch_recs.push_back({ name, ev });
+}
 
 int32_t fetch_counters(DustCtx *ctx)
 {
@@ -405,13 +427,13 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
         else if (nl == 4) { if (stats) wf_trace<4, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<4, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
         else { if (stats) wf_trace<0, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<0, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
-        count_launch(ctx);
+        count_launch(ctx, list ? "wf_trace (overflow)" : "wf_trace");
     };
     cudaError_t pt_err = cudaSuccess;
     auto trace_pt = [&](const WfQueue &q, const uint32_t *count, uint32_t slot, uint32_t grid) {
         if (stats) wf_cull<true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, ovf_counts + slot);
         else wf_cull<false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, ovf_counts + slot);
-        count_launch(ctx);
+        count_launch(ctx, "wf_cull");
         auto launch = [&](auto kernel) {
             if (!pt_blocks) pt_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pt_blocks, kernel, DUST_THREADS, 0);
             const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(pt_blocks, 1)));
@@ -420,7 +442,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
         else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
         else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
-        count_launch(ctx);
+        count_launch(ctx, "wf_trace_pt");
         trace(q, ovf_counts + slot, p.overflow, grid);                 // rays whose candidate list overflowed (normally none: CTAs exit at once)
     };
 
@@ -434,7 +456,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         p.qc = q_even; p.qn = q_odd;
         // the depth-0 queue is implicit (slot i = camera ray of path i, recomputed by its consumers) unless it goes to the persistent tracer
         const bool implicit0 = pt_depth > 0;
-        if (!implicit0) { wf_gen_primary<<<grid256, 256, 0, ctx->stream>>>(p); count_launch(ctx); }
+        if (!implicit0) { wf_gen_primary<<<grid256, 256, 0, ctx->stream>>>(p); count_launch(ctx, "wf_gen_primary"); }
         for (uint32_t depth = 0; depth <= cfg.max_bounces; depth++) {
             p.depth = depth;
             p.qc = depth & 1 ? q_odd : q_even; p.qn = depth & 1 ? q_even : q_odd;
@@ -443,11 +465,11 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
             const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : (implicit0 ? nullptr : p.counts + 3);
             if (depth >= pt_depth) trace_pt(p.qc, n_closest, 2 * depth, grid128); else trace(p.qc, n_closest, nullptr, grid128);
             if (stats) wf_shade<true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_shade<false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p);
-            count_launch(ctx);
+            count_launch(ctx, "wf_shade");
             if (depth >= pt_depth) trace_pt(p.qs, p.counts + 4 * depth + 1, 2 * depth + 1, grid128); else trace(p.qs, p.counts + 4 * depth + 1, nullptr, grid128);
         }
         wf_resolve<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(p);
-        count_launch(ctx);
+        count_launch(ctx, "wf_resolve");
         CU_TRY(ctx, pt_err);
         CU_TRY(ctx, cudaGetLastError());
     }
@@ -531,6 +553,9 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
     if (ctx->d_wf_counters) cudaFree(ctx->d_wf_counters);
+    for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->h_snaps) cudaFreeHost(ctx->h_snaps);
     for (int k = 0; k < 2; k++) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1003,6 +1028,13 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     const bool stats = (cfg.flags & DUST_TRACE_STATS) != 0;
     p.counters = ctx->d_counters;
     if (stats) CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DCounters), ctx->stream));
+    ctx->timing_on = (cfg.flags & DUST_TRACE_TIMING) != 0;
+    if (ctx->timing_on) {
+        ctx->launch_recs.clear();
+        if (!ctx->ev_begin) CU_TRY(ctx, cudaEventCreate(&ctx->ev_begin));
+        if (!ctx->h_snaps) CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_snaps), kMaxLaunchRecs * sizeof(DCounters)));
+        ctx->snaps_valid = stats;
+    }
     if (cfg.shard_count > 1 && tiles_per_shard * cfg.shard_count != p.tiles_x * p.tiles_y)
         CU_TRY(ctx, cudaMemsetAsync(p.radiance32 ? (void *)p.radiance32 : (void *)p.radiance16, 0, out_pixels * px_bytes, ctx->stream));
 
@@ -1017,16 +1049,18 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     bool wavefront = cfg.max_bounces >= 1 && (uint64_t)tiles_per_shard * 1024u * cfg.spp >= (1u << 18);
     if (cfg.flags & DUST_TRACE_PIPELINE_WAVEFRONT) wavefront = true;
     if (cfg.flags & DUST_TRACE_PIPELINE_MEGAKERNEL) wavefront = false;
+    if (ctx->timing_on) CU_TRY(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (wavefront) {
         const int32_t rc = trace_wavefront(ctx, p, tiles_per_shard, nl, stats);
-        if (rc != DUST_OK) return rc;
+        if (rc != DUST_OK) { ctx->timing_on = false; return rc; }
     } else {
         auto launch = [&](auto kernel) { kernel<<<grid, DUST_THREADS, 0, ctx->stream>>>(p); };
         if (nl == 3) { if (stats) launch(frame_kernel<3, true>); else launch(frame_kernel<3, false>); }
         else if (nl == 4) { if (stats) launch(frame_kernel<4, true>); else launch(frame_kernel<4, false>); }
         else { if (stats) launch(frame_kernel<0, true>); else launch(frame_kernel<0, false>); }
-        count_launch(ctx);
+        count_launch(ctx, "frame_kernel");
     }
+    ctx->timing_on = false;
     CU_TRY(ctx, cudaGetLastError());
 
     if (frame->memory == DUST_MEM_HOST) {
@@ -1380,6 +1414,33 @@ int32_t dust_allgather_framebuffer(DustCtx *ctx, const void *shard, uint64_t byt
     if (!api) return fail(ctx, DUST_ERR_COMM, why);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     NCCL_TRY(ctx, api, api->AllGather(shard, gathered, (size_t)bytes_per_rank, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream));
+    return DUST_OK;
+}
+
+int32_t dust_get_launch_info(DustCtx *ctx, DustLaunchInfo *out, uint32_t capacity, uint32_t *n_out)
+{
+    if (!ctx || !n_out || (capacity && !out)) return DUST_ERR_INVALID_ARGUMENT;
+    *n_out = (uint32_t)ctx->launch_recs.size();
+    if (ctx->launch_recs.empty()) return DUST_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    DCounters prev;
+    memset(&prev, 0, sizeof prev);
+    cudaEvent_t before = ctx->ev_begin;
+    for (uint32_t k = 0; k < ctx->launch_recs.size() && k < capacity; k++) {
+        DustLaunchInfo &o = out[k];
+        memset(&o, 0, sizeof o);
+        strncpy(o.kernel, ctx->launch_recs[k].name, sizeof o.kernel - 1);
+        CU_TRY(ctx, cudaEventElapsedTime(&o.ms, before, ctx->launch_recs[k].ev));
+        before = ctx->launch_recs[k].ev;
+        if (ctx->snaps_valid) {                                             // counters are cumulative over the call: differences per launch
+            const DCounters &c = ctx->h_snaps[k];
+            o.primary_rays = c.primary_rays - prev.primary_rays; o.bounce_rays = c.bounce_rays - prev.bounce_rays;
+            o.shadow_rays = c.shadow_rays - prev.shadow_rays; o.mask_words = c.mask_words - prev.mask_words;
+            o.child_ptrs = c.child_ptrs - prev.child_ptrs; o.hits_shaded = c.hits_shaded - prev.hits_shaded;
+            prev = c;
+        }
+    }
     return DUST_OK;
 }
 

@@ -53,6 +53,15 @@ class Context:
         check(self.h, self.lib.dust_get_stats(self.h, C.byref(s)), "dust_get_stats")
         return s.as_dict()
 
+    def launch_info(self) -> list:
+        """Per-launch device times (and counter deltas) of the last trace call made with timing=True."""
+        n = C.c_uint32()
+        buf = (capi.DustLaunchInfo * 512)()
+        check(self.h, self.lib.dust_get_launch_info(self.h, buf, 512, C.byref(n)), "dust_get_launch_info")
+        return [{"kernel": buf[k].kernel.decode(), "ms": float(buf[k].ms),
+                 **{f: int(getattr(buf[k], f)) for f in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded")}}
+                for k in range(min(int(n.value), 512))]
+
     # ---- multi-GPU exchange step (dust_comm_* / dust_allgather_framebuffer) ---------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -240,10 +249,11 @@ class Scene:
         return res
 
     def trace_device(self, camera, sky, width, height, radiance, spp=1, max_bounces=0, seed=0, frame_index=0,
-                     shard_index=0, shard_count=1, stats=False, fmt=DUST_FMT_RGBA32F, hit_buffers=None, pipeline=None):
+                     shard_index=0, shard_count=1, stats=False, fmt=DUST_FMT_RGBA32F, hit_buffers=None, pipeline=None, timing=False):
         """Device-buffer call (no copies, no sync): `radiance` is a CUDA tensor the kernel writes."""
         ctx, lib = self.ctx, self.ctx.lib
-        flags = (DUST_TRACE_STATS if stats else 0) | (DUST_TRACE_WRITE_HITS if hit_buffers else 0) | PIPELINE_FLAGS[pipeline]
+        flags = (DUST_TRACE_STATS if stats else 0) | (DUST_TRACE_WRITE_HITS if hit_buffers else 0) | PIPELINE_FLAGS[pipeline] | \
+                (capi.DUST_TRACE_TIMING if timing else 0)
         cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count, flags)
         fr = DustFrame(_ptr(radiance), None, None, None, None, DUST_MEM_DEVICE, fmt)
         if hit_buffers:

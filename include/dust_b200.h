@@ -105,7 +105,10 @@ enum {
     /* Leave the primary-hit albedo factor out of the radiance (the reference's img_illuminance holds the
      * incoming light; tone_map.comp:192-203 multiplies DustGBuffer.albedo back in): radiance for
      * dust_tone_map.  Default (flag clear): the product, i.e. tone_map's `mapped` before exposure. */
-    DUST_TRACE_DEMODULATE = 16u
+    DUST_TRACE_DEMODULATE = 16u,
+    /* Measurement: drop a CUDA event behind every kernel launch of this call (and, together with DUST_TRACE_STATS,
+     * a snapshot of the counters), readable with dust_get_launch_info: per-kernel device times of the live run. */
+    DUST_TRACE_TIMING = 32u
 };
 
 /* Replaces the push constants + launch size of the four vkCmdTraceRaysKHR dispatches
@@ -272,6 +275,16 @@ int32_t dust_tone_map(DustCtx *ctx, const DustExposure *exposure, const void *il
                       uint32_t width, uint32_t height, uint32_t memory, const DustToneMapParams *params, void *dst);
 
 int32_t dust_get_stats(DustCtx *ctx, DustStats *out);
+/* The launches of the last dust_trace call made with DUST_TRACE_TIMING, in order: kernel name, device time between the
+ * event behind the previous launch and the one behind this launch, and (when that call also had DUST_TRACE_STATS) what
+ * this launch added to the counters.  Synchronises the context's stream.  *n_out = number of launches recorded. */
+typedef struct DustLaunchInfo {
+    char kernel[24];
+    float ms;
+    uint32_t _pad;
+    uint64_t primary_rays, bounce_rays, shadow_rays, mask_words, child_ptrs, hits_shaded;
+} DustLaunchInfo;
+int32_t dust_get_launch_info(DustCtx *ctx, DustLaunchInfo *out, uint32_t capacity, uint32_t *n_out);
 
 #ifdef __cplusplus
 }

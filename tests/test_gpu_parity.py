@@ -355,3 +355,28 @@ def test_cuda_matches_committed_golden_fixtures(oracle, host, ctx):
                            spp=3, max_bounces=2, seed=21, frame_index=5, hits=True)
     _assert_hits_equal(g, want["two_models_gi"])
     _assert_radiance_close(g, want["two_models_gi"])
+
+
+def test_launch_info_timing_and_counter_deltas(castle_small, host):
+    """DUST_TRACE_TIMING: one record per launch of the call; with STATS the per-launch counter deltas add up to the call's totals."""
+    import torch
+    from dust_b200 import scenes
+    W, H = 256, 144
+    cam = host.camera_look_at(width=W, height=H, **{k: v for k, v in scenes.CASTLE_CAMERA.items()})
+    sky = host.sunlight_bake(direction=host.castle_sun_direction(0.0))
+    ctx = castle_small.loaded.scene.ctx
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    ctx.use_torch_stream()
+    try:
+        for pipeline, names in (("wavefront", {"wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace (overflow)"}), ("megakernel", {"frame_kernel"})):
+            castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1, stats=True, timing=True, pipeline=pipeline)
+            info = ctx.launch_info()
+            tot = ctx.stats()
+            assert {r["kernel"] for r in info} == names and all(r["ms"] > 0 for r in info)
+            assert len(info) == (11 if pipeline == "wavefront" else 1)
+            for k in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded"):
+                assert sum(r[k] for r in info) == tot[k], k
+        castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1)     # no flag: the records of the last timed call stay
+        assert len(ctx.launch_info()) == 1
+    finally:
+        ctx.set_stream(None)
