@@ -380,3 +380,86 @@ def test_launch_info_timing_and_counter_deltas(castle_small, host):
         assert len(ctx.launch_info()) == 1
     finally:
         ctx.set_stream(None)
+
+
+def _mixed_scene(castle_small, host, oracle, ctx, extra=()):
+    """castle_small's 3-level instances + a 4-level synthetic domain + `extra` (matrix, model id) instances, built twice."""
+    from dust_b200.pipeline import Scene
+    dom = host.SynthDomain(seed=11, fill=0.03, domain_leaves=48)
+    desc = dom.describe()
+    dtree = ctx.upload_tree(desc)
+    otree = oracle.TreeView(desc)
+    dom_m = np.array([1, 0, 0, -96, 0, 1, 0, 40, 0, 0, 1, -96], np.float32)                   # above the castle
+    ginst = [(m, castle_small.loaded.trees[mid]) for mid, m in castle_small.loaded.instances] + [(dom_m, dtree)]
+    oinst = [(m, castle_small.omodels[mid].tree._h, castle_small.omodels[mid].materials, castle_small.ovox.palette)
+             for mid, m in castle_small.ovox.instances] + [(dom_m, otree._h, dom.materials, dom.palette)]
+    for m, mid in extra:
+        ginst.append((m, castle_small.loaded.trees[mid]))
+        oinst.append((m, castle_small.omodels[mid].tree._h, castle_small.omodels[mid].materials, castle_small.ovox.palette))
+    keep = (dom, desc, dtree, otree)
+    return Scene(ctx, ginst), oracle.Scene(oinst), keep
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
+def test_mixed_three_and_four_level_instances(castle_small, host, oracle, ctx, pipeline):
+    """A scene whose instances mix hierarchy!(4,2,2) and hierarchy!(4,4,2,2) trees runs the NL = 0 kernel instantiations
+    (levels decided per instance), and a sheared / non-uniformly scaled instance exercises the general 3x4 inverse."""
+    from dust_b200 import scenes
+    mid0 = castle_small.ovox.instances[0][0]
+    skew = np.array([1.5, 0.25, 0, 60, 0, 0.75, 0.1, 90, 0.2, 0, 1.25, -40], np.float32)
+    gscene, oscene, keep = _mixed_scene(castle_small, host, oracle, ctx, extra=[(skew, mid0)])
+    W, H = 224, 126
+    cam = host.camera_look_at(width=W, height=H, **{k: v for k, v in scenes.CASTLE_CAMERA.items()})
+    sky = host.sunlight_bake(direction=host.castle_sun_direction(0.0))
+    g = gscene.trace(cam, sky, W, H, spp=2, max_bounces=2, seed=9, hits=True, pipeline=pipeline)
+    o = oscene.render(cam, sky, W, H, spp=2, max_bounces=2, seed=9)
+    _assert_hits_equal(g, o)
+    _assert_radiance_close(g, o)
+    n_inst = len(castle_small.ovox.instances)
+    assert (o["hit_instance"] == n_inst).sum() > 50 and (o["hit_instance"] == n_inst + 1).sum() > 50     # the 4-level and the skewed instance are seen
+    lo, hi = castle_small.bounds()
+    rays = scenes.ray_batch(120_000, 1.0, seed=21)
+    rays["o"] = (lo - 30).astype(np.float32) + rays["o"] * (hi - lo + 60).astype(np.float32)
+    og, _ = oscene.trace_rays(rays)
+    assert np.array_equal(gscene.trace_rays(rays).view(np.uint32), og.view(np.uint32))
+
+
+def test_two_thousand_instances(teapot, host, oracle, ctx):
+    """2 000 instances of one tree on a jittered grid with the 24 axis rotations: 11 instance-id bits, a deep SAH BVH,
+    candidate lists that overflow the pre-cull record (rays along the grid rows touch dozens of boxes)."""
+    from dust_b200 import scenes
+    from dust_b200.pipeline import Scene
+    rng = np.random.default_rng(5)
+    rots = []
+    for perm in ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)):
+        for signs in ((1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)):
+            R = np.zeros((3, 3), np.float32)
+            for r in range(3):
+                R[r, perm[r]] = signs[r]
+            if np.linalg.det(R) < 0:
+                R[2] = -R[2]
+            rots.append(R)
+    mats = []
+    for k in range(2000):
+        gx, gy, gz = k % 20, (k // 20) % 10, k // 200
+        t = np.array([gx * 90, gy * 70, gz * 80], np.float32) + rng.integers(-6, 7, 3).astype(np.float32)
+        M = np.concatenate([rots[k % 24], t[:, None]], axis=1).astype(np.float32).reshape(12)
+        mats.append(M)
+    mid = teapot.ovox.instances[0][0]
+    gscene = Scene(ctx, [(m, teapot.loaded.trees[mid]) for m in mats])
+    om = teapot.omodels[mid]
+    oscene = oracle.Scene([(m, om.tree._h, om.materials, teapot.ovox.palette) for m in mats])
+    rays = scenes.ray_batch(150_000, 1.0, seed=31)
+    rays["o"] = np.array([-100, -100, -100], np.float32) + rays["o"] * np.array([2000, 900, 1000], np.float32)
+    rays["d"][::4, 1:] *= 0.02                                   # a quarter of the rays run along the grid rows
+    o, _ = oscene.trace_rays(rays)
+    assert 0.2 < (o["instance"] != 0xFFFFFFFF).mean() < 0.99 and o["instance"][o["instance"] != 0xFFFFFFFF].max() > 1500
+    assert np.array_equal(gscene.trace_rays(rays).view(np.uint32), o.view(np.uint32))
+    W, H = 160, 90
+    cam = host.camera_look_at((-150, 500, -200), (900, 300, 400), width=W, height=H)
+    sky = host.sunlight_bake()
+    for pipeline in PIPELINES:
+        g = gscene.trace(cam, sky, W, H, spp=2, max_bounces=1, seed=2, hits=True, pipeline=pipeline)
+        of = oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=2)
+        _assert_hits_equal(g, of)
+        _assert_radiance_close(g, of)
