@@ -168,6 +168,44 @@ def reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def reference_arm_rays(args, cfg):
+    """--impl reference --config 5: the oracle port on all host threads, each step a bounded sample of the ray batch."""
+    from dust_b200 import host, scenes
+    from oracle import pyoracle as po
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dom = host.SynthDomain(seed=5, fill=0.01, domain_leaves=1024)
+    desc = dom.describe()
+    otree = po.TreeView(desc)
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    osc = po.Scene([(ident, otree._h, dom.materials, dom.palette)])
+    n = int(args.rays or cfg["rays"])
+    rays = scenes.ray_batch(n, dom.extent, seed=5)
+    n_cal = min(n, 200_000)
+    t0 = time.perf_counter()
+    osc.trace_rays(rays[:n_cal])
+    rate = n_cal / max(time.perf_counter() - t0, 1e-6)
+    n_step = int(max(n_cal, min(n, 4.0 * rate)))                          # ~4 s of CPU work per step
+    for _ in range(args.warmup):
+        osc.trace_rays(rays[: max(n_cal, n_step // 8)])
+    tot_t = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        osc.trace_rays(rays[:n_step])
+        tot_t += time.perf_counter() - t0
+    value = args.steps * n_step / tot_t / 1e6
+    cores = os.cpu_count() or 1
+    sample = f"first {n_step} of {n} rays per step, all host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s, random-origin ray batch on the synthetic 4096^3 VDB", "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: {cfg['name']}", "rays_per_gpu": n, "leaves": dom.num_leaves},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU port of the reference semantics (oracle/); the reference itself has no ray traversal outside the Vulkan driver"}), flush=True)
+
+
 def workload_config(cfg, label, args, spp):
     return {"workload": f"BASELINE configs[{args.config}]: {cfg['name']}", "scene": label, "width": cfg["width"], "height": cfg["height"],
             "spp_per_frame": spp, "max_bounces": cfg["max_bounces"], "camera": "examples/castle.rs:126-128", "sun": "zenith (castle.rs:260-265 scroll 0)",
@@ -534,9 +572,9 @@ def main():
     cfg = CONFIGS[args.config]
     if args.config == 5:
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the frame configs (2, 1, 3)"}))
-            return
-        rays_config(args, cfg)
+            reference_arm_rays(args, cfg)
+        else:
+            rays_config(args, cfg)
         return
     if args.impl == "reference":
         reference_arm(args, cfg)
