@@ -393,7 +393,7 @@ def ours(args, cfg):
             traffic = None
     launches_per_step = launches / max(1, args.steps) - (1 if world > 1 else 0)     # resolve_kernel follows the all-gather
     pipeline = "frame_kernel (megakernel, 1 launch)" if cfg["max_bounces"] == 0 else \
-        "wavefront pipeline: wf_gen_primary, wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_resolve (%d launches)" % launches_per_step
+        "wavefront pipeline: wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_resolve (%d launches)" % launches_per_step
     kernels, total_ms = [], sum(r["ms"] for r in per_launch) or 1.0
     for r in per_launch:
         b = 8 * r["mask_words"] + 4 * r["child_ptrs"] + 5 * r["hits_shaded"] + (16 * my_pixels if r["kernel"] in ("wf_resolve", "frame_kernel") else 0)
@@ -515,6 +515,9 @@ def rays_config(args, cfg):
         int(hits_host["instance"][0])
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_same = bool(np.array_equal(hits_host.view(np.uint32).reshape(-1, 4), d_hits.cpu().numpy().view(np.uint32)))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
