@@ -239,15 +239,20 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         // inclusive end; a stepping axis that leaves the occupied bounds has t_next >= t_box (same float
         // expressions as the bounds planes, see the CPU checker): ONE comparison, no per-axis range checks
         if (!(t_next <= w.t_exit) || !(t_next < w.t_box)) { w.L4 = 0; return WS_OUT; }
-        int nx = w.jx, ny = w.jy, nz = w.jz;
+        int nx, ny, nz;
         // axes whose plane time ties the minimum step one cell; the others are re-derived from the ray at
         // t_next and clamped into the cell's own range — a no-op at leaf granularity when L4 == 1
-        if (tx <= t_next) nx = px_ ? cx + L4 : cx - 1;
-        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.x, t_next, w.o.x)) >> 2; nx = min(max(ip, cx), cx + L4 - 1); }
-        if (ty <= t_next) ny = py_ ? cy + L4 : cy - 1;
-        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.y, t_next, w.o.y)) >> 2; ny = min(max(ip, cy), cy + L4 - 1); }
-        if (tz <= t_next) nz = pz_ ? cz + L4 : cz - 1;
-        else if (L4 > 1) { const int ip = __float2int_rd(__fmaf_rn(w.d.z, t_next, w.o.z)) >> 2; nz = min(max(ip, cz), cz + L4 - 1); }
+        {   // select form — both values for every axis, no divergent regions: +1.6 % (config 2) / +3.4 % (config 5) over
+            // `if (t_a <= t_next) step else if (L4 > 1) re-derive` per axis (profiles/r01_history.md)
+            const int hx_ = cx + L4 - 1, hy_ = cy + L4 - 1, hz_ = cz + L4 - 1;
+            const int rx = min(max(__float2int_rd(__fmaf_rn(w.d.x, t_next, w.o.x)) >> 2, cx), hx_);
+            const int ry = min(max(__float2int_rd(__fmaf_rn(w.d.y, t_next, w.o.y)) >> 2, cy), hy_);
+            const int rz = min(max(__float2int_rd(__fmaf_rn(w.d.z, t_next, w.o.z)) >> 2, cz), hz_);
+            // (for L4 == 1 the clamp range is the single value c = j: the re-derived coordinate is the old one)
+            nx = tx <= t_next ? (px_ ? cx + L4 : cx - 1) : rx;
+            ny = ty <= t_next ? (py_ ? cy + L4 : cy - 1) : ry;
+            nz = tz <= t_next ? (pz_ ? cz + L4 : cz - 1) : rz;
+        }
         // the cached 4^3 node survives a step that stays inside its 16-cell
         w.have_mid = w.have_mid && (((uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz)) >> 2) == 0u);
         w.jx = nx; w.jy = ny; w.jz = nz;

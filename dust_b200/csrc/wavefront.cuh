@@ -367,8 +367,11 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 
 // One thread per ray of the closest queue of depth p.depth: apply the pending sun term, consume the
 // hit, emit the vertex's shadow and bounce rays.  The per-path arithmetic is frame_kernel's, in order.
+#ifndef DUST_SHADE_MIN_BLOCKS
+#define DUST_SHADE_MIN_BLOCKS 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(DUST_THREADS) wf_shade(const __grid_constant__ WfParams p)
+__global__ void __launch_bounds__(DUST_THREADS, DUST_SHADE_MIN_BLOCKS) wf_shade(const __grid_constant__ WfParams p)
 {
     const unsigned full = 0xffffffffu;
     const DustTraceConfig &cfg = p.f.cfg;
