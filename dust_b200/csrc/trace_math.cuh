@@ -204,10 +204,9 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
         const bool ky = (mx >= my) && (mz >= my);
         const bool kz = (my >= mz) && (mx >= mz);
         hitDistance = fminf(fminf(mx, my), mz);                         // :106
-        if (hitDistance + 0.001f >= t_max) return false;                // :107
         cell += (kx ? isx : 0) + (ky ? isy : 0) + (kz ? isz : 0);       // :103-104, :112
-        // deviation (2), see oracle: a tie-step that leaves 0..3 on any axis ends the walk
-        if (cell & 0x124) return false;
+        // :107, and deviation (2), see oracle: a tie-step that leaves 0..3 on any axis ends the walk — one exit for both
+        if ((hitDistance + 0.001f >= t_max) | ((cell & 0x124) != 0)) return false;
         hit = ((cell >> 2) & 0x30) | ((cell >> 1) & 0xC) | (cell & 3);
         mx += kx ? dx : 0.0f; my += ky ? dy : 0.0f; mz += kz ? dz : 0.0f;          // :110
     }

@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 
         if (op == W_WALK) {
 #pragma unroll 1
-            for (int rep = 0; rep < DUST_WALK_REPS; rep++)                 // several cells per vote: WALK -> WALK is the common transition
+            // cells per vote: two for the long empty runs of the 4096^3 domain (one: -5 % on config 5), one for 256^3 models, where
+            // a second cell serves too few lanes (+0.9 % on config 2)
+            for (int rep = 0; rep < (NL == 3 ? 1 : DUST_WALK_REPS); rep++)
                 if (mode == W_WALK) {
                     const int r = walk_step<NL, STATS>(w, st);
                     mode = r == WS_LEAF ? W_LEAF : (r == WS_OUT ? W_NEXT : W_WALK);
