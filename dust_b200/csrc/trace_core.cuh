@@ -128,8 +128,9 @@ __device__ __forceinline__ void cull_expand(const DSceneView &sc, f3 ro, f3 winv
     float t0 = box_entry(a.x, a.y, a.z, b.x, b.y, b.z, ro, winv, tmin, tmax);
     float t1 = box_entry(c.x, c.y, c.z, e.x, e.y, e.z, ro, winv, tmin, tmax);
     int c0 = __float_as_int(a.w), c1 = __float_as_int(b.w);
-    // (no near-first ordering of the two children: the candidate set does not depend on the visiting order, and
-    //  the list is sorted by entry distance as it is built)
+    // near child first: the candidate set does not depend on the visiting order, but candidates then arrive almost
+    // sorted and the insertion below rarely moves anything (without the swap wf_cull was 8 % slower)
+    if (t1 < t0) { const float tf = t0; t0 = t1; t1 = tf; const int ci = c0; c0 = c1; c1 = ci; }
     int next = -1;
 #pragma unroll
     for (int s = 0; s < 2; s++) {
