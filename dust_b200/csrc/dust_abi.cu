@@ -422,6 +422,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
     uint32_t pt_depth = 1;
     if (const char *e = std::getenv("DUST_WF_PT_DEPTH")) pt_depth = (uint32_t)atoi(e);           // tuning / A-B only
     int pt_blocks = 0;
+    const bool fuse0 = std::getenv("DUST_WF_FUSE0") != nullptr;                                  // A/B only: depth 0 as ONE kernel (measured 2.8 % slower)
 
     auto trace = [&](const WfQueue &q, const uint32_t *count, const uint32_t *list, uint32_t grid) {
         if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, list); }
@@ -463,9 +464,17 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
             if (depth == 0 && implicit0) { p.qc.a = nullptr; p.qc.b = nullptr; p.qc.path = nullptr; p.qc.stride = 0; }
             // queue sizes live on the device: launch for the largest possible queue, surplus CTAs exit at once
             const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : (implicit0 ? nullptr : p.counts + 3);
-            if (depth >= pt_depth) trace_pt(p.qc, n_closest, 2 * depth, grid128); else trace(p.qc, n_closest, nullptr, grid128);
-            if (stats) wf_shade<true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_shade<false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p);
-            count_launch(ctx, "wf_shade");
+            if (depth == 0 && implicit0 && fuse0) {
+                // depth 0 in one kernel: trace + shade, the hit record stays in registers
+                if (nl == 3) { if (stats) wf_trace_shade0<3, true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_trace_shade0<3, false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); }
+                else if (nl == 4) { if (stats) wf_trace_shade0<4, true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_trace_shade0<4, false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); }
+                else { if (stats) wf_trace_shade0<0, true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_trace_shade0<0, false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); }
+                count_launch(ctx, "wf_trace_shade0");
+            } else {
+                if (depth >= pt_depth) trace_pt(p.qc, n_closest, 2 * depth, grid128); else trace(p.qc, n_closest, nullptr, grid128);
+                if (stats) wf_shade<true><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p); else wf_shade<false><<<grid128, DUST_THREADS, 0, ctx->stream>>>(p);
+                count_launch(ctx, "wf_shade");
+            }
             if (depth >= pt_depth) trace_pt(p.qs, p.counts + 4 * depth + 1, 2 * depth + 1, grid128); else trace(p.qs, p.counts + 4 * depth + 1, nullptr, grid128);
         }
         wf_resolve<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(p);

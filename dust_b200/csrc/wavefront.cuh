@@ -372,17 +372,15 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 #ifndef DUST_SHADE_MIN_BLOCKS
 #define DUST_SHADE_MIN_BLOCKS 8
 #endif
+// All 32 lanes of a warp call this together (the emitted rays are compacted with warp votes); lanes without a ray
+// pass live = false.  `hw_in` != NULL: the hit record of slot i is passed in registers instead of read from p.hits
+// (the fused depth-0 kernel below).
 template <bool STATS>
-__global__ void __launch_bounds__(DUST_THREADS, DUST_SHADE_MIN_BLOCKS) wf_shade(const __grid_constant__ WfParams p)
+__device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_t i, const bool live, const uint4 *hw_in, Counters &st)
 {
     const unsigned full = 0xffffffffu;
     const DustTraceConfig &cfg = p.f.cfg;
-    const uint32_t n = wf_in_count(p);
-    if (blockIdx.x * DUST_THREADS >= n) return;
-    const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    bool live = i < n;
-    Counters st = {};
     uint32_t path = 0;
     bool emit_shadow = false, emit_bounce = false;
     f3 ro = mk3(0.0f, 0.0f, 0.0f), rd = mk3(0.0f, 0.0f, 0.0f);
@@ -408,7 +406,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_SHADE_MIN_BLOCKS) wf_shade(
                 }
             }
         }
-        const uint4 hw = __ldg(&p.hits[i]);
+        const uint4 hw = hw_in ? *hw_in : __ldg(&p.hits[i]);
         ro = mk3(a.x, a.y, a.z); rd = mk3(b.x, b.y, b.z);
         float pend_ndl = 0.0f;                                           // n.l of this vertex's sun term while its shadow ray is in flight
         if (valid) {
@@ -489,6 +487,39 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_SHADE_MIN_BLOCKS) wf_shade(
             }
         }
     }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS, DUST_SHADE_MIN_BLOCKS) wf_shade(const __grid_constant__ WfParams p)
+{
+    const uint32_t n = wf_in_count(p);
+    if (blockIdx.x * DUST_THREADS >= n) return;
+    const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
+    Counters st = {};
+    wf_shade_vertex<STATS>(p, i, i < n, nullptr, st);
+    if (STATS) flush_counters(p.f.counters, st);
+}
+
+// Experiment (DUST_WF_FUSE0=1; off by default): depth 0 of a frame in ONE kernel — the camera ray of path i is traced and its
+// vertex shaded at once, the hit record stays in registers.  Same arithmetic as wf_trace followed by wf_shade, bit-identical
+// frames, but 2.8 % slower on config 2: the latency-bound shading then runs at the tracer's occupancy (6 CTAs/SM, 80 registers)
+// instead of 8 (profiles/r01_history.md).
+template <int NL, bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace_shade0(const __grid_constant__ WfParams p)
+{
+    __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
+    const uint32_t n = p.n_paths;
+    if (blockIdx.x * DUST_THREADS >= n) return;
+    const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
+    const bool live = i < n;
+    float4 a = make_float4(0.0f, 0.0f, 0.0f, 1.0f), b = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    if (live) { uint32_t s1, smp, px, py, oi; wf_primary_ray(p, i, a, b, s1, smp, px, py, oi); }
+    Counters st = {};
+    Hit h;
+    trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, false, live, s_scratch + threadIdx.x, h, st);
+    const uint4 hw = h.hit ? make_uint4(__float_as_uint(h.t), h.inst | (h.voxel << 20), h.leaf, h.pos)
+                           : make_uint4(__float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    wf_shade_vertex<STATS>(p, i, live, &hw, st);
     if (STATS) flush_counters(p.f.counters, st);
 }
 
