@@ -438,13 +438,18 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         auto launch = [&](auto kernel) {
             if (!pt_blocks) pt_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pt_blocks, kernel, DUST_THREADS, 0);
             const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(pt_blocks, 1)));
-            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, work + slot);
+            kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, work + slot, ovf_counts + slot);
         };
-        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
-        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
-        else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
+        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true, true>); else launch(wf_trace_pt<3, false, true>); }
+        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true, true>); else launch(wf_trace_pt<4, false, true>); }
+        else { if (stats) launch(wf_trace_pt<0, true, true>); else launch(wf_trace_pt<0, false, true>); }
         count_launch(ctx, "wf_trace_pt");
-        trace(q, ovf_counts + slot, p.overflow, grid);                 // rays whose candidate list overflowed (normally none: CTAs exit at once)
+        // rays that wf_cull could not pre-cull: one warp per ray, persistent grid (the list length lives on the device)
+        const uint32_t sgrid = std::min<uint32_t>(grid, (uint32_t)ctx->sms * 8u);
+        if (nl == 3) { if (stats) wf_trace_slow<3, true><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); else wf_trace_slow<3, false><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); }
+        else if (nl == 4) { if (stats) wf_trace_slow<4, true><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); else wf_trace_slow<4, false><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); }
+        else { if (stats) wf_trace_slow<0, true><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); else wf_trace_slow<0, false><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); }
+        count_launch(ctx, "wf_trace_slow");
     };
 
     for (uint32_t first = 0; first < cfg.spp; first += batch_spp) {
@@ -479,6 +484,14 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         }
         wf_resolve<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(p);
         count_launch(ctx, "wf_resolve");
+        if (stats && std::getenv("DUST_DEBUG_STATS")) {                                           // queue sizes of this batch (diagnostics)
+            std::vector<uint32_t> h(kWfCounterWords);
+            CU_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_wf_counters, kWfCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint32_t d = 0; d <= cfg.max_bounces; d++)
+                fprintf(stderr, "[dust dbg] depth %u: shadow rays %u, bounce rays %u, slow-path rays closest %u / shadow %u\n", d, h[4 * d + 1], h[4 * d + 2],
+                        h[4 * kWfMaxDepths + 2 * d], h[4 * kWfMaxDepths + 2 * d + 1]);
+        }
         CU_TRY(ctx, pt_err);
         CU_TRY(ctx, cudaGetLastError());
     }
@@ -1128,13 +1141,25 @@ static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const 
         int per_sm = 0;
         le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
         const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
-        kernel<<<pgrid, DUST_THREADS, 0, stream>>>(p, q, nullptr, work);
+        kernel<<<pgrid, DUST_THREADS, 0, stream>>>(p, q, nullptr, work, ovf_count);
     };
-    if (nl == 3) { if (stats) launch(wf_trace_pt<3, true>); else launch(wf_trace_pt<3, false>); }
-    else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true>); else launch(wf_trace_pt<4, false>); }
-    else { if (stats) launch(wf_trace_pt<0, true>); else launch(wf_trace_pt<0, false>); }
+    if (need_cull) {
+        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true, true>); else launch(wf_trace_pt<3, false, true>); }
+        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true, true>); else launch(wf_trace_pt<4, false, true>); }
+        else { if (stats) launch(wf_trace_pt<0, true, true>); else launch(wf_trace_pt<0, false, true>); }
+    } else {
+        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true, false>); else launch(wf_trace_pt<3, false, false>); }
+        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true, false>); else launch(wf_trace_pt<4, false, false>); }
+        else { if (stats) launch(wf_trace_pt<0, true, false>); else launch(wf_trace_pt<0, false, false>); }
+    }
     count_launch(ctx);
-    if (need_cull) trace(ovf_count, p.overflow);                       // rays whose candidate list overflowed
+    if (need_cull) {                                                   // rays that wf_cull could not pre-cull: one warp per ray
+        const uint32_t sgrid = std::min<uint32_t>(grid, (uint32_t)ctx->sms * 8u);
+        if (nl == 3) { if (stats) wf_trace_slow<3, true><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); else wf_trace_slow<3, false><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); }
+        else if (nl == 4) { if (stats) wf_trace_slow<4, true><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); else wf_trace_slow<4, false><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); }
+        else { if (stats) wf_trace_slow<0, true><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); else wf_trace_slow<0, false><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); }
+        count_launch(ctx);
+    }
     return le != cudaSuccess ? le : cudaGetLastError();
 }
 

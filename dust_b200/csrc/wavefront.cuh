@@ -184,12 +184,22 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
         const f3 winv = cull_inverse(rd);
         int sp, pend, nc;
         cull_begin(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc);
-        while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc, st);
-        over = pend >= 0 || nc > WF_CANDS;                            // list incomplete or too long: slow path
+        bool trunc = false;
+        while (pend >= 0 && cull_room(sp, nc)) {
+            cull_expand<STATS>(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc, st);
+            // The record holds WF_CANDS keys: drop the farthest ones as the walk goes (the list is sorted, and the last kept key only
+            // moves nearer afterwards, so every dropped candidate starts at or behind it) — the scratch then always has room for
+            // the BVH stack and the walk completes.
+            if (nc > WF_CANDS) { nc = WF_CANDS; trunc = true; }
+        }
+        over = pend >= 0;                                             // BVH walk not finished (scratch full): slow path
         uint32_t c[WF_CANDS];
 #pragma unroll
         for (int k = 0; k < WF_CANDS; k++) c[k] = (!over && k < nc) ? sm[k * DUST_THREADS] : 0xFFFFFFFFu;
         if (over) c[0] = 0xFFFFFFFEu;                                  // marker: not pre-culled
+        // A truncated list is flagged in its last key (keys are non-negative floats: bit 31 is free).  The tracer finishes such a
+        // ray itself when its best hit lies before that key's entry distance and only otherwise hands it to the slow path.
+        else if (trunc) c[WF_CANDS - 1] |= 0x80000000u;
 #pragma unroll
         for (int v = 0; v < WF_CVECS; v++) p.cand[WF_CVECS * (size_t)i + v] = make_uint4(c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]);
     }
@@ -203,6 +213,68 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
     if (STATS) flush_counters(p.f.counters, st);
 }
 
+// ---- the slow path: ONE WARP PER RAY ------------------------------------------------------------------------------
+// Rays whose candidate list was not conclusive (they graze dozens of instance boxes and hit nothing early; a few hundred per frame) used to be
+// re-traced one thread per ray: a handful of warps, each walking 30+ instances in sequence, held the whole pass for 0.19 ms.
+// Here the 32 lanes of a warp take the INSTANCES of one ray in parallel: lane k enters instances k, k + 32, ... (walk_enter
+// is the exact box clip, the BVH is only an accelerator), walks each to its closest hit, and the warp reduces the
+// lexicographic minimum of (t, instance) — the same result as any other visiting order.  Persistent grid: warps stride
+// over the list, whose length lives on the device.
+template <int NL, bool STATS>
+__global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, const uint32_t *list)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const DSceneView &sc = p.f.scene;
+    const uint32_t n = *count;
+    const uint32_t warps = gridDim.x * (DUST_THREADS / 32u);
+    Counters st = {};
+    for (uint32_t k = blockIdx.x * (DUST_THREADS / 32u) + (threadIdx.x >> 5); k < n; k += warps) {
+        const uint32_t i = __ldg(&list[k]);
+        const float4 a = __ldg(&q.a[(size_t)i * q.stride]), b = __ldg(&q.b[(size_t)i * q.stride]);
+        const uint32_t pw = q.path ? __ldg(&q.path[i]) : i;
+        const f3 ro = mk3(a.x, a.y, a.z), rd = mk3(b.x, b.y, b.z);
+        const float tmin = a.w, tmax = b.w;
+        const bool any = (pw >> 31) != 0u;
+        bool hit = false;
+        float bt = tmax;
+        uint32_t b_inst = 0xFFFFFFFFu, b_leaf = 0, b_pos = 0, b_vox = 0;
+        Walk w;
+        w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
+        for (uint32_t inst = lane; inst < sc.n_inst; inst += 32u) {
+            if (!walk_enter<NL, STATS>(sc, w, inst, ro, rd, tmin, bt, st)) continue;       // bt: this lane's own best so far (tmax shrinks per lane)
+            for (;;) {
+                const int r = walk_step<NL, STATS>(w, st);
+                if (r == WS_OUT) break;
+                if (r == WS_LEAF) {
+                    float th; uint32_t vox;
+                    if (walk_leaf<STATS>(w, tmin, th, vox, st) && tmin <= th && th <= bt) {  // reportIntersectionEXT; ascending inst: ties keep the earlier one
+                        if (!hit || th < bt) { hit = true; bt = th; b_inst = inst; b_leaf = w.leaf_i; b_pos = walk_pos(w); b_vox = vox; }
+                        break;                                                              // first accepted hit is this instance's closest
+                    }
+                    w.L4 = 1;
+                }
+            }
+            if (any && hit) break;
+        }
+        // lexicographic minimum of (t, instance) over the lanes
+        float rt = hit ? bt : CUDART_INF_F;
+        uint32_t ri = hit ? b_inst : 0xFFFFFFFFu;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const float ot = __shfl_xor_sync(full, rt, ofs);
+            const uint32_t oi = __shfl_xor_sync(full, ri, ofs);
+            if (ot < rt || (ot == rt && oi < ri)) { rt = ot; ri = oi; }
+        }
+        const bool any_hit = ri != 0xFFFFFFFFu;
+        if (any) { if (lane == 0) p.vis[pw & 0x7FFFFFFFu] = any_hit ? 1 : 0; }
+        else if (!any_hit) { if (lane == 0) wf_store_hit(p, i, false, tmax, 0xFFFFFFFFu, 0u, 0u, 0u); }
+        else if (hit && b_inst == ri) wf_store_hit(p, i, true, bt, b_inst, b_leaf, b_pos, b_vox);        // exactly one lane owns the winner
+        if (STATS && q.stride == 2u && lane == 0) st.primary_rays++;
+    }
+    if (STATS) flush_counters(p.f.counters, st);
+}
+
 #ifndef DUST_PT_MIN_BLOCKS2
 #define DUST_PT_MIN_BLOCKS2 8                 // 64 registers: 8 CTAs / SM beat 6 with no spills that matter (A/B in profiles/r01_history.md)
 #endif
@@ -212,8 +284,11 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
 
 enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
 
-template <int NL, bool STATS>
-__global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : DUST_PT_MIN_BLOCKS4) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work)
+// CAND: the queue comes with pre-culled candidate records (p.cand, multi-instance scenes); without them the only candidate is the
+// scene box and the truncated-list logic compiles away.
+template <int NL, bool STATS, bool CAND>
+__global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : DUST_PT_MIN_BLOCKS4) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work,
+                                                                                                                  uint32_t *overflow_count)
 {
     __shared__ uint32_t s_cand[WF_CANDS * DUST_THREADS];
     const unsigned full = 0xffffffffu;
@@ -232,6 +307,7 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
     uint32_t b_inst = 0xFFFFFFFFu, b_leaf = 0, b_pos = 0, b_vox = 0;
     int mode = W_NEXT, j = 0;                                          // j == WF_CANDS or key 0xFFFFFFFF: list exhausted
     bool exhausted = true;
+    float e_trunc = CUDART_INF_F;                                      // truncated candidate list: entry distance of its last key (+inf: complete list)
     Walk w;
     w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
 
@@ -318,9 +394,14 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
             const unsigned want = __ballot_sync(full, need);
             if (want) {
                 if (need && have_ray) {
-                    if (STATS && q.stride == 2u) st.primary_rays++;
-                    if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = hit ? 1 : 0;
-                    else wf_store_hit(p, ri, hit, cur, b_inst, b_leaf, b_pos, b_vox);
+                    // a truncated list is conclusive only if the dropped candidates (all starting at or behind e_trunc) cannot change the result
+                    const bool conclusive = !CAND || e_trunc == CUDART_INF_F || (hit && ((pw >> 31) != 0u || cur < e_trunc));
+                    if (!conclusive) p.overflow[atomicAdd(overflow_count, 1u)] = ri;             // rare (hundreds per frame): wf_trace_slow redoes the ray
+                    else {
+                        if (STATS && q.stride == 2u) st.primary_rays++;
+                        if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = hit ? 1 : 0;
+                        else wf_store_hit(p, ri, hit, cur, b_inst, b_leaf, b_pos, b_vox);
+                    }
                 }
                 const int leader = __ffs(want) - 1;
                 unsigned long long base = 0;
@@ -336,10 +417,13 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                         uint4 c0, cv[WF_CVECS];
 #pragma unroll
                         for (int v = 0; v < WF_CVECS; v++) cv[v] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                        if (p.cand) {
+                        if (CAND) {
 #pragma unroll
                             for (int v = 0; v < WF_CVECS; v++) cv[v] = __ldg(&p.cand[WF_CVECS * (size_t)ri + v]);
                             c0 = cv[0];
+                            uint32_t &last = cv[WF_CVECS - 1].w;
+                            e_trunc = CUDART_INF_F;
+                            if ((last >> 31) && last < 0xFFFFFFFEu) { last &= 0x7FFFFFFFu; e_trunc = __uint_as_float(last & ~id_mask); }
                         } else {
                             // single-instance scene (no wf_cull pass): the candidate list is the scene box test
                             const float te = sc.n_inst ? box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2],

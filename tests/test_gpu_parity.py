@@ -368,7 +368,7 @@ def test_launch_info_timing_and_counter_deltas(castle_small, host):
     out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     ctx.use_torch_stream()
     try:
-        for pipeline, names in (("wavefront", {"wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace (overflow)"}), ("megakernel", {"frame_kernel"})):
+        for pipeline, names in (("wavefront", {"wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace_slow"}), ("megakernel", {"frame_kernel"})):
             castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1, stats=True, timing=True, pipeline=pipeline)
             info = ctx.launch_info()
             tot = ctx.stats()
