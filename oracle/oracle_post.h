@@ -5,6 +5,8 @@
  *   tone map + OETF       assets/shaders/tone_map.comp:36-219
  * Images: illuminance = R16G16B16A16_SFLOAT holding REBLUR_FrontEnd_PackRadianceAndNormHitDist's YCoCg
  * (headers/nrd.glsl:99-147), albedo = A2R10G10B10_UNORM_PACK32 (standard.rs:880-917), dst = float RGBA.
+ * Parity status: PARITY UNPINNED — the reference holds no test, golden image or fixture for these passes and cannot be
+ * run here; tests/test_post.py cross-checks this restatement against independent float64 formulas of the same shaders.
  * One documented deviation: log2() of the histogram is a fixed mul/add/div expression (o_post_log2) so
  * bins are bit-reproducible on the GPU; GLSL leaves log2's precision to the implementation. */
 #ifndef ORACLE_POST_H
