@@ -28,6 +28,7 @@ DUST_MEM_HOST, DUST_MEM_DEVICE = 0, 1
 DUST_FMT_RGBA32F, DUST_FMT_RGBA16F, DUST_FMT_YCOCG16F = 0, 1, 2
 DUST_TRACE_DEMODULATE = 16
 DUST_TRACE_TIMING = 32
+DUST_RAYS_ROUGH = 64
 
 
 class DustError(RuntimeError):

@@ -1108,7 +1108,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
 // One chunk (<= 16 Mi rays) of a ray batch on `stream`: wf_cull (multi-instance scenes) + wf_trace_pt + the overflow pass.
 // `counters`: 4 words (overflow count, pad, 64-bit work counter); `cand`: cn * (4 * WF_CANDS + 4) bytes of scratch when need_cull.
 static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const DustRay *d_rays, DustHit *d_hits, uint32_t cn, cudaStream_t stream,
-                                    uint32_t *counters, uint8_t *cand, bool need_cull, bool plain, bool stats, int nl)
+                                    uint32_t *counters, uint8_t *cand, bool need_cull, bool plain, bool stats, int nl, bool rough)
 {
     WfParams p;
     memset(&p, 0, sizeof p);
@@ -1121,13 +1121,21 @@ static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const 
     const uint32_t grid = (cn + DUST_THREADS - 1) / DUST_THREADS;
     uint32_t *ovf_count = counters;
     unsigned long long *work = reinterpret_cast<unsigned long long *>(counters + 2);
-    auto trace = [&](const uint32_t *count, const uint32_t *list) {
-        if (nl == 3) { if (stats) wf_trace<3, true><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); else wf_trace<3, false><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); }
-        else if (nl == 4) { if (stats) wf_trace<4, true><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); else wf_trace<4, false><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); }
-        else { if (stats) wf_trace<0, true><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); else wf_trace<0, false><<<grid, DUST_THREADS, 0, stream>>>(p, q, count, list); }
+    // kernel variants by (levels, stats | rough): DUST_RAYS_ROUGH has its own instantiations (without the STATS counters)
+    const int variant = rough ? 2 : (stats ? 1 : 0);
+#define DUST_BY_NL(KERNEL, ...)                                                                                  \
+    do {                                                                                                         \
+        if (nl == 3) { if (variant == 2) KERNEL<3, false, ##__VA_ARGS__, true> LAUNCH; else if (variant == 1) KERNEL<3, true, ##__VA_ARGS__> LAUNCH; else KERNEL<3, false, ##__VA_ARGS__> LAUNCH; } \
+        else if (nl == 4) { if (variant == 2) KERNEL<4, false, ##__VA_ARGS__, true> LAUNCH; else if (variant == 1) KERNEL<4, true, ##__VA_ARGS__> LAUNCH; else KERNEL<4, false, ##__VA_ARGS__> LAUNCH; } \
+        else { if (variant == 2) KERNEL<0, false, ##__VA_ARGS__, true> LAUNCH; else if (variant == 1) KERNEL<0, true, ##__VA_ARGS__> LAUNCH; else KERNEL<0, false, ##__VA_ARGS__> LAUNCH; } \
+    } while (0)
+    if (plain) {
+#define LAUNCH <<<grid, DUST_THREADS, 0, stream>>>(p, q, nullptr, nullptr)
+        DUST_BY_NL(wf_trace);
+#undef LAUNCH
         count_launch(ctx);
-    };
-    if (plain) { trace(nullptr, nullptr); return cudaGetLastError(); }
+        return cudaGetLastError();
+    }
     cudaError_t le = cudaMemsetAsync(counters, 0, 16, stream);
     if (le != cudaSuccess) return le;
     if (need_cull) {
@@ -1137,29 +1145,26 @@ static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const 
         else wf_cull<false><<<grid, DUST_THREADS, 0, stream>>>(p, q, nullptr, ovf_count);
         count_launch(ctx);
     }
-    auto launch = [&](auto kernel) {
-        int per_sm = 0;
-        le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DUST_THREADS, 0);
-        const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
-        kernel<<<pgrid, DUST_THREADS, 0, stream>>>(p, q, nullptr, work, ovf_count);
-    };
-    if (need_cull) {
-        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true, true>); else launch(wf_trace_pt<3, false, true>); }
-        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true, true>); else launch(wf_trace_pt<4, false, true>); }
-        else { if (stats) launch(wf_trace_pt<0, true, true>); else launch(wf_trace_pt<0, false, true>); }
-    } else {
-        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true, false>); else launch(wf_trace_pt<3, false, false>); }
-        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true, false>); else launch(wf_trace_pt<4, false, false>); }
-        else { if (stats) launch(wf_trace_pt<0, true, false>); else launch(wf_trace_pt<0, false, false>); }
+    int per_sm = 0;
+    {
+        // occupancy of the variant about to be launched (all variants of one NL share their launch bounds)
+        if (nl == 3) le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_pt<3, false, true>, DUST_THREADS, 0);
+        else if (nl == 4) le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_pt<4, false, true>, DUST_THREADS, 0);
+        else le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_pt<0, false, true>, DUST_THREADS, 0);
     }
+    const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(per_sm, 1)));
+#define LAUNCH <<<pgrid, DUST_THREADS, 0, stream>>>(p, q, nullptr, work, ovf_count)
+    if (need_cull) DUST_BY_NL(wf_trace_pt, true); else DUST_BY_NL(wf_trace_pt, false);
+#undef LAUNCH
     count_launch(ctx);
-    if (need_cull) {                                                   // rays that wf_cull could not pre-cull: one warp per ray
+    if (need_cull) {                                                   // rays whose candidate list was not conclusive: one warp per ray
         const uint32_t sgrid = std::min<uint32_t>(grid, (uint32_t)ctx->sms * 8u);
-        if (nl == 3) { if (stats) wf_trace_slow<3, true><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); else wf_trace_slow<3, false><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); }
-        else if (nl == 4) { if (stats) wf_trace_slow<4, true><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); else wf_trace_slow<4, false><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); }
-        else { if (stats) wf_trace_slow<0, true><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); else wf_trace_slow<0, false><<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow); }
+#define LAUNCH <<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow)
+        DUST_BY_NL(wf_trace_slow);
+#undef LAUNCH
         count_launch(ctx);
     }
+#undef DUST_BY_NL
     return le != cudaSuccess ? le : cudaGetLastError();
 }
 
@@ -1216,7 +1221,7 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
         if (host) le = cudaMemcpyAsync(const_cast<DustRay *>(d_rays) + first, rays + first, (size_t)cn * sizeof(DustRay), cudaMemcpyHostToDevice, st);
         if (le == cudaSuccess)
             le = launch_ray_chunk(ctx, scene, d_rays + first, d_hits + first, cn, st, ctx->d_wf_counters + 4 * sl,
-                                  static_cast<uint8_t *>(ctx->wf_scratch) + cand_slot * sl, need_cull, plain, stats, nl);
+                                  static_cast<uint8_t *>(ctx->wf_scratch) + cand_slot * sl, need_cull, plain, stats, nl, (flags & DUST_RAYS_ROUGH) != 0);
         if (host && le == cudaSuccess) le = cudaMemcpyAsync(hits + first, d_hits + first, (size_t)cn * sizeof(DustHit), cudaMemcpyDeviceToHost, st);
     }
     if (host) {

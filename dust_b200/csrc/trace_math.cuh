@@ -215,4 +215,19 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
     return true;
 }
 
+// assets/shaders/final_gather/rough.rint:46-58 — the far-field intersection shader: a non-empty leaf is one solid 4x4x4 box,
+// hit where the ray enters it (no DDA); voxel id 0.  The caller applies the [tmin, tmax] acceptance.
+__device__ __forceinline__ bool leaf_rough(f3 origin, f3 dir, uint32_t grid_lo, uint32_t grid_hi, float &t_out, uint32_t &voxel)
+{
+    float ax = (0.0f - origin.x) / dir.x, bx = (4.0f - origin.x) / dir.x;
+    float ay = (0.0f - origin.y) / dir.y, by = (4.0f - origin.y) / dir.y;
+    float az = (0.0f - origin.z) / dir.z, bz = (4.0f - origin.z) / dir.z;
+    const float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    if (t_min >= t_max || (grid_lo | grid_hi) == 0u) return false;      // :47-53
+    t_out = t_min + 0.0f;                                               // :54; canonical +0
+    voxel = 0u;
+    return true;
+}
+
 }  // namespace dust

@@ -124,7 +124,9 @@ __device__ __forceinline__ void wf_store_hit(const WfParams &p, uint32_t i, bool
 
 // One thread per ray of a queue; the same trace_scene as the megakernel.
 // `list` != NULL: trace only the queue slots list[0 .. *count) (the rays wf_cull could not pre-cull).
-template <int NL, bool STATS>
+// ROUGH (ray batches only, DUST_RAYS_ROUGH): block-granular leaves; a compile-time flag — as a run-time one the cold branch cost the
+// hot path registers (-2.5 % on config 5).
+template <int NL, bool STATS, bool ROUGH = false>
 __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count,
                                                                           const uint32_t *list)
 {
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
     }
     Counters st = {};
     Hit h;
-    trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st);
+    trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st, ROUGH);
     if (live) {
         if (STATS && q.stride == 2u) st.primary_rays++;
         if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = h.hit ? 1 : 0;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
 // is the exact box clip, the BVH is only an accelerator), walks each to its closest hit, and the warp reduces the
 // lexicographic minimum of (t, instance) — the same result as any other visiting order.  Persistent grid: warps stride
 // over the list, whose length lives on the device.
-template <int NL, bool STATS>
+template <int NL, bool STATS, bool ROUGH = false>
 __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, const uint32_t *list)
 {
     const unsigned full = 0xffffffffu;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
                 if (r == WS_OUT) break;
                 if (r == WS_LEAF) {
                     float th; uint32_t vox;
-                    if (walk_leaf<STATS>(w, tmin, th, vox, st) && tmin <= th && th <= bt) {  // reportIntersectionEXT; ascending inst: ties keep the earlier one
+                    if (walk_leaf<STATS>(w, tmin, th, vox, st, ROUGH) && tmin <= th && th <= bt) {  // reportIntersectionEXT; ascending inst: ties keep the earlier one
                         if (!hit || th < bt) { hit = true; bt = th; b_inst = inst; b_leaf = w.leaf_i; b_pos = walk_pos(w); b_vox = vox; }
                         break;                                                              // first accepted hit is this instance's closest
                     }
@@ -286,7 +288,7 @@ enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
 
 // CAND: the queue comes with pre-culled candidate records (p.cand, multi-instance scenes); without them the only candidate is the
 // scene box and the truncated-list logic compiles away.
-template <int NL, bool STATS, bool CAND>
+template <int NL, bool STATS, bool CAND, bool ROUGH = false>
 __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : DUST_PT_MIN_BLOCKS4) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work,
                                                                                                                   uint32_t *overflow_count)
 {
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
         } else if (op == W_LEAF) {
             if (mode == W_LEAF) {
                 float th; uint32_t vox;
-                if (walk_leaf<STATS>(w, tmin, th, vox, st) && tmin <= th && th <= cur) {               // reportIntersectionEXT
+                if (walk_leaf<STATS>(w, tmin, th, vox, st, ROUGH) && tmin <= th && th <= cur) {   // reportIntersectionEXT
                     if (pw >> 31) { hit = true; exhausted = true; }                    // any hit ends a shadow ray
                     else if (!hit || th < cur || w.inst < b_inst) {                    // (t, instance) lexicographic
                         hit = true; cur = th; b_inst = w.inst; b_leaf = w.leaf_i; b_pos = walk_pos(w); b_vox = vox;

@@ -261,7 +261,7 @@ class Scene:
         check(ctx.h, lib.dust_trace(ctx.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr)), "dust_trace")
 
     # ---- dust_trace_rays -------------------------------------------------------------------------
-    def trace_rays(self, rays: np.ndarray, stats=False, out=None) -> np.ndarray:
+    def trace_rays(self, rays: np.ndarray, stats=False, out=None, rough=False) -> np.ndarray:
         """Host-buffer call.  Copies and kernels of consecutive 2 Mi-ray chunks overlap when `rays` / `out` are pinned."""
         rays = np.ascontiguousarray(rays)
         assert rays.dtype == RAY_DTYPE
@@ -269,7 +269,7 @@ class Scene:
         assert hits.dtype == HIT_DTYPE and len(hits) == len(rays) and hits.flags.c_contiguous
         ctx = self.ctx
         check(ctx.h, ctx.lib.dust_trace_rays(ctx.h, self.h, _ptr(rays), len(rays), _ptr(hits), DUST_MEM_HOST,
-                                             DUST_TRACE_STATS if stats else 0), "dust_trace_rays")
+                                             (DUST_TRACE_STATS if stats else 0) | (capi.DUST_RAYS_ROUGH if rough else 0)), "dust_trace_rays")
         return hits
 
     def trace_rays_device(self, rays, hits, n, stats=False):

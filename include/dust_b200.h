@@ -108,7 +108,12 @@ enum {
     DUST_TRACE_DEMODULATE = 16u,
     /* Measurement: drop a CUDA event behind every kernel launch of this call (and, together with DUST_TRACE_STATS,
      * a snapshot of the counters), readable with dust_get_launch_info: per-kernel device times of the live run. */
-    DUST_TRACE_TIMING = 32u
+    DUST_TRACE_TIMING = 32u,
+    /* dust_trace_rays only: block-granular leaves — the reference's far-field intersection shader
+     * (assets/shaders/final_gather/rough.rint:46-58, the rays of final_gather.rgen:38-51): every non-empty leaf is a solid
+     * 4x4x4 box, hit where the ray enters it; DustHit.voxel = 0, DustHit.leaf = the block (gl_PrimitiveID).  First piece of
+     * SURVEY.md 8f rank 2 (the far-field gather); the radiance cache those hits look up is not built. */
+    DUST_RAYS_ROUGH = 64u
 };
 
 /* Replaces the push constants + launch size of the four vkCmdTraceRaysKHR dispatches

@@ -183,6 +183,11 @@ OScene *o_scene_create(uint32_t n, const float *obj2world, const OTree *const *t
 
 void o_scene_set_cull(OScene *s, int enabled) { s->cull = enabled; }
 
+/* Block-granular leaves (assets/shaders/final_gather/rough.rint:46-58, the reference's far-field intersection shader): a
+ * non-empty leaf is hit where the ray enters its 4x4x4 box, no DDA.  Process-wide switch, set around a call by the tests. */
+static int g_rough_blocks;
+void o_set_rough_blocks(int enabled) { g_rough_blocks = enabled; }
+
 void o_scene_set_previous(OScene *s, const float *obj2world_prev)
 {
     for (uint32_t k = 0; k < s->n; k++) memcpy(s->inst[k].prev_obj2world, obj2world_prev + 12 * (size_t)k, 12 * sizeof(float));
@@ -366,7 +371,14 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
             st->mask_words++;
             float lo_[3] = { o[0] - (float)cmin[0], o[1] - (float)cmin[1], o[2] - (float)cmin[2] };   /* hit.rint:140 */
             float th; uint32_t vox;
-            if (o_leaf_dda(lo_, d, grid, tmin, &th, &vox) && tmin <= th && th <= tmax) {   /* reportIntersectionEXT */
+            int reported;
+            if (g_rough_blocks) {
+                float tb[2];
+                intersect_aabb(lo_, d, 0.0f, 4.0f, tb);                 /* rough.rint:46 */
+                reported = !(tb[0] >= tb[1]) && grid != 0;              /* :47-53 */
+                th = tb[0] + 0.0f; vox = 0;                             /* :54 reportIntersectionEXT(initialIntersectionT.x, 0); canonical +0 */
+            } else reported = o_leaf_dda(lo_, d, grid, tmin, &th, &vox);
+            if (reported && tmin <= th && th <= tmax) {                 /* reportIntersectionEXT */
                 out->t = th; out->leaf_ptr = ptr; out->voxel = vox;
                 memcpy(out->leaf_min, cmin, sizeof cmin);
                 memcpy(out->o, o, sizeof o); memcpy(out->d, d, sizeof d);

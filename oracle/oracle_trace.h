@@ -108,6 +108,8 @@ void o_render_rows(const OScene *s, const OCamera *cam, const OSky *sky, const O
                    OStats *stats, uint32_t n_threads);
 
 /* Explicit ray batch, closest hit (BASELINE config 5) */
+/* rough.rint: leaves are solid 4x4x4 boxes (hit = entry into the box, voxel 0).  Process-wide; affects every later trace call. */
+void o_set_rough_blocks(int enabled);
 void o_trace_rays(const OScene *s, const ORay *rays, uint64_t n, OHitRec *hits, OStats *stats, uint32_t n_threads);
 
 /* debug aid: every ray of one pixel's paths + the oracle's answers (voxel bit 31 = any-hit ray) */

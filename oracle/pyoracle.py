@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
         "o_scene_set_previous": (None, [vp, vp]),
         "o_render_rows": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), vp, u32, vp, vp, vp, vp, vp, C.POINTER(OStats), u32]),
         "o_trace_rays": (None, [vp, vp, u64, vp, C.POINTER(OStats), u32]),
+        "o_set_rough_blocks": (None, [i32]),
         "o_debug_pixel": (u32, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), u32, u32, vp, vp, u32, pf32]),
         "o_leaf_dda": (i32, [pf32, pf32, u64, f32, pf32, pu32]),
         "o_camera_ray": (None, [C.POINTER(OCamera), u32, u32, u32, u32, f32, f32, pf32, pf32]),
@@ -406,12 +407,17 @@ class Scene:
         n = lib().o_debug_pixel(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), px, py, rays.ctypes.data, hits.ctypes.data, cap, rgba)
         return rays[:n], hits[:n], np.array(rgba, np.float32)
 
-    def trace_rays(self, rays: np.ndarray, threads=None):
+    def trace_rays(self, rays: np.ndarray, threads=None, rough=False):
+        """rough: block-granular leaves (final_gather/rough.rint): a leaf is hit where the ray enters its 4^3 box."""
         rays = np.ascontiguousarray(rays)
         assert rays.dtype.itemsize == 32
         hits = np.zeros(len(rays), HIT_DTYPE)
         st = OStats()
-        lib().o_trace_rays(self._h, rays.ctypes.data, len(rays), hits.ctypes.data, C.byref(st), threads or os.cpu_count() or 1)
+        lib().o_set_rough_blocks(int(bool(rough)))
+        try:
+            lib().o_trace_rays(self._h, rays.ctypes.data, len(rays), hits.ctypes.data, C.byref(st), threads or os.cpu_count() or 1)
+        finally:
+            lib().o_set_rough_blocks(0)
         return hits, st.as_dict()
 
 

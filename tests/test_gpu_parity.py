@@ -463,3 +463,26 @@ def test_two_thousand_instances(teapot, host, oracle, ctx):
         of = oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=2)
         _assert_hits_equal(g, of)
         _assert_radiance_close(g, of)
+
+
+def test_ray_batch_rough_block_hits(castle_small, teapot, host, oracle, ctx):
+    """DUST_RAYS_ROUGH (final_gather/rough.rint): block-granular leaves, far-field ray interval [8, far], against the oracle bit for
+    bit — multi-instance scene (pre-cull + persistent lanes + slow path) and a single-instance one (no cull pass)."""
+    from dust_b200 import scenes
+    lo, hi = castle_small.bounds()
+    rays = scenes.ray_batch(150_000, 1.0, seed=41)
+    rays["o"] = lo.astype(np.float32) - 20 + rays["o"] * (hi - lo + 40).astype(np.float32)
+    rays["tmin"] = 8.0
+    rays["tmax"][::3] = 200.0
+    o, _ = castle_small.oscene.trace_rays(rays, rough=True)
+    fine, _ = castle_small.oscene.trace_rays(rays)
+    assert 0.1 < (o["instance"] != 0xFFFFFFFF).mean() < 0.95 and not np.array_equal(o.view(np.uint32), fine.view(np.uint32))
+    g = castle_small.loaded.scene.trace_rays(rays, rough=True)
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+    assert np.array_equal(castle_small.loaded.scene.trace_rays(rays).view(np.uint32), fine.view(np.uint32))     # the flag does not stick
+    tl, th = teapot.bounds()
+    r2 = scenes.ray_batch(100_000, 1.0, seed=42)
+    r2["o"] = tl.astype(np.float32) - 30 + r2["o"] * (th - tl + 60).astype(np.float32)
+    o2, _ = teapot.oscene.trace_rays(r2, rough=True)
+    assert (o2["instance"] != 0xFFFFFFFF).mean() > 0.02
+    assert np.array_equal(teapot.loaded.scene.trace_rays(r2, rough=True).view(np.uint32), o2.view(np.uint32))

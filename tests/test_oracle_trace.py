@@ -225,3 +225,43 @@ def test_gbuffer_images_of_the_primary_hit(oracle, teapot, host):
     mo = g2["motion"].astype(np.float32)
     assert np.abs(mo[hit][:, 0] - 1.5).max() < 2e-3 and np.abs(mo[hit][:, 1]).max() < 2e-3 and np.abs(mo[hit][:, 2] + 0.25).max() < 2e-3
     assert (mo[~hit] == 0).all() and (mo[..., 3] == 0).all()
+
+
+def test_rough_block_hits_against_brute_force(oracle, teapot):
+    """final_gather/rough.rint: with block-granular leaves a ray hits the first leaf box it enters (within [tmin, tmax]);
+    the hierarchical walk must agree with a float64 slab test over ALL leaf boxes."""
+    model = teapot.omodels[0]
+    pos, _ = model.tree.iter_leaf()
+    lo = pos.astype(np.float64)
+    rng = np.random.default_rng(17)
+    n = 3000
+    rays = np.zeros(n, oracle.RAY_DTYPE)
+    size = np.array(model.size, np.float32)
+    rays["o"] = (rng.random((n, 3), dtype=np.float32) * 3 - 1) * size
+    target = rng.random((n, 3), dtype=np.float32) * size
+    d = target - rays["o"]
+    rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["tmin"] = 8.0                                               # AMBIENT_OCCLUSION_THRESHOLD, final_gather.rgen:47
+    rays["tmax"] = 1e4
+    one = oracle.Scene([(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), model.tree._h, model.materials, teapot.ovox.palette)])
+    hits, _ = one.trace_rays(rays, rough=True)
+    fine, _ = one.trace_rays(rays)
+    agree = differ = nhit = 0
+    for i in range(n):
+        o, dd = rays["o"][i].astype(np.float64), rays["d"][i].astype(np.float64)
+        with np.errstate(divide="ignore"):
+            t0, t1 = (lo - o) / dd, (lo + 4.0 - o) / dd
+        tn, tf = np.minimum(t0, t1).max(axis=1), np.maximum(t0, t1).min(axis=1)
+        ok = (tn < tf) & (tn >= 8.0) & (tn <= 1e4)                   # a box straddling tmin is skipped (reportIntersectionEXT rejects t < tmin)
+        ref = int(np.argmin(np.where(ok, tn, np.inf))) if ok.any() else None
+        got = int(hits["leaf"][i]) if hits["instance"][i] != 0xFFFFFFFF else None
+        if ref == got and (ref is None or abs(tn[ref] - float(hits["t"][i])) < 1e-3 * (1 + tn[ref])):
+            agree += 1
+            nhit += ref is not None
+        else:
+            differ += 1
+    assert nhit > 300 and differ <= 0.003 * n, (nhit, differ)
+    assert (hits["voxel"][hits["instance"] != 0xFFFFFFFF] == 0).all()
+    # (a leaf box straddling tmin is skipped by the block test while the fine DDA may still hit a voxel behind tmin inside it,
+    #  so block hits are not simply "nearer than fine hits" — only different)
+    assert not np.array_equal(hits["t"], fine["t"])
