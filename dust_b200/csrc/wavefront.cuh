@@ -6,7 +6,7 @@
 // lanes and 17 lanes waiting for the slowest ray of the warp (profiles/r01_history.md).  The wavefront
 // pipeline cuts a path at its vertices and keeps rays, not paths, in flight:
 //
-//   wf_gen_primary   camera rays of every (pixel, sample) path of the batch          -> closest queue
+//   (depth-0 queue)  implicit: slot i is the camera ray of path i, recomputed by the kernels that need it
 //   per depth v = 0 .. max_bounces:
 //     trace          closest hit of every ray of the queue                           -> hit records
 //     wf_shade       apply the previous vertex's sun visibility, consume the hit (sky on a miss,
@@ -16,13 +16,14 @@
 //   wf_resolve       last visibility, sRGB -> ACEScg, mean over samples in sample order -> frame
 //
 // trace = wf_trace (one thread per ray) for the coherent depth-0 queues; for the incoherent queues
-// behind a bounce it is wf_cull + wf_trace_pt: candidate instances are collected with all lanes busy,
-// then persistent lanes walk them and CLAIM THE NEXT RAY of the queue the moment their own is finished.
+// behind a bounce it is wf_cull + wf_trace_pt + wf_trace_slow: candidate instances are collected with all lanes
+// busy (the 8 nearest per ray), persistent lanes walk them and CLAIM THE NEXT RAY of the queue the moment their own
+// is finished, and the few rays whose truncated list was not conclusive are redone one WARP per ray.
 // Every ray is traced by the same walk code as in the megakernel and every float of a path is
 // accumulated in the same order, so results are bit-identical to frame_kernel; queue order (atomics)
 // varies from run to run but no result depends on it.  (Sorting the bounce rays by direction bin was
 // tried and removed: with refilling lanes it only added a pass and scattered the path-state accesses.)
-// Path state and queues live in HBM: ~200 B per path per batch.
+// Path state and queues live in HBM: ~150 B per path per batch.
 #pragma once
 #include "kernels.cuh"
 
