@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -1374,26 +1375,23 @@ struct NcclApi {
 NcclApi *nccl_api(std::string &why)
 {
     static NcclApi api;
-    static bool tried = false;
     static std::string err;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;                                        // contexts of different GPUs may be driven from different threads
+    std::call_once(once, [] {
         const char *override_path = std::getenv("DUST_NCCL_LIB");
         api.lib = dlopen(override_path ? override_path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!api.lib) err = std::string("dlopen libnccl.so.2: ") + dlerror();
-        else {
-            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
-            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
-            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
-            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
-            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
-            if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
-                err = "libnccl.so.2 lacks a required symbol";
-                dlclose(api.lib);
-                api.lib = nullptr;
-            }
+        if (!api.lib) { err = std::string("dlopen libnccl.so.2: ") + dlerror(); return; }
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
+            err = "libnccl.so.2 lacks a required symbol";
+            dlclose(api.lib);
+            api.lib = nullptr;
         }
-    }
+    });
     why = err;
     return api.lib ? &api : nullptr;
 }

@@ -103,6 +103,20 @@ def test_no_device_means_error_not_fallback():
     assert lib.dust_scene_update_transforms(None, None, None, 0) == 1
 
 
+def test_nccl_binding_resolves_at_run_time():
+    """dust_comm_unique_id dlopens libnccl.so.2 on first use: with NCCL present it yields 128 non-trivial bytes (no GPU needed),
+    without it the call fails cleanly with DUST_ERR_COMM — never a load-time dependency of the library."""
+    from dust_b200 import capi
+    lib = capi.load()
+    buf = (C.c_uint8 * capi.DUST_COMM_ID_BYTES)()
+    rc = lib.dust_comm_unique_id(buf)
+    assert rc in (0, 6)
+    if rc == 0:
+        assert any(buf)
+    out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out
+
+
 def test_product_never_references_the_oracle():
     """oracle/ is test infrastructure: no source under dust_b200/ or include/ may include, import, link or
     dlopen it (a product path through the oracle would void every parity claim)."""
