@@ -58,6 +58,14 @@ class OExposureParams(C.Structure):
     _fields_ = [("min_log_lum", C.c_float), ("log_lum_range", C.c_float), ("time_coeff", C.c_float)]
 
 
+class OSpatialHashEntry(C.Structure):
+    _fields_ = [("fingerprint", C.c_uint32), ("radiance", C.c_uint32), ("last_accessed_frame", C.c_uint16), ("sample_count", C.c_uint16)]
+
+
+class OSpatialHashKey(C.Structure):
+    _fields_ = [("position", C.c_int32 * 3), ("direction", C.c_uint32)]
+
+
 class OHistogram(C.Structure):
     _fields_ = [("histogram", C.c_uint32 * 256), ("avg", C.c_float)]
 
@@ -137,6 +145,13 @@ def lib() -> C.CDLL:
         "o_exposure_histogram": (None, [vp, u32, u32, C.POINTER(OExposureParams), C.POINTER(OHistogram)]),
         "o_exposure_average": (None, [C.POINTER(OHistogram), u32, u32, C.POINTER(OExposureParams)]),
         "o_tone_map": (None, [vp, vp, u32, u32, f32, pf32, u32, vp]),
+        "o_xxhash32": (u32, [u32]),
+        "o_cache_fingerprint": (u32, [C.POINTER(OSpatialHashKey)]), "o_cache_location": (u32, [C.POINTER(OSpatialHashKey), u32]),
+        "o_logluv_encode": (u32, [pf32]), "o_logluv_decode": (None, [u32, pf32]),
+        "o_normal_to_face_id": (u32, [pf32]), "o_face_id_to_normal": (None, [u32, pf32]),
+        "o_cache_key_of": (None, [pf32, pf32, C.POINTER(OSpatialHashKey)]),
+        "o_cache_insert": (None, [vp, u32, C.POINTER(OSpatialHashKey), pf32, u32]),
+        "o_cache_get": (i32, [vp, u32, C.POINTER(OSpatialHashKey), u32, pf32, pu32]),
         "o_dense_from_tree": (vp, [vp]), "o_dense_free": (None, [vp]),
         "o_dense_march": (i32, [vp, C.POINTER(f64), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
     }
@@ -419,6 +434,31 @@ class Scene:
         finally:
             lib().o_set_rough_blocks(0)
         return hits, st.as_dict()
+
+
+# ---- radiance cache (oracle_cache.c): groundwork for SURVEY 8f rank 2, no CUDA counterpart yet ---------
+
+class RadianceCache:
+    """Sequential semantics of headers/spatial_hash.glsl's insert / get on a table of `capacity` SpatialHashEntry."""
+
+    def __init__(self, capacity: int):
+        self.capacity = int(capacity)
+        self.table = (OSpatialHashEntry * (self.capacity + 2))()
+
+    @staticmethod
+    def key(position, direction) -> OSpatialHashKey:
+        return OSpatialHashKey((C.c_int32 * 3)(*[int(v) for v in position]), int(direction))
+
+    def insert(self, key, value, frame_index):
+        lib().o_cache_insert(self.table, self.capacity, C.byref(key), (C.c_float * 3)(*[float(v) for v in value]), int(frame_index))
+
+    def get(self, key, frame_index):
+        out, n = (C.c_float * 3)(), C.c_uint32()
+        found = lib().o_cache_get(self.table, self.capacity, C.byref(key), int(frame_index), out, C.byref(n))
+        return bool(found), np.array(out[:], np.float32), int(n.value)
+
+    def entries(self) -> np.ndarray:
+        return np.frombuffer(self.table, dtype=np.dtype([("fingerprint", "<u4"), ("radiance", "<u4"), ("frame", "<u2"), ("count", "<u2")])).copy()
 
 
 # ---- post chain (oracle_post.c) ----------------------------------------------------------------------
