@@ -133,9 +133,6 @@ enum { DUST_MEM_HOST = 0, DUST_MEM_DEVICE = 1 };
  * REBLUR_FrontEnd_PackRadianceAndNormHitDist (headers/nrd.glsl:99-147): half (Y, Co, Cg, 1) */
 enum { DUST_FMT_RGBA32F = 0, DUST_FMT_RGBA16F = 1, DUST_FMT_YCOCG16F = 2 };
 
-/* Replaces the GBuffer images the reference writes (standard.rs:880-917).  With shard_count == 1
- * every array is row-major width*height.  With shard_count > 1 `radiance` is the compact
- * per-shard tile buffer (dust_shard_layout) and the hit arrays must be NULL. */
 /* The G-buffer images of the primary hit that hit.rchit:57-94 / miss.rmiss:13-16 write for the downstream
  * consumers (NRD, tone map; formats: GBuffer, standard.rs:880-917), for sample 0 of every pixel.  Row-major
  * width*height, same memory space as the frame, shard_count == 1 only; NULL members are skipped.
@@ -149,8 +146,11 @@ typedef struct DustGBuffer {
     uint32_t *voxel_id;        /* R32_UINT: voxel << 24 | palette_index << 16 | instance & 0xFFFF            hit.rchit:87 */
 } DustGBuffer;
 
+/* Replaces the GBuffer images the reference writes (standard.rs:880-917).  With shard_count == 1
+ * every array is row-major width*height.  With shard_count > 1 `radiance` is the compact
+ * per-shard tile buffer (dust_shard_layout) and the hit arrays must be NULL. */
 typedef struct DustFrame {
-    void *radiance;            /* RGBA32F (ACEScg rgb, a = 1) or RGBA16F */
+    void *radiance;            /* radiance_format: RGBA32F / RGBA16F (ACEScg rgb, a = 1) or YCOCG16F */
     uint32_t *hit_instance;    /* 0xFFFFFFFF = miss */
     uint32_t *hit_leaf;        /* index in Tree::iter_leaf order == gl_PrimitiveID (geometry.rs:68) */
     uint8_t *hit_voxel;        /* x<<4 | y<<2 | z inside the leaf (hit.rint:30-32) */
