@@ -72,7 +72,40 @@ def case_sky(oracle):
     return out
 
 
-CASES = {"two_models_primary": case_primary, "two_models_gi": case_gi, "sky_bake": case_sky}
+def _rays(s, n, seed):
+    from dust_b200 import scenes
+    lo, hi = s.bounds()
+    rays = scenes.ray_batch(n, 1.0, seed=seed)
+    rays["o"] = lo.astype(np.float32) - 6 + rays["o"] * (hi - lo + 12).astype(np.float32)
+    return rays
+
+
+def case_rays(oracle):
+    """Explicit ray batch: fine hits (hit.rint) and block-granular far-field hits (final_gather/rough.rint, tmin = 8)."""
+    s = _built(oracle)
+    rays = _rays(s, 4000, 77)
+    fine, _ = s.oscene.trace_rays(rays)
+    far = rays.copy()
+    far["tmin"] = 8.0
+    rough, _ = s.oscene.trace_rays(far, rough=True)
+    return {"hit_fine": fine.view(np.uint32).reshape(-1, 4), "hit_rough": rough.view(np.uint32).reshape(-1, 4)}
+
+
+def case_post(oracle):
+    """Demodulated YCoCg16F frame + G-buffer of the primary hit -> exposure histogram / adapted luminance -> tone map (sRGB OETF)."""
+    s = _built(oracle)
+    W, H = 40, 32
+    r = s.oscene.render(_camera(s, W, H), s.host.sunlight_bake(), W, H, spp=2, max_bounces=1, seed=13, demodulate=True, gbuffer=True)
+    illum = oracle.pack_illuminance(r["radiance"])
+    bins, avg = oracle.exposure_update(illum, 0.0)
+    ldr = oracle.tone_map(illum, r["gbuffer"]["albedo"], avg)
+    g = r["gbuffer"]
+    return {"illuminance": illum.view(np.uint16), "hit_albedo": g["albedo"], "hit_normal": g["normal"], "hit_voxel_id": g["voxel_id"],
+            "hit_depth": g["depth"].view(np.uint32), "hit_histogram": bins, "adapted_luminance": np.float32(avg).reshape(1), "ldr": ldr}
+
+
+CASES = {"two_models_primary": case_primary, "two_models_gi": case_gi, "sky_bake": case_sky, "two_models_rays": case_rays,
+         "two_models_post": case_post}
 
 
 class _Npz(dict):

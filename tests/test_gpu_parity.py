@@ -355,6 +355,30 @@ def test_cuda_matches_committed_golden_fixtures(oracle, host, ctx):
                            spp=3, max_bounces=2, seed=21, frame_index=5, hits=True)
     _assert_hits_equal(g, want["two_models_gi"])
     _assert_radiance_close(g, want["two_models_gi"])
+    # ray batch: fine and block-granular hits, bit for bit
+    rays = make_golden._rays(s, 4000, 77)
+    assert np.array_equal(loaded.scene.trace_rays(rays).view(np.uint32).reshape(-1, 4), want["two_models_rays"]["hit_fine"])
+    far = rays.copy()
+    far["tmin"] = 8.0
+    assert np.array_equal(loaded.scene.trace_rays(far, rough=True).view(np.uint32).reshape(-1, 4), want["two_models_rays"]["hit_rough"])
+    # demodulated frame + G-buffer -> exposure -> tone map
+    from dust_b200.capi import DUST_FMT_YCOCG16F
+    from dust_b200.pipeline import Exposure
+    wp = want["two_models_post"]
+    W, H = 40, 32
+    g = loaded.scene.trace(make_golden._camera(s, W, H), host.sunlight_bake(), W, H, spp=2, max_bounces=1, seed=13, fmt=DUST_FMT_YCOCG16F,
+                           demodulate=True, gbuffer=True)
+    for k, gk in (("hit_albedo", "albedo"), ("hit_normal", "normal"), ("hit_voxel_id", "voxel_id")):
+        assert np.array_equal(g["gbuffer"][gk], wp[k]), k
+    assert np.array_equal(g["gbuffer"]["depth"].view(np.uint32), wp["hit_depth"])
+    a, b = g["radiance"].astype(np.float32), wp["illuminance"].view(np.float16).astype(np.float32)
+    assert np.allclose(a, b, rtol=1.5e-3, atol=1e-6)
+    ex = Exposure(ctx)
+    avg = ex.update(wp["illuminance"].view(np.float16), W, H)                  # the golden image itself: bins are then exact
+    assert abs(avg - float(wp["adapted_luminance"][0])) <= 1e-6 * avg
+    ldr = ex.tone_map(wp["illuminance"].view(np.float16), wp["hit_albedo"], W, H, np.empty((H, W, 4), np.float32))
+    assert np.abs(ldr - wp["ldr"]).max() <= 1e-4
+    ex.close()
 
 
 def test_launch_info_timing_and_counter_deltas(castle_small, host):

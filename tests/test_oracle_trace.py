@@ -144,10 +144,14 @@ def test_oracle_reproduces_golden_fixtures(oracle):
         for k in want.files:
             if k.startswith("hit_"):
                 assert np.array_equal(got[k], want[k]), (name, k)          # ids and t: bit-exact, machine-independent
+            elif k == "illuminance":
+                # half-precision image of a libm-dependent radiance: a last-ulp difference may flip a half rounding
+                a, b = got[k].view(np.float16).astype(np.float32), want[k].view(np.float16).astype(np.float32)
+                assert np.allclose(a, b, rtol=1.5e-3, atol=1e-6), (name, k)
             else:
-                # radiance / baked sky go through libm (expf, powf, acosf, asinf): last-ulp differences
+                # radiance / baked sky / tone map go through libm (expf, powf, acosf, asinf): last-ulp differences
                 # between glibc builds are allowed, nothing more
-                assert np.allclose(got[k], want[k], rtol=5e-6, atol=0), (name, k)
+                assert np.allclose(got[k], want[k], rtol=5e-6, atol=1e-7), (name, k)
 
 
 def test_instance_order_independence(oracle):
