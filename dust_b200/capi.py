@@ -107,7 +107,7 @@ class DustTreeLayout(C.Structure):
 
 class DustLaunchInfo(C.Structure):
     _fields_ = [("kernel", C.c_char * 24), ("ms", C.c_float), ("_pad", C.c_uint32)] + \
-               [(n, C.c_uint64) for n in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded")]
+               [(n, C.c_uint64) for n in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded", "mask_words_strict")]
 
 
 class DustExposureParams(C.Structure):
@@ -120,7 +120,7 @@ class DustToneMapParams(C.Structure):
 
 class DustStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
-                ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded", "kernel_launches")]
+                ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded", "kernel_launches", "mask_words_strict")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -149,6 +149,9 @@ SYMBOLS = {
     "dust_scene_set_previous_transforms": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "dust_trace": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(DustCamera), C.POINTER(DustSky),
                                C.POINTER(DustTraceConfig), C.POINTER(DustFrame)]),
+    "dust_trace_async": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(DustCamera), C.POINTER(DustSky),
+                                     C.POINTER(DustTraceConfig), C.POINTER(DustFrame), C.POINTER(C.c_uint64)]),
+    "dust_frame_wait": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "dust_trace_rays": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
     "dust_shard_layout": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "dust_resolve_shards": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -184,7 +187,7 @@ def load() -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.dust_abi_version() != 3:
+    if lib.dust_abi_version() != 4:
         raise RuntimeError("libdust_b200.so ABI version mismatch")
     _lib = lib
     return lib

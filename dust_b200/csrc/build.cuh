@@ -23,7 +23,7 @@ namespace dust {
 constexpr uint32_t VB_BLOCKS = 64u * 64u * 64u;      // 4^3-voxel blocks (= leaf slots) of a 256^3 model
 constexpr uint32_t VB_MIDS = 16u * 16u * 16u;        // 4^3-leaf mid nodes
 
-struct VbCounts { uint32_t n_leaves, n_mids, n_materials, pad; int32_t bmin[3], bmax[3]; };
+struct VbCounts { uint32_t n_leaves, n_mids, n_materials, max_mat_end; int32_t bmin[3], bmax[3]; };   // max_mat_end = max over leaves of material_ptr + popcount
 
 // collector block index (x>>2) + (y>>2) * 64 + (z>>2) * 4096  <->  tree-order key (mid index << 6 | leaf-in-mid index)
 __device__ __forceinline__ uint32_t vb_block_of_key(uint32_t key)
@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(256) vb_emit_leaves(const unsigned long long *
     if (!m) return;
     const uint32_t block = vb_block_of_key(key);
     leaves[leaf_slot[key]] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), mat_ptr[block], 0u);
+    // material_ptr counts duplicate voxels (collector.rs:29), the compacted array does not: the caller rejects a model whose
+    // material_ptr + popcount runs past it, exactly like dust_tree_upload does for a host-built tree
+    atomicMax(&counts->max_mat_end, mat_ptr[block] + (uint32_t)__popcll(m));
     uint32_t pos = mat_pos[block];
     for (unsigned long long b = m; b; b &= b - 1)                                        // ascending bit order (collector.rs:47-60)
         materials[pos++] = (uint8_t)((grid[(size_t)block * 64u + (uint32_t)(__ffsll((long long)b) - 1)] & 511ull) - 1ull);

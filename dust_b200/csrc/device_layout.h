@@ -72,6 +72,7 @@ struct DSceneView {
 struct DCounters {                 // DUST_TRACE_STATS
     unsigned long long primary_rays, bounce_rays, shadow_rays, mask_words, child_ptrs, hits_shaded;
     unsigned long long dbg[16];    // scheduling diagnostics (trace_core.cuh Counters::dbg)
+    unsigned long long mask_words_strict;   // W by SURVEY.md 8d's letter: node words tested + mid nodes entered + leaves entered (no block masks, no re-counts)
 };
 
 }  // namespace dust

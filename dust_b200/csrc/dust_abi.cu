@@ -24,6 +24,7 @@ struct DustCtx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t side[2] = { nullptr, nullptr };   // dust_trace_rays(DUST_MEM_HOST): copy / compute overlap across chunks
+    cudaEvent_t ev_join = nullptr;                 // fork / join of the side streams (created once, lives with the context)
     std::string err;
     // scratch for DUST_MEM_HOST frames / ray batches
     void *scratch = nullptr;
@@ -40,9 +41,16 @@ struct DustCtx {
     bool timing_on = false;
     cudaEvent_t ev_begin = nullptr;
     std::vector<LaunchRec> launch_recs;
+    uint32_t launch_dropped = 0;             // launches past kMaxLaunchRecs of the last timed call (reported, not silently lost)
     std::vector<cudaEvent_t> ev_pool;
     DCounters *h_snaps = nullptr;            // pinned, kMaxLaunchRecs entries
     bool snaps_valid = false;
+    // dust_trace_async: frames in flight (the reference keeps up to 3, crates/rhyolite_bevy/src/lib.rs:58): each slot owns a device
+    // staging buffer; the D2H copy of frame k runs on `copy_stream` behind the event `traced` while frame k+1 traces
+    struct FrameSlot { void *scratch = nullptr; size_t scratch_bytes = 0; cudaEvent_t traced = nullptr, done = nullptr; uint64_t ticket = 0; bool busy = false; };
+    FrameSlot slots[3];
+    cudaStream_t copy_stream = nullptr;
+    uint64_t next_ticket = 1;
     // multi-GPU: NCCL communicator of the shard group (dust_comm_init); NCCL is dlopen'ed on first use
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_size = 1;
@@ -103,6 +111,7 @@ int32_t ensure_scratch(DustCtx *ctx, size_t bytes)
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }   // 128-bit loads / stores (include/dust_b200.h "Alignment")
 
 // ---- reading the reference's host layout (crates/vdb) ------------------------------------------
 
@@ -215,13 +224,17 @@ inline float srgb_to_linear(float c)
 
 // gl_WorldToObjectEXT: inverse of the row-major 3x4 affine, adjugate / determinant in double,
 // rounded once to f32 (DESIGN.md "Instance transforms")
-void world2obj(const float m[12], float w[12])
+bool world2obj(const float m[12], float w[12])
 {
+    for (int k = 0; k < 12; k++) if (!std::isfinite(m[k])) return false;
     const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
     const double A = e * i - f * h, B = c * h - b * i, C = b * f - c * e;
     const double D = f * g - d * i, E = a * i - c * g, F = c * d - a * f;
     const double G = d * h - e * g, H = b * g - a * h, I = a * e - b * d;
     const double det = a * A + b * D + c * G;
+    // singular (or nearly so, relative to the matrix scale): no world -> object map exists
+    const double scale = std::max({ std::fabs(a), std::fabs(b), std::fabs(c), std::fabs(d), std::fabs(e), std::fabs(f), std::fabs(g), std::fabs(h), std::fabs(i) });
+    if (!(std::fabs(det) > 1e-12 * scale * scale * scale)) return false;
     const double inv[9] = { A / det, B / det, C / det, D / det, E / det, F / det, G / det, H / det, I / det };
     const double t[3] = { m[3], m[7], m[11] };
     for (int r = 0; r < 3; r++) {
@@ -230,6 +243,8 @@ void world2obj(const float m[12], float w[12])
         w[4 * r + 2] = (float)inv[3 * r + 2];
         w[4 * r + 3] = (float)(-(inv[3 * r + 0] * t[0] + inv[3 * r + 1] * t[1] + inv[3 * r + 2] * t[2]));
     }
+    for (int k = 0; k < 12; k++) if (!std::isfinite(w[k])) return false;
+    return true;
 }
 
 struct Box { float lo[3], hi[3]; };
@@ -337,14 +352,15 @@ void sun_radiance_host(const DustSky &sky, float ar2, const float dir[3], float 
     for (int r = 0; r < 3; r++) out[r] = (m[r] * xyz[0] + m[3 + r] * xyz[1]) + m[6 + r] * xyz[2];
 }
 
-constexpr size_t kMaxLaunchRecs = 512;
+constexpr size_t kMaxLaunchRecs = 1024;                              // a 64-bounce wavefront frame issues ~7 launches per depth
 
 // called after every kernel launch; with DUST_TRACE_TIMING it also drops an event behind the launch (launches of one call are
 // back to back on one stream, so consecutive events bracket one kernel) and, in a STATS pass, snapshots the counters
 void count_launch(DustCtx *ctx, const char *name = nullptr)
 {
     ctx->stats.kernel_launches++;
-    if (!ctx->timing_on || !name || ctx->launch_recs.size() >= kMaxLaunchRecs) return;
+    if (!ctx->timing_on || !name) return;
+    if (ctx->launch_recs.size() >= kMaxLaunchRecs) { ctx->launch_dropped++; return; }
     cudaEvent_t ev = nullptr;
     if (ctx->launch_recs.size() < ctx->ev_pool.size()) ev = ctx->ev_pool[ctx->launch_recs.size()];
     else { if (cudaEventCreate(&ev) != cudaSuccess) return; ctx->ev_pool.push_back(ev); }
@@ -360,6 +376,7 @@ int32_t fetch_counters(DustCtx *ctx)
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.primary_rays = h.primary_rays; ctx->stats.bounce_rays = h.bounce_rays; ctx->stats.shadow_rays = h.shadow_rays;
     ctx->stats.mask_words = h.mask_words; ctx->stats.child_ptrs = h.child_ptrs; ctx->stats.hits_shaded = h.hits_shaded;
+    ctx->stats.mask_words_strict = h.mask_words_strict;
     if (std::getenv("DUST_DEBUG_STATS")) {
         fprintf(stderr, "[dust dbg] rays p/b/s %llu %llu %llu |", h.primary_rays, h.bounce_rays, h.shadow_rays);
         for (int i = 0; i < 16; i++) fprintf(stderr, " %llu", h.dbg[i]);
@@ -580,6 +597,13 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->h_snaps) cudaFreeHost(ctx->h_snaps);
     for (int k = 0; k < 2; k++) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (DustCtx::FrameSlot &fs : ctx->slots) {
+        if (fs.scratch) cudaFree(fs.scratch);
+        if (fs.traced) cudaEventDestroy(fs.traced);
+        if (fs.done) cudaEventDestroy(fs.done);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DUST_OK;
@@ -638,9 +662,9 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     const BlobLayout L = blob_layout(r.n16.size(), r.mids.size(), r.leaves.size(), (size_t)desc->n_materials);
     const size_t off_n16 = L.n16, off_blocks = L.blocks, off_mids = L.mids, off_leaves = L.leaves, off_pal = L.pal, off_praw = L.praw, off_mat = L.mat, total = L.total;
 
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     DustTree *t = new (std::nothrow) DustTree();
     if (!t) return DUST_ERR_OUT_OF_MEMORY;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaError_t e = cudaMalloc(&t->blob, total);
     if (e != cudaSuccess) { delete t; return fail(ctx, DUST_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
     uint8_t *base = static_cast<uint8_t *>(t->blob);
@@ -748,6 +772,10 @@ int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);                                   // bounds; pal / praw die at return
     if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e)); }
+    if (h_counts.max_mat_end > h_counts.n_materials) {                                    // duplicate voxels: same verdict as dust_tree_upload
+        cudaFree(t->blob); delete t;
+        return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "leaf material_ptr runs past the material array (duplicate voxels in the model)");
+    }
     t->n_levels = 3;
     t->n_leaves = h_counts.n_leaves; t->n_mids = h_counts.n_mids; t->n_n16 = 1; t->n_materials = h_counts.n_materials;
     for (int a = 0; a < 3; a++) { t->bmin[a] = h_counts.n_leaves ? h_counts.bmin[a] : 0; t->bmax[a] = h_counts.n_leaves ? h_counts.bmax[a] : 0; }
@@ -813,7 +841,7 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         if (!t) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "instance without a tree");
         DInstance &d = inst[k];
         const float *m = o2w + 12 * (size_t)k;
-        world2obj(m, d.w2o);
+        if (!world2obj(m, d.w2o)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "instance transform is singular or not finite");
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
         d.n_levels = t->n_levels;
         d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin; d.palette_raw = t->palette_raw;
@@ -878,10 +906,10 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     uint32_t max_levels = 3, min_levels = 4;
     const int32_t rc = scene_arrays(ctx, n, trees.data(), o2w.data(), inst, nodes, root_box, root_ref, max_levels, min_levels);
     if (rc != DUST_OK) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     DustScene *s = new (std::nothrow) DustScene();
     if (!s) return DUST_ERR_OUT_OF_MEMORY;
     s->n_inst = n; s->n_bvh = (uint32_t)nodes.size(); s->max_levels = max_levels; s->min_levels = std::min(min_levels, max_levels);
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (n) {
         cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
         if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * (size_t)n);           // a binary tree over n leaves has n - 1 nodes
@@ -962,8 +990,10 @@ int32_t dust_shard_layout(uint32_t width, uint32_t height, uint32_t shard_count,
     return DUST_OK;
 }
 
-int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
-                   const DustTraceConfig *config, const DustFrame *frame)
+// dust_trace (slot == NULL: the call returns when the host buffers are complete) and dust_trace_async (slot: the frame's staging
+// buffer; kernels on the context's stream, D2H copies on the copy stream behind them, nothing waits on the host)
+static int32_t trace_impl(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
+                          const DustTraceConfig *config, const DustFrame *frame, DustCtx::FrameSlot *slot)
 {
     if (!ctx || !scene || !camera || !sky || !config || !frame) return DUST_ERR_INVALID_ARGUMENT;
     const DustTraceConfig &cfg = *config;
@@ -1022,9 +1052,18 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
             const size_t bytes[5] = { 4, 4, 4, 8, 4 };
             for (int k = 0; k < 5; k++) if (src[k]) { off_gb[k] = need; need += align_up(npx * bytes[k], 256); }
         }
-        int32_t rc = ensure_scratch(ctx, need);
-        if (rc != DUST_OK) return rc;
-        scratch = static_cast<uint8_t *>(ctx->scratch);
+        if (slot) {
+            if (need > slot->scratch_bytes) {
+                if (slot->scratch) { CU_TRY(ctx, cudaFree(slot->scratch)); slot->scratch = nullptr; slot->scratch_bytes = 0; }
+                CU_TRY(ctx, cudaMalloc(&slot->scratch, need));
+                slot->scratch_bytes = need;
+            }
+            scratch = static_cast<uint8_t *>(slot->scratch);
+        } else {
+            int32_t rc = ensure_scratch(ctx, need);
+            if (rc != DUST_OK) return rc;
+            scratch = static_cast<uint8_t *>(ctx->scratch);
+        }
         if (frame->radiance_format == DUST_FMT_RGBA32F) p.radiance32 = reinterpret_cast<float4 *>(scratch);
         else p.radiance16 = reinterpret_cast<__half *>(scratch);
         if (want_hits) {
@@ -1042,6 +1081,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
             if (gb->voxel_id) CU_TRY(ctx, cudaMemcpyAsync(p.gb.voxel_id, gb->voxel_id, npx * 4, cudaMemcpyHostToDevice, ctx->stream));
         }
     } else if (frame->memory == DUST_MEM_DEVICE) {
+        if (!aligned16(frame->radiance)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "device radiance buffer must be 16-byte aligned");
         if (frame->radiance_format == DUST_FMT_RGBA32F) p.radiance32 = static_cast<float4 *>(frame->radiance);
         else p.radiance16 = static_cast<__half *>(frame->radiance);
         if (want_hits) { p.hit_instance = frame->hit_instance; p.hit_leaf = frame->hit_leaf; p.hit_voxel = frame->hit_voxel; p.hit_t = frame->hit_t; }
@@ -1054,6 +1094,7 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     ctx->timing_on = (cfg.flags & DUST_TRACE_TIMING) != 0;
     if (ctx->timing_on) {
         ctx->launch_recs.clear();
+        ctx->launch_dropped = 0;
         if (!ctx->ev_begin) CU_TRY(ctx, cudaEventCreate(&ctx->ev_begin));
         if (!ctx->h_snaps) CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_snaps), kMaxLaunchRecs * sizeof(DCounters)));
         ctx->snaps_valid = stats;
@@ -1087,22 +1128,66 @@ int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camer
     CU_TRY(ctx, cudaGetLastError());
 
     if (frame->memory == DUST_MEM_HOST) {
-        CU_TRY(ctx, cudaMemcpyAsync(frame->radiance, scratch, out_pixels * px_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaStream_t cs = ctx->stream;
+        if (slot) {                                                       // the copies leave the trace stream: frame k+1 traces while frame k downloads
+            CU_TRY(ctx, cudaEventRecord(slot->traced, ctx->stream));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, slot->traced, 0));
+            cs = ctx->copy_stream;
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(frame->radiance, scratch, out_pixels * px_bytes, cudaMemcpyDeviceToHost, cs));
         if (want_hits) {
-            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_instance, scratch + off_hi, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_leaf, scratch + off_hl, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_t, scratch + off_ht, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_voxel, scratch + off_hv, npx, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_instance, scratch + off_hi, npx * 4, cudaMemcpyDeviceToHost, cs));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_leaf, scratch + off_hl, npx * 4, cudaMemcpyDeviceToHost, cs));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_t, scratch + off_ht, npx * 4, cudaMemcpyDeviceToHost, cs));
+            CU_TRY(ctx, cudaMemcpyAsync(frame->hit_voxel, scratch + off_hv, npx, cudaMemcpyDeviceToHost, cs));
         }
         if (gb) {
             void *dst[5] = { gb->albedo, gb->depth, gb->normal, gb->motion, gb->voxel_id };
             const size_t bytes[5] = { 4, 4, 4, 8, 4 };
             for (int k = 0; k < 5; k++)
-                if (dst[k]) CU_TRY(ctx, cudaMemcpyAsync(dst[k], scratch + off_gb[k], npx * bytes[k], cudaMemcpyDeviceToHost, ctx->stream));
+                if (dst[k]) CU_TRY(ctx, cudaMemcpyAsync(dst[k], scratch + off_gb[k], npx * bytes[k], cudaMemcpyDeviceToHost, cs));
         }
+        if (slot) { CU_TRY(ctx, cudaEventRecord(slot->done, cs)); return DUST_OK; }
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (stats) return fetch_counters(ctx);
+    return DUST_OK;
+}
+
+int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
+                   const DustTraceConfig *config, const DustFrame *frame)
+{
+    return trace_impl(ctx, scene, camera, sky, config, frame, nullptr);
+}
+
+int32_t dust_trace_async(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
+                         const DustTraceConfig *config, const DustFrame *frame, uint64_t *ticket_out)
+{
+    if (!ctx || !frame || !config || !ticket_out) return DUST_ERR_INVALID_ARGUMENT;
+    if (frame->memory != DUST_MEM_HOST) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "dust_trace_async downloads into host buffers (DUST_MEM_HOST); device frames are asynchronous already");
+    if (config->flags & (DUST_TRACE_STATS | DUST_TRACE_TIMING)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "dust_trace_async: STATS / TIMING need the synchronous call");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    DustCtx::FrameSlot &fs = ctx->slots[ctx->next_ticket % 3];
+    if (!fs.traced) CU_TRY(ctx, cudaEventCreateWithFlags(&fs.traced, cudaEventDisableTiming));
+    if (!fs.done) CU_TRY(ctx, cudaEventCreateWithFlags(&fs.done, cudaEventDisableTiming));
+    // three frames in flight at most: the slot's previous frame must have left its staging buffer
+    if (fs.busy) { CU_TRY(ctx, cudaEventSynchronize(fs.done)); fs.busy = false; }
+    const int32_t rc = trace_impl(ctx, scene, camera, sky, config, frame, &fs);
+    if (rc != DUST_OK) return rc;
+    fs.busy = true; fs.ticket = ctx->next_ticket;
+    *ticket_out = ctx->next_ticket++;
+    return DUST_OK;
+}
+
+int32_t dust_frame_wait(DustCtx *ctx, uint64_t ticket)
+{
+    if (!ctx || !ticket || ticket >= ctx->next_ticket) return DUST_ERR_INVALID_ARGUMENT;
+    DustCtx::FrameSlot &fs = ctx->slots[ticket % 3];
+    if (fs.ticket != ticket || !fs.busy) return DUST_OK;                 // already waited for, or its slot was recycled (which waited)
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventSynchronize(fs.done));
+    fs.busy = false;
     return DUST_OK;
 }
 
@@ -1175,6 +1260,7 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     if (!ctx || !scene || (n && (!rays || !hits))) return DUST_ERR_INVALID_ARGUMENT;
     if (n == 0) return DUST_OK;
     if (memory != DUST_MEM_HOST && memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    if (memory == DUST_MEM_DEVICE && (!aligned16(rays) || !aligned16(hits))) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "device ray / hit buffers must be 16-byte aligned");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const bool host = memory == DUST_MEM_HOST;
     const bool stats = (flags & DUST_TRACE_STATS) != 0;
@@ -1202,6 +1288,8 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
     DustHit *d_hits = hits;
     cudaEvent_t ev = nullptr;
     if (host) {
+        if (!ctx->ev_join) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        ev = ctx->ev_join;
         const size_t ray_bytes = align_up((size_t)n * sizeof(DustRay), 256);
         const int32_t rc = ensure_scratch(ctx, ray_bytes + (size_t)n * sizeof(DustHit));
         if (rc != DUST_OK) return rc;
@@ -1209,7 +1297,6 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
         d_hits = reinterpret_cast<DustHit *>(static_cast<uint8_t *>(ctx->scratch) + ray_bytes);
         for (int k = 0; k < 2; k++)
             if (!ctx->side[k]) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-        CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU_TRY(ctx, cudaEventRecord(ev, ctx->stream));                                     // side streams start after the work already queued
         for (int k = 0; k < 2; k++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->side[k], ev, 0));
     }
@@ -1230,7 +1317,6 @@ int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *ray
             if (cudaEventRecord(ev, ctx->side[k]) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, ev, 0);
             cudaStreamSynchronize(ctx->side[k]);
         }
-        cudaEventDestroy(ev);
     }
     CU_TRY(ctx, le);
     CU_TRY(ctx, cudaGetLastError());
@@ -1263,7 +1349,8 @@ int32_t dust_exposure_create(DustCtx *ctx, DustExposure **out)
     DustExposure *e = new (std::nothrow) DustExposure();
     if (!e) return fail(ctx, DUST_ERR_OUT_OF_MEMORY, "host allocation failed");
     if (cudaMalloc(&e->d, sizeof(DHistogram)) != cudaSuccess) { delete e; return fail(ctx, DUST_ERR_OUT_OF_MEMORY, "cudaMalloc(histogram)"); }
-    CU_TRY(ctx, cudaMemsetAsync(e->d, 0, sizeof(DHistogram), ctx->stream));          // fill_buffer(&mut buffer, 0), auto_exposure.rs:116-118
+    const cudaError_t me = cudaMemsetAsync(e->d, 0, sizeof(DHistogram), ctx->stream);  // fill_buffer(&mut buffer, 0), auto_exposure.rs:116-118
+    if (me != cudaSuccess) { cudaFree(e->d); delete e; return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(me)); }
     *out = e;
     return DUST_OK;
 }
@@ -1309,6 +1396,7 @@ int32_t dust_auto_exposure(DustCtx *ctx, DustExposure *exposure, const void *ill
         CU_TRY(ctx, cudaMemcpyAsync(ctx->scratch, illuminance, n * 8, cudaMemcpyHostToDevice, ctx->stream));
         img = static_cast<const uint2 *>(ctx->scratch);
     } else if (memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    else if (!aligned16(illuminance)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "device illuminance image must be 16-byte aligned");
     const uint32_t grid = (uint32_t)std::min<uint64_t>((n / 2 + 255) / 256 + 1, (uint64_t)ctx->sms * 8);
     exposure_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(img, n, params->min_log_luminance, 1.0f / params->log_luminance_range, exposure->d);
     count_launch(ctx);
@@ -1343,6 +1431,7 @@ int32_t dust_tone_map(DustCtx *ctx, const DustExposure *exposure, const void *il
         CU_TRY(ctx, cudaMemcpyAsync(s + off_alb, albedo, n * 4, cudaMemcpyHostToDevice, ctx->stream));
         img = reinterpret_cast<const uint2 *>(s); alb = reinterpret_cast<const uint32_t *>(s + off_alb); d_dst = s + off_dst;
     } else if (memory != DUST_MEM_DEVICE) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "bad memory space");
+    else if (!aligned16(illuminance) || !aligned16(dst)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "device illuminance / dst images must be 16-byte aligned");
     ToneMapParams tp;
     memcpy(tp.csc, params->color_space_conversion, sizeof tp.csc);
     tp.oetf = params->output_transfer_function; tp.dst_format = params->dst_format;
@@ -1371,6 +1460,7 @@ struct NcclApi {
     int (*CommDestroy)(void *) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
+    int (*CommGetAsyncError)(void *, int *) = nullptr;                  // optional (NCCL >= 2.4)
 };
 NcclApi *nccl_api(std::string &why)
 {
@@ -1386,6 +1476,7 @@ NcclApi *nccl_api(std::string &why)
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
         api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+        api.CommGetAsyncError = reinterpret_cast<decltype(api.CommGetAsyncError)>(dlsym(api.lib, "ncclCommGetAsyncError"));
         if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
             err = "libnccl.so.2 lacks a required symbol";
             dlclose(api.lib);
@@ -1451,13 +1542,23 @@ int32_t dust_allgather_framebuffer(DustCtx *ctx, const void *shard, uint64_t byt
     if (!api) return fail(ctx, DUST_ERR_COMM, why);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     NCCL_TRY(ctx, api, api->AllGather(shard, gathered, (size_t)bytes_per_rank, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream));
+    // failure detection: an asynchronous error of the communicator (a peer died, a link went down) surfaces here
+    // instead of as a hang in the next stream synchronisation.  ncclInProgress (7) is the normal state of an enqueued collective.
+    if (api->CommGetAsyncError) {
+        int async_err = 0;
+        NCCL_TRY(ctx, api, api->CommGetAsyncError(ctx->nccl_comm, &async_err));
+        if (async_err != 0 && async_err != 7)
+            return fail(ctx, DUST_ERR_COMM, std::string("ncclCommGetAsyncError: ") + api->GetErrorString(async_err));
+    }
     return DUST_OK;
 }
 
 int32_t dust_get_launch_info(DustCtx *ctx, DustLaunchInfo *out, uint32_t capacity, uint32_t *n_out)
 {
     if (!ctx || !n_out || (capacity && !out)) return DUST_ERR_INVALID_ARGUMENT;
-    *n_out = (uint32_t)ctx->launch_recs.size();
+    // n_out counts every launch of the call: a value above the records returned (capacity, or the library's own limit of
+    // kMaxLaunchRecs) tells the caller the list is truncated
+    *n_out = (uint32_t)ctx->launch_recs.size() + ctx->launch_dropped;
     if (ctx->launch_recs.empty()) return DUST_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1475,6 +1576,7 @@ int32_t dust_get_launch_info(DustCtx *ctx, DustLaunchInfo *out, uint32_t capacit
             o.primary_rays = c.primary_rays - prev.primary_rays; o.bounce_rays = c.bounce_rays - prev.bounce_rays;
             o.shadow_rays = c.shadow_rays - prev.shadow_rays; o.mask_words = c.mask_words - prev.mask_words;
             o.child_ptrs = c.child_ptrs - prev.child_ptrs; o.hits_shaded = c.hits_shaded - prev.hits_shaded;
+            o.mask_words_strict = c.mask_words_strict - prev.mask_words_strict;
             prev = c;
         }
     }

@@ -118,9 +118,30 @@ public:
             }
             c.pos += static_cast<size_t>(content);
         }
-        if (!have_palette)
-            for (int i = 0; i < 256; ++i) f->palette[static_cast<size_t>(i)] = { uint8_t(i), uint8_t(i), uint8_t(i), 255 };
+        if (!have_palette) default_palette(f->palette);
         return f;
+    }
+
+    // A file without an RGBA chunk uses MagicaVoxel's default palette (dot_vox substitutes its DEFAULT_PALETTE table).  The table of
+    // the published format description is regular: colour index i = 1..215 walks a 6x6x6 cube with levels ff cc 99 66 33 00 (blue
+    // fastest, then green, then red; black omitted), 216..255 are four ramps (red, green, blue, grey) over ee dd bb aa 88 77 55 44 22 11.
+    // Stored like an RGBA chunk: entry k holds colour index k + 1.  Restated from the format description — dot_vox's own table is
+    // not in the reference tree, so this is unverifiable here (DESIGN.md "deviations").
+    static void default_palette(std::array<std::array<uint8_t, 4>, 256> &pal)
+    {
+        static const uint8_t ramp[10] = { 0xee, 0xdd, 0xbb, 0xaa, 0x88, 0x77, 0x55, 0x44, 0x22, 0x11 };
+        for (int i = 1; i < 256; ++i) {
+            uint8_t r = 0, g = 0, b = 0;
+            if (i <= 215) {
+                const int k = i - 1;
+                b = uint8_t(0xff - 0x33 * (k % 6)); g = uint8_t(0xff - 0x33 * ((k / 6) % 6)); r = uint8_t(0xff - 0x33 * (k / 36));
+            } else {
+                const int k = i - 216, v = ramp[k % 10];
+                if (k < 10) r = uint8_t(v); else if (k < 20) g = uint8_t(v); else if (k < 30) b = uint8_t(v); else r = g = b = uint8_t(v);
+            }
+            pal[static_cast<size_t>(i - 1)] = { r, g, b, 255 };
+        }
+        pal[255] = { 0, 0, 0, 0 };
     }
 
     // loader.rs:178-204 — see DESIGN.md "Scene ingest" for the signed-permutation derivation

@@ -173,12 +173,13 @@ __device__ __forceinline__ bool gbuffer_wanted(const DustGBuffer &gb)
 __device__ __forceinline__ void flush_counters(DCounters *g, const Counters &st)
 {
     // warp-aggregate, one atomic per counter per warp
-    uint32_t v[22] = { st.primary_rays, st.bounce_rays, st.shadow_rays, st.mask_words, st.child_ptrs, st.hits_shaded };
+    uint32_t v[23] = { st.primary_rays, st.bounce_rays, st.shadow_rays, st.mask_words, st.child_ptrs, st.hits_shaded };
 #pragma unroll
     for (int i = 0; i < 16; i++) v[6 + i] = st.dbg[i];
+    v[22] = st.mask_words_strict;
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(g);
 #pragma unroll
-    for (int i = 0; i < 22; i++) {
+    for (int i = 0; i < 23; i++) {
         unsigned long long s = v[i];
         for (int ofs = 16; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
         if ((threadIdx.x & 31) == 0 && s) atomicAdd(&dst[i], s);

@@ -27,6 +27,7 @@ struct Counters {
     //  7 cells left with edge 1   8 edge 4   9 edge 64 (leaf units)   10 leaf steps   11 leaf DDA iterations
     //  12 instances entered   13 BVH nodes expanded   14 candidates   15 trace_scene calls (per warp)
     uint32_t dbg[16];
+    uint32_t mask_words_strict;      // see DCounters
 };
 
 #define DUST_DIR_EPS 9.094947017729282e-13f   // 2^-40
@@ -281,7 +282,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
 #else
             const uint4 q = __ldg(&node->word[tidx >> 6]);
 #endif
-            if (STATS) st.mask_words++;
+            if (STATS) { st.mask_words++; st.mask_words_strict++; }
             const uint32_t b = tidx & 63u;
             if (!bit64(q.x, q.y, b)) { w.L4 = 64; return WS_WALK; }
             if (STATS) st.child_ptrs++;
@@ -293,7 +294,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (STATS) st.mask_words++;
         if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
         const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
-        if (STATS) st.mask_words++;
+        if (STATS) { st.mask_words++; st.mask_words_strict++; }
 #ifdef DUST_TMA_TOP
         const uint4 q = four ? __ldg(&node->word[ridx >> 6]) : w.topw[ridx >> 6];
 #else
@@ -302,6 +303,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         const uint32_t b = ridx & 63u;
         if (!bit64(q.x, q.y, b)) { w.L4 = 4; return WS_WALK; }
         const uint4 mid = __ldg(&w.mids[q.z + rank64(q.x, q.y, b)]);
+        if (STATS) st.mask_words_strict++;                              // a mid node entered
         w.mid_lo = mid.x; w.mid_hi = mid.y; w.mid_base = mid.z;
         w.have_mid = true;
     } else if (STATS) {
@@ -323,7 +325,7 @@ template <bool STATS>
 __device__ __forceinline__ bool walk_leaf(const Walk &w, float tmin, float &th, uint32_t &vox, Counters &st, const bool rough = false)
 {
     const uint4 leaf = __ldg(&w.leaves[w.leaf_i]);
-    if (STATS) st.dbg[10]++;
+    if (STATS) { st.dbg[10]++; st.mask_words_strict++; }
     const f3 lo = mk3(w.o.x - (float)(w.jx << 2), w.o.y - (float)(w.jy << 2), w.o.z - (float)(w.jz << 2));   // hit.rint:140
     if (rough) return leaf_rough(lo, w.d, leaf.x, leaf.y, th, vox);     // block-granular far rays (rough.rint); uniform per launch
     return leaf_dda_inv<STATS>(lo, w.d, w.inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]);

@@ -59,7 +59,7 @@ class Context:
         buf = (capi.DustLaunchInfo * 512)()
         check(self.h, self.lib.dust_get_launch_info(self.h, buf, 512, C.byref(n)), "dust_get_launch_info")
         return [{"kernel": buf[k].kernel.decode(), "ms": float(buf[k].ms),
-                 **{f: int(getattr(buf[k], f)) for f in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded")}}
+                 **{f: int(getattr(buf[k], f)) for f in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded", "mask_words_strict")}}
                 for k in range(min(int(n.value), 512))]
 
     # ---- multi-GPU exchange step (dust_comm_* / dust_allgather_framebuffer) ---------------------------
@@ -247,6 +247,20 @@ class Scene:
         if stats:
             res["stats"] = ctx.stats()
         return res
+
+    def trace_async(self, camera, sky, width, height, out, spp=1, max_bounces=0, seed=0, frame_index=0, shard_index=0, shard_count=1,
+                    fmt=DUST_FMT_RGBA16F, pipeline=None) -> int:
+        """dust_trace_async: queue the frame and its download into `out` (a pinned host array the caller keeps alive and does not
+        read until frame_wait(ticket)); returns the ticket.  Up to 3 frames in flight."""
+        ctx, lib = self.ctx, self.ctx.lib
+        cfg = DustTraceConfig(width, height, spp, max_bounces, seed, frame_index, shard_index, shard_count, PIPELINE_FLAGS[pipeline])
+        fr = DustFrame(_ptr(out), None, None, None, None, DUST_MEM_HOST, fmt)
+        t = C.c_uint64()
+        check(ctx.h, lib.dust_trace_async(ctx.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr), C.byref(t)), "dust_trace_async")
+        return int(t.value)
+
+    def frame_wait(self, ticket: int):
+        check(self.ctx.h, self.ctx.lib.dust_frame_wait(self.ctx.h, ticket), "dust_frame_wait")
 
     def trace_device(self, camera, sky, width, height, radiance, spp=1, max_bounces=0, seed=0, frame_index=0,
                      shard_index=0, shard_count=1, stats=False, fmt=DUST_FMT_RGBA32F, hit_buffers=None, pipeline=None, timing=False):

@@ -15,6 +15,12 @@
  * device memory behind opaque handles; one DustCtx per GPU, calls on a ctx serialised by the
  * caller (the reference has one recorder thread per frame).  There is NO CPU fallback: without a
  * CUDA device dust_ctx_create fails with DUST_ERR_NO_DEVICE.
+ *
+ * Alignment of DUST_MEM_DEVICE buffers: the kernels read rays, hit records and half-float images with 128-bit
+ * loads, so device pointers passed to dust_trace_rays (rays, hits), dust_auto_exposure / dust_tone_map
+ * (illuminance, dst) and DustFrame.radiance must be 16-byte aligned (cudaMalloc and torch allocations are; a
+ * sub-view at an odd element offset may not be).  A misaligned pointer is rejected with
+ * DUST_ERR_INVALID_ARGUMENT.  Host buffers (DUST_MEM_HOST) have no alignment requirement.
  */
 #ifndef DUST_B200_H
 #define DUST_B200_H
@@ -24,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DUST_ABI_VERSION 3
+#define DUST_ABI_VERSION 4
 
 enum {
     DUST_OK = 0,
@@ -169,6 +175,8 @@ typedef struct DustStats {
     uint64_t child_ptrs;       /* P: child links followed */
     uint64_t hits_shaded;      /* H */
     uint64_t kernel_launches;  /* launches of this library's kernels since ctx creation */
+    uint64_t mask_words_strict; /* W by the letter of SURVEY.md 8d: node words tested + mid nodes entered + leaves entered;
+                                 * mask_words also counts the block-mask words and the words of a node already in registers */
 } DustStats;
 
 int32_t dust_abi_version(void);
@@ -224,6 +232,16 @@ int32_t dust_scene_set_previous_transforms(DustCtx *ctx, DustScene *scene, const
 /* Replaces StandardPipeline::render (standard.rs:228-810) for the primary + bounce passes. */
 int32_t dust_trace(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
                    const DustTraceConfig *config, const DustFrame *frame);
+
+/* Frames in flight.  The reference submits a frame and moves on (up to 3 in flight behind fences:
+ * crates/rhyolite_bevy/src/lib.rs:58, queue.rs:222-241).  dust_trace_async is dust_trace for a DUST_MEM_HOST frame without the
+ * final wait: the kernels are queued on the context's stream, the device -> host copies follow on a second stream, and the call
+ * returns a ticket; the host buffers of `frame` (pinned memory, or the copies serialise) belong to the library until
+ * dust_frame_wait(ticket) returns.  The download of frame k overlaps the kernels of frame k+1.  At most 3 tickets are
+ * outstanding: the 4th call first waits for the oldest.  DUST_TRACE_STATS / DUST_TRACE_TIMING are not accepted here. */
+int32_t dust_trace_async(DustCtx *ctx, const DustScene *scene, const DustCamera *camera, const DustSky *sky,
+                         const DustTraceConfig *config, const DustFrame *frame, uint64_t *ticket_out);
+int32_t dust_frame_wait(DustCtx *ctx, uint64_t ticket);
 
 /* Explicit ray batch, closest hit (BASELINE.json config 5).  `memory` = DUST_MEM_*. */
 int32_t dust_trace_rays(DustCtx *ctx, const DustScene *scene, const DustRay *rays, uint64_t n,
@@ -282,12 +300,13 @@ int32_t dust_tone_map(DustCtx *ctx, const DustExposure *exposure, const void *il
 int32_t dust_get_stats(DustCtx *ctx, DustStats *out);
 /* The launches of the last dust_trace call made with DUST_TRACE_TIMING, in order: kernel name, device time between the
  * event behind the previous launch and the one behind this launch, and (when that call also had DUST_TRACE_STATS) what
- * this launch added to the counters.  Synchronises the context's stream.  *n_out = number of launches recorded. */
+ * this launch added to the counters.  Synchronises the context's stream.  *n_out = number of launches of that call;
+ * at most min(capacity, 1024) records are returned, so *n_out above that means the list is truncated. */
 typedef struct DustLaunchInfo {
     char kernel[24];
     float ms;
     uint32_t _pad;
-    uint64_t primary_rays, bounce_rays, shadow_rays, mask_words, child_ptrs, hits_shaded;
+    uint64_t primary_rays, bounce_rays, shadow_rays, mask_words, child_ptrs, hits_shaded, mask_words_strict;
 } DustLaunchInfo;
 int32_t dust_get_launch_info(DustCtx *ctx, DustLaunchInfo *out, uint32_t capacity, uint32_t *n_out);
 

@@ -142,8 +142,21 @@ OVoxScene *o_vox_parse(const uint8_t *bytes, uint64_t len)
     }
     if (r.err) { o_vox_scene_free(s); return NULL; }
     if (!have_rgba) {
-        /* dot_vox falls back to MagicaVoxel's default palette; our writers always emit RGBA */
-        for (int i = 0; i < 256; i++) { s->palette[i][0] = s->palette[i][1] = s->palette[i][2] = (uint8_t)i; s->palette[i][3] = 255; }
+        /* dot_vox falls back to MagicaVoxel's default palette (published format description: colour 1..215 = 6x6x6 cube over
+         * ff cc 99 66 33 00, blue fastest, black omitted; 216..255 = red / green / blue / grey ramps); entry k = colour k + 1 */
+        static const uint8_t ramp[10] = { 0xee, 0xdd, 0xbb, 0xaa, 0x88, 0x77, 0x55, 0x44, 0x22, 0x11 };
+        memset(s->palette, 0, 1024);
+        for (int i = 1; i < 256; i++) {
+            uint8_t *c = s->palette[i - 1];
+            if (i <= 215) {
+                int k = i - 1;
+                c[2] = (uint8_t)(0xff - 0x33 * (k % 6)); c[1] = (uint8_t)(0xff - 0x33 * ((k / 6) % 6)); c[0] = (uint8_t)(0xff - 0x33 * (k / 36));
+            } else {
+                int k = i - 216, v = ramp[k % 10];
+                if (k < 10) c[0] = (uint8_t)v; else if (k < 20) c[1] = (uint8_t)v; else if (k < 30) c[2] = (uint8_t)v; else c[0] = c[1] = c[2] = (uint8_t)v;
+            }
+            c[3] = 255;
+        }
     }
     return s;
 }

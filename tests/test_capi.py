@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (dust_[a-z0-9_]+)", out))
     assert set(names) <= exported
-    assert lib.dust_abi_version() == 3
+    assert lib.dust_abi_version() == 4
 
 
 def test_ctypes_structs_match_header(tmp_path):
@@ -44,7 +44,8 @@ def test_ctypes_structs_match_header(tmp_path):
         "DustTraceConfig": ["width", "spp", "seed", "shard_index", "flags"],
         "DustFrame": ["radiance", "hit_instance", "hit_leaf", "hit_voxel", "hit_t", "memory", "radiance_format", "gbuffer"],
         "DustGBuffer": ["albedo", "depth", "normal", "motion", "voxel_id"],
-        "DustStats": ["primary_rays", "mask_words", "kernel_launches"],
+        "DustStats": ["primary_rays", "mask_words", "kernel_launches", "mask_words_strict"],
+        "DustLaunchInfo": ["kernel", "ms", "primary_rays", "hits_shaded", "mask_words_strict"],
         "DustExposureParams": ["min_log_luminance", "log_luminance_range", "time_coefficient"],
         "DustToneMapParams": ["color_space_conversion", "output_transfer_function", "dst_format"],
         "DustTreeLayout": ["n_levels", "n_nodes16", "n_materials", "off_nodes16", "off_materials", "total_bytes", "bounds_min", "bounds_max"],

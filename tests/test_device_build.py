@@ -41,8 +41,8 @@ def test_device_build_edge_cases(ctx, host):
     d = e.download()
     assert e.leaf_count == 0 and d["leaves"].shape == (0, 4) and d["mids"].shape == (0, 4) and not d["nodes16"][..., :2].any()
     assert d["bounds"] == ((0, 0, 0), (0, 0, 0))
-    # full-size model corners + a duplicated voxel (the later one wins, like ModelIndexCollector::set overwriting its grid)
-    v = np.array([[0, 0, 0, 5], [255, 255, 255, 7], [255, 0, 0, 9], [10, 20, 30, 1], [10, 20, 30, 2], [11, 20, 30, 3]], np.uint8)
+    # full-size model corners
+    v = np.array([[0, 0, 0, 5], [255, 255, 255, 7], [255, 0, 0, 9], [10, 20, 30, 2], [11, 20, 30, 3]], np.uint8)
     t = DeviceTree.build_voxels(ctx, v, (256, 256, 256), pal)
     d = t.download()
     assert t.leaf_count == 4 and len(d["materials"]) == 5
@@ -51,6 +51,16 @@ def test_device_build_edge_cases(ctx, host):
     # voxel (x, y, z)_vox -> tree (x, z, 255 - y): (10, 20, 30) -> (10, 30, 235): leaf (8, 28, 232), bit (z&3) | (y&3) << 2 | (x&3) << 4
     leaf = [l for l in d["leaves"] if (int(l[0]) | int(l[1]) << 32) == ((1 << ((235 & 3) | (30 & 3) << 2 | (10 & 3) << 4)) | (1 << ((235 & 3) | (30 & 3) << 2 | (11 & 3) << 4)))]
     assert len(leaf) == 1
+    # A duplicated XYZI entry: ModelIndexCollector::set counts it twice in block_counts (collector.rs:29) but its grid keeps one
+    # value, so every later leaf's material_ptr runs ahead of the compacted material array (a latent out-of-bounds read in the
+    # reference).  Both build paths reject such a model with the same error instead of tracing wrong colours.
+    dup = np.array([[0, 0, 0, 5], [255, 255, 255, 7], [255, 0, 0, 9], [10, 20, 30, 1], [10, 20, 30, 2], [11, 20, 30, 3]], np.uint8)
+    with pytest.raises(Exception, match="material"):
+        DeviceTree.build_voxels(ctx, dup, (256, 256, 256), pal)
+    # ... unless the duplicate sits in the LAST block of the collector order (nothing comes after it): accepted by both paths, last value wins
+    last = np.array([[255, 255, 255, 7], [3, 0, 255, 1], [3, 0, 255, 4]], np.uint8)           # (3, 0, 255) -> tree (3, 255, 255): block (0, 63, 63)
+    t2 = DeviceTree.build_voxels(ctx, last, (256, 256, 256), pal)
+    assert sorted(t2.download()["materials"].tolist()) == [4, 7]
     with pytest.raises(Exception):
         DeviceTree.build_voxels(ctx, v, (257, 1, 1), pal)
 

@@ -510,3 +510,53 @@ def test_ray_batch_rough_block_hits(castle_small, teapot, host, oracle, ctx):
     o2, _ = teapot.oscene.trace_rays(r2, rough=True)
     assert (o2["instance"] != 0xFFFFFFFF).mean() > 0.02
     assert np.array_equal(teapot.loaded.scene.trace_rays(r2, rough=True).view(np.uint32), o2.view(np.uint32))
+
+
+def test_frames_in_flight_equal_synchronous_frames(castle_small, host, ctx):
+    """dust_trace_async / dust_frame_wait (the reference keeps up to 3 frames in flight, rhyolite_bevy/src/lib.rs:58): five frames
+    queued back to back, three in flight at most, each bitwise equal to the synchronous call's frame."""
+    import torch
+    from dust_b200.capi import DUST_FMT_RGBA16F, DustError
+    W, H = 192, 108
+    cam, sky = _cam_for(castle_small, host, W, H), host.sunlight_bake()
+    scene = castle_small.loaded.scene
+    kw = dict(spp=2, max_bounces=1, seed=9, fmt=DUST_FMT_RGBA16F)
+    want = [scene.trace(cam, sky, W, H, frame_index=k, **kw)["radiance"].copy() for k in range(5)]
+    assert not np.array_equal(want[0], want[1])                      # frame_index reseeds the paths
+    bufs = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(5)]
+    tickets = [scene.trace_async(cam, sky, W, H, bufs[k].numpy(), frame_index=k, **kw) for k in range(5)]
+    assert tickets == sorted(tickets) and len(set(tickets)) == 5
+    for k in (4, 0, 2, 1, 3):                                        # any order; waiting twice is harmless
+        scene.frame_wait(tickets[k])
+        assert np.array_equal(bufs[k].numpy(), want[k]), k
+    scene.frame_wait(tickets[0])
+    with pytest.raises(DustError):
+        scene.frame_wait(tickets[-1] + 1)                            # a ticket that was never issued
+
+
+def test_bad_transforms_and_misaligned_device_buffers_are_rejected(teapot, host, ctx):
+    import torch
+    from dust_b200.capi import DustError
+    from dust_b200.pipeline import Scene
+    from dust_b200.pipeline import RAY_DTYPE
+    tree = next(iter(teapot.loaded.trees.values()))
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    singular = ident.copy(); singular[10] = 0.0                      # a flattened instance has no world -> object map
+    nan = ident.copy(); nan[3] = np.nan
+    for m in (singular, nan):
+        with pytest.raises(DustError, match="singular|finite"):
+            Scene(ctx, [(m, tree)])
+    good = Scene(ctx, [(ident, tree)])
+    with pytest.raises(DustError, match="singular|finite"):
+        good.update_transforms(singular.reshape(1, 12))
+    # the scene keeps its last valid state
+    rays = np.zeros(4, dtype=RAY_DTYPE)
+    rays["o"] = (-5, 10, 10); rays["d"] = (1, 0.01, 0.02); rays["tmax"] = np.inf
+    before = good.trace_rays(rays).copy()
+    # 128-bit loads: a device pointer at an 8-byte offset is refused, not faulted on
+    d = torch.zeros(4 * 8 + 2, dtype=torch.float32, device="cuda")
+    d[2:].view(4, 8).copy_(torch.from_numpy(rays.view(np.float32).reshape(4, 8)))
+    hits = torch.empty((4, 4), dtype=torch.int32, device="cuda")
+    with pytest.raises(DustError, match="aligned"):
+        good.trace_rays_device(d[2:], hits, 4)
+    assert np.array_equal(good.trace_rays(rays), before)

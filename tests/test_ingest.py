@@ -137,3 +137,23 @@ def test_max_size_model_corners(host, oracle):
     assert len(mh.nodes) == 8 and np.array_equal(mh.nodes, mo.nodes)
     assert mh.tree.get_value((255, 255, 255)) is True and mh.tree.get_value((128, 128, 128)) is None
     assert mh.tree.pool_count(1) == 8 and mh.tree.pool_count(0) == 8
+
+
+def test_file_without_rgba_chunk_gets_the_magicavoxel_default_palette(oracle, host):
+    """dot_vox substitutes MagicaVoxel's default palette when a file has no RGBA chunk.  Host mirror and
+    oracle must agree, and the table must show the published structure: a 6x6x6 colour cube then four ramps."""
+    pts = np.array([[1, 2, 3, 0], [4, 5, 6, 215]], np.uint8)
+    data = scenes.write_vox([((8, 8, 8), pts)], None, scenes.default_palette())
+    k = data.index(b"RGBA")
+    stripped = data[:k]                                            # RGBA is the last chunk write_vox emits
+    stripped = stripped[:16] + np.uint32(len(stripped) - 20).tobytes() + stripped[20:]   # MAIN's children_bytes
+    vo, vh = oracle.VoxFile(stripped), host.VoxFile(stripped)
+    assert np.array_equal(vo.palette, vh.palette)
+    pal = np.asarray(vh.palette).reshape(-1, 4)
+    assert pal[0].tolist() == [255, 255, 255, 255]                # colour 1 = 0xffffffff
+    assert pal[1].tolist() == [255, 255, 0xcc, 255]               # colour 2 = 0xffccffff (A B G R): blue steps first
+    assert pal[6].tolist() == [255, 0xcc, 255, 255]               # colour 7 = 0xffffccff
+    assert pal[36].tolist() == [0xcc, 255, 255, 255]              # colour 37 = 0xffffffcc
+    assert pal[214].tolist() == [0, 0, 0x33, 255]                 # colour 215: last cube entry (black is omitted)
+    assert pal[215].tolist() == [0xee, 0, 0, 255] and pal[225].tolist() == [0, 0xee, 0, 255]    # red / green ramps
+    assert pal[235].tolist() == [0, 0, 0xee, 255] and pal[254].tolist() == [0x11, 0x11, 0x11, 255]
