@@ -287,7 +287,7 @@ def load_asset(kind: str, search=("assets", "/root/assets")):
             if hashlib.sha256(data).hexdigest() == want:
                 return data, f"{kind}.vox (genuine, sha256 verified)"
     if kind == "castle":
-        return cached("castle_like_s2_t8", castle_like), "castle.vox STAND-IN (procedural castle_like(seed=2), ~21M voxels)"
+        return cached("castle_like_s2_t8", castle_like), "castle.vox STAND-IN (procedural castle_like(seed=2): 110 instances of 20 models, 30.0 M voxels)"
     return cached("teapot_like_s1", teapot_like), "teapot.vox STAND-IN (procedural teapot_like(seed=1))"
 
 
@@ -304,3 +304,74 @@ def ray_batch(n: int, extent: float, seed=5) -> np.ndarray:
     rays["tmin"] = 0.0
     rays["tmax"] = np.inf
     return rays
+
+
+# ---- BASELINE.json configs[4] rays as SURVEY.md 8d specifies them: drawn from the reference's `pcg` hash
+# (assets/shaders/headers/spatial_hash.glsl:105-111), counter-based, so ray i is the same whoever generates it and however
+# the batch is split.  The same op sequence runs on numpy (CPU arms, tests) or torch (on the GPU: 10^8 rays in a blink);
+# only exactly-rounded f32 operations (mul, add, sqrt, int -> float) are used, so both give the same bits.
+
+def _pcg_x(v, xp):
+    M = 0xFFFFFFFF
+    state = (v * 747796405 + 2891336453) & M
+    word = (((state >> ((state >> 28) + 4)) ^ state) * 277803737) & M
+    return ((word >> 22) ^ word) & M
+
+
+def ray_batch_pcg(n: int, extent: float, seed=5, first=0, device=None):
+    """Rays first .. first+n-1 of the seeded batch: origin uniform in [0, extent)^3, direction uniform on the sphere, tmin 0, tmax inf.
+    device=None: numpy structured array (RAY_DTYPE).  device="cuda": torch float32 tensor [n, 8] on that device."""
+    if device is None:
+        xp = np
+        i = np.arange(first, first + n, dtype=np.int64)
+        f32 = lambda a: a.astype(np.float32)
+        f64 = lambda a: a.astype(np.float64)
+        sqrt, floor, where = np.sqrt, np.floor, np.where
+        stack = lambda cols: np.stack(cols, axis=1)
+    else:
+        import torch
+        xp = torch
+        i = torch.arange(first, first + n, dtype=torch.int64, device=device)
+        f32 = lambda a: a.to(torch.float32)
+        f64 = lambda a: a.to(torch.float64)
+        sqrt, floor, where = torch.sqrt, torch.floor, torch.where
+        stack = lambda cols: torch.stack(cols, dim=1)
+    s = _pcg_x((i + _pcg_x_scalar(seed)) & 0xFFFFFFFF, xp)
+    u = [f32(_pcg_x((s + k) & 0xFFFFFFFF, xp) >> 8) * np.float32(1.0 / 16777216.0) for k in range(5)]
+    ext = np.float32(extent)
+    ox, oy, oz = u[0] * ext, u[1] * ext, u[2] * ext
+    z = u[3] * np.float32(2.0) - np.float32(1.0)
+    # cos / sin(2 pi u) from the kernel's own mul/add polynomial (trace_math.cuh cossin_2pi): bit-reproducible everywhere
+    x4 = u[4] * np.float32(4.0)
+    qf = floor(x4)
+    th = ((x4 - qf) - np.float32(0.5)) * np.float32(1.57079632679489661923)
+    t2 = th * th
+    c = [np.float32(v) for v in (-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0)]
+    sn = th * (np.float32(1.0) + t2 * (c[0] + t2 * (c[1] + t2 * (c[2] + t2 * c[3]))))
+    k = [np.float32(v) for v in (-0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0)]
+    cs = np.float32(1.0) + t2 * (k[0] + t2 * (k[1] + t2 * (k[2] + t2 * (k[3] + t2 * k[4]))))
+    r2 = np.float32(0.70710678118654752440)
+    c45, s45 = (cs - sn) * r2, (cs + sn) * r2
+    q = qf  # 0, 1, 2, 3 as floats
+    cosv = where(q == 0, c45, where(q == 1, -s45, where(q == 2, -c45, s45)))
+    sinv = where(q == 0, s45, where(q == 1, c45, where(q == 2, -s45, -c45)))
+    one_m = np.float32(1.0) - z * z
+    # the one square root goes through float64 (correctly rounded by every library; vectorised float32 sqrt is not, on all of them)
+    r = f32(sqrt(f64(where(one_m > 0, one_m, one_m * np.float32(0.0)))))
+    if device is None:
+        from .pipeline import RAY_DTYPE
+        rays = np.zeros(n, dtype=RAY_DTYPE)
+        rays["o"] = stack([ox, oy, oz])
+        rays["d"] = stack([r * cosv, r * sinv, z])
+        rays["tmax"] = np.inf
+        return rays
+    import torch
+    zero = torch.zeros_like(ox)
+    return stack([ox, oy, oz, zero, r * cosv, r * sinv, z, torch.full_like(ox, float("inf"))]).contiguous()
+
+
+def _pcg_x_scalar(v: int) -> int:
+    M = 0xFFFFFFFF
+    state = (v * 747796405 + 2891336453) & M
+    word = (((state >> ((state >> 28) + 4)) ^ state) * 277803737) & M
+    return ((word >> 22) ^ word) & M
