@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
         "o_cache_get": (i32, [vp, u32, C.POINTER(OSpatialHashKey), u32, pf32, pu32]),
         "o_dense_from_tree": (vp, [vp]), "o_dense_free": (None, [vp]),
         "o_dense_march": (i32, [vp, C.POINTER(f64), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
+        "o_dense_march_batch": (None, [vp, vp, vp, u64, f64, f64, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -509,6 +510,8 @@ def leaf_dda(origin, direction, grid, tmin=0.0):
 class Dense:
     def __init__(self, tree: Tree):
         self._h = lib().o_dense_from_tree(tree._h)
+        if not self._h:
+            raise MemoryError("dense grid of this tree's occupied bounds would exceed 2 GiB")
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -520,3 +523,13 @@ class Dense:
         ok = lib().o_dense_march(self._h, (C.c_double * 3)(*[float(v) for v in o]), (C.c_double * 3)(*[float(v) for v in d]),
                                  float(tmin), float(tmax), xyz, C.byref(t))
         return (tuple(xyz), float(t.value)) if ok else None
+
+    def march_batch(self, o, d, tmin, tmax, guard=False):
+        """o, d: [n, 3] float64 object-space rays.  Returns (hit[n] bool, xyz[n, 3] int32, t[n] float64).
+        guard: also apply hit.rint:107's leaf-exit rule (see oracle_dense.c)."""
+        o = np.ascontiguousarray(o, np.float64); d = np.ascontiguousarray(d, np.float64)
+        n = len(o)
+        xyz, t, hit = np.zeros((n, 3), np.int32), np.zeros(n, np.float64), np.zeros(n, np.uint8)
+        lib().o_dense_march_batch(self._h, o.ctypes.data, d.ctypes.data, n, float(tmin), float(tmax), int(bool(guard)),
+                                  xyz.ctypes.data, t.ctypes.data, hit.ctypes.data)
+        return hit.astype(bool), xyz, t

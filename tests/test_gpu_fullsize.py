@@ -95,7 +95,7 @@ def test_config2_full_frame_properties(castle, ctx, oracle):
     ov = oracle.VoxFile(data)
     models = {m: ov.load_model(m) for m in sorted({m for m, _ in ov.instances})}
     osc = oracle.Scene([(mat, models[m].tree._h, models[m].materials, ov.palette) for m, mat in ov.instances])
-    rows = [int((i + 0.5) * H / 6) for i in range(6)]
+    rows = [int((i + 0.5) * H / 24) for i in range(24)]           # (bench.py compares ALL 1080 rows with the oracle on every run: `parity`)
     o = osc.render(cam, sky, W, H, rows=rows, **kw)
     for k in ("hit_instance", "hit_leaf", "hit_voxel"):
         assert np.array_equal(wf[k][rows], o[k][rows]), k
@@ -103,6 +103,49 @@ def test_config2_full_frame_properties(castle, ctx, oracle):
     a, b = wf["radiance"][rows][..., :3].astype(np.float64), o["radiance"][rows][..., :3].astype(np.float64)
     scale = np.maximum(np.abs(b).max(axis=-1, keepdims=True), 1e-3 * np.abs(b).mean())
     assert (np.abs(a - b) / scale).max() <= 1e-4
+
+
+def test_config3_4k_sample_batches_against_oracle(castle, ctx, host, oracle):
+    """BASELINE.json configs[3]: 3840x2160, 2 bounces, 8 spp.  66 M paths do not fit one wavefront batch (16 Mi paths), so the frame runs
+    in four sample batches of 2 spp, carried by the per-pixel accumulator: evenly spread rows against the oracle (ids / t bit-exact,
+    radiance 1e-4), and two 32-row bands of the megakernel's frame (no batches at all) bit for bit."""
+    from dust_b200 import scenes
+    data, loaded, _, sky = castle
+    W4, H4 = 3840, 2160
+    cam = host.camera_look_at(width=W4, height=H4, **dict(scenes.CASTLE_CAMERA))
+    kw = dict(spp=8, max_bounces=2, seed=2)
+    launches0 = ctx.stats()["kernel_launches"]
+    wf = loaded.scene.trace(cam, sky, W4, H4, hits=True, pipeline="wavefront", **kw)
+    assert ctx.stats()["kernel_launches"] - launches0 >= 4 * 10           # four batches of >= 10 launches each
+    ov = oracle.VoxFile(data)
+    models = {m: ov.load_model(m) for m in sorted({m for m, _ in ov.instances})}
+    osc = oracle.Scene([(mat, models[m].tree._h, models[m].materials, ov.palette) for m, mat in ov.instances])
+    rows = [int((i + 0.5) * H4 / 8) for i in range(8)]
+    o = osc.render(cam, sky, W4, H4, rows=rows, **kw)
+    for k in ("hit_instance", "hit_leaf", "hit_voxel"):
+        assert np.array_equal(wf[k][rows], o[k][rows]), k
+    assert np.array_equal(wf["hit_t"][rows].view(np.uint32), o["hit_t"][rows].view(np.uint32))
+    a, b = wf["radiance"][rows][..., :3].astype(np.float64), o["radiance"][rows][..., :3].astype(np.float64)
+    scale = np.maximum(np.abs(b).max(axis=-1, keepdims=True), 1e-3 * np.abs(b).mean())
+    assert (np.abs(a - b) / scale).max() <= 1e-4
+    # one shard of a 64-way split through the megakernel (a different scheduling, no sample batches): its tiles equal the frame's
+    from dust_b200.pipeline import shard_layout
+    shards, idx = 64, 17
+    tiles_per, per = shard_layout(W4, H4, shards)
+    part = loaded.scene.trace(cam, sky, W4, H4, shard_index=idx, shard_count=shards, pipeline="megakernel", **kw)["radiance"].reshape(tiles_per, 32, 32, 4)
+    tiles_x = (W4 + 31) // 32
+    n_tiles = tiles_x * ((H4 + 31) // 32)
+    checked = 0
+    for lt in range(tiles_per):
+        t = lt * shards + idx
+        if t >= n_tiles:
+            continue
+        ty, tx = divmod(t, tiles_x)
+        ref = wf["radiance"][ty * 32:ty * 32 + 32, tx * 32:tx * 32 + 32]
+        got = part[lt][:ref.shape[0], :ref.shape[1]]
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (lt, t)
+        checked += 1
+    assert checked >= 120
 
 
 def test_config5_ray_batch_properties(ctx, host, oracle):

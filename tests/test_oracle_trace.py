@@ -92,26 +92,20 @@ def test_hdda_against_dense_marcher(oracle, teapot):
     d = target - rays["o"]
     rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True)
     rays["tmin"], rays["tmax"] = 0.0, 1e4
-    one = oracle.Scene([(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), model.tree._h, model.materials, teapot.ovox.palette)])
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    one = oracle.Scene([(ident, model.tree._h, model.materials, teapot.ovox.palette)])
+    # plain brute force (no leaf rule): the only systematic difference is hit.rint:107's 0.001 exit guard, a few rays per thousand
     hits, _ = one.trace_rays(rays)
-    pos, _ = model.tree.iter_leaf()
-    agree = differ = nhit = 0
-    for i in range(n):
-        ref = dense.march(rays["o"][i], rays["d"][i], 0.0, 1e4)
-        got = None
-        if hits["instance"][i] != 0xFFFFFFFF:
-            v = int(hits["voxel"][i])
-            got = tuple((pos[hits["leaf"][i]] + np.array([v >> 4, (v >> 2) & 3, v & 3])).tolist())
-        if ref is None and got is None:
-            agree += 1
-        elif ref is not None and got is not None and ref[0] == got and abs(ref[1] - float(hits["t"][i])) < 1e-3 * (1 + ref[1]):
-            agree += 1
-            nhit += 1
-        else:
-            differ += 1
-    assert nhit > 500
-    # grazing rays (a corner within rounding, or the 0.001 exit guard of hit.rint:107) may legitimately differ
-    assert differ <= 0.003 * n, f"{differ} of {n} rays disagree with the dense marcher"
+    hit, xyz, t = dense.march_batch(rays["o"].astype(np.float64), rays["d"].astype(np.float64), 0.0, 1e4, guard=False)
+    pos = model.tree.iter_leaf()[0].astype(np.int64)
+    got_hit = hits["instance"] != 0xFFFFFFFF
+    v = hits["voxel"].astype(np.int64)
+    gxyz = pos[np.where(got_hit, hits["leaf"], 0)] + np.stack([v >> 4, (v >> 2) & 3, v & 3], axis=1)
+    plain_same = (got_hit == hit) & (~hit | (gxyz == xyz).all(axis=1))
+    assert plain_same.mean() >= 0.995
+    # with the guard rule restated in the marcher every ray is accounted for
+    n_bad, coplanar, ties = _check_against_dense(oracle, one, [(ident, dense, pos)], rays, min_hits=500)
+    assert coplanar == 0 and ties == n_bad <= 2, (n_bad, coplanar, ties)
 
 
 def test_cull_and_threads_do_not_change_results(oracle):
@@ -269,3 +263,131 @@ def test_rough_block_hits_against_brute_force(oracle, teapot):
     # (a leaf box straddling tmin is skipped by the block test while the fine DDA may still hit a voxel behind tmin inside it,
     #  so block hits are not simply "nearer than fine hits" — only different)
     assert not np.array_equal(hits["t"], fine["t"])
+
+
+# ---- the independent check, widened: multi-instance scenes with rotated / sheared instances and a 4-level tree,
+# >= 10^5 rays, and EVERY disagreement classified — none may stay unexplained.
+
+def _dense_scene_trace(instances, o, d, tmax=1e4):
+    """instances: [(obj2world[12] float32, Dense, leaf_positions)].  Brute force in float64: every instance's dense grid is marched
+    with the ray mapped through the float64 inverse of its transform; closest hit = min t (first instance on ties).
+    Returns the scene answer (instance, voxel, t) and the per-instance answers [K, n]."""
+    n = len(o)
+    best_t = np.full(n, np.inf)
+    best_i = np.full(n, -1, np.int64)
+    best_xyz = np.zeros((n, 3), np.int64)
+    per = []
+    for k, (m, dense, _) in enumerate(instances):
+        M = np.asarray(m, np.float64).reshape(3, 4)
+        A = np.linalg.inv(M[:, :3])
+        oo = (o - M[:, 3]) @ A.T
+        dd = d @ A.T
+        hit, xyz, t = dense.march_batch(oo, dd, 0.0, tmax, guard=True)
+        t = np.where(hit, t, np.inf)
+        per.append((hit, xyz.astype(np.int64), t))
+        better = hit & (t < best_t)
+        best_t[better], best_i[better], best_xyz[better] = t[better], k, xyz[better]
+    return best_i, best_xyz, best_t, per
+
+
+def _check_against_dense(oracle, oscene, instances, rays, min_hits):
+    """Returns (disagreements, coplanar ties, float ties); fails on any disagreement that is neither."""
+    o64, d64 = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    hits, _ = oscene.trace_rays(rays)
+    ri, rxyz, rt, per = _dense_scene_trace(instances, o64, d64)
+    gi = np.where(hits["instance"] == 0xFFFFFFFF, -1, hits["instance"].astype(np.int64))
+    gt = np.where(gi >= 0, hits["t"].astype(np.float64), np.inf)
+    gxyz = np.zeros((len(rays), 3), np.int64)
+    for k, (_, _, pos) in enumerate(instances):
+        sel = gi == k
+        v = hits["voxel"][sel].astype(np.int64)
+        gxyz[sel] = pos[hits["leaf"][sel]] + np.stack([v >> 4, (v >> 2) & 3, v & 3], axis=1)
+    with np.errstate(invalid="ignore"):
+        t_close = np.abs(gt - rt) <= 1e-3 * (1 + np.abs(rt))
+    same = (gi == ri) & ((gi < 0) | ((gxyz == rxyz).all(axis=1) & t_close))
+    assert int((same & (gi >= 0)).sum()) >= min_hits
+    bad = np.flatnonzero(~same)
+    # Classification of every disagreement:
+    #  COPLANAR TIE  two instances present faces in the same world plane (touching / overlapping models): the brute force finds the
+    #                oracle's voxel in the oracle's instance, at a t equal to the scene minimum within 1e-5 relative — which of two
+    #                equal times is "first" is decided by float32 rounding of two different object-space computations
+    #  FLOAT TIE     the brute-force answer flips to the oracle's answer under a perturbation of the ray far below the float32
+    #                resolution of the coordinates involved (the ray grazes a voxel edge / corner / the 0.001 guard within rounding)
+    #  anything else is unexplained and fails the test
+    rng = np.random.default_rng(5)
+    coplanar, ties, unexplained = 0, 0, []
+    for i in bad:
+        if gi[i] >= 0:
+            h, xyz, t = per[gi[i]]
+            if h[i] and (xyz[i] == gxyz[i]).all() and abs(t[i] - rt[i]) <= 1e-5 * (1 + abs(rt[i])) and abs(gt[i] - t[i]) <= 1e-3 * (1 + abs(t[i])):
+                coplanar += 1
+                continue
+        far = max(v for v in (rt[i], gt[i], 0.0) if np.isfinite(v))
+        scale = 2e-6 * (1.0 + np.abs(o64[i]).max() + far)
+        P = 64
+        po = o64[i] + rng.uniform(-1, 1, (P, 3)) * scale
+        pd = d64[i] * (1 + rng.uniform(-1, 1, (P, 3)) * 2e-6) + rng.uniform(-1, 1, (P, 3)) * 2e-6
+        pi, pxyz, pt, _ = _dense_scene_trace(instances, po, pd)
+        flips = (pi == gi[i]) & ((gi[i] < 0) | (pxyz == gxyz[i]).all(axis=1))
+        if flips.any():
+            ties += 1
+        else:
+            unexplained.append((int(i), int(gi[i]), gxyz[i].tolist(), float(gt[i]), int(ri[i]), rxyz[i].tolist(), float(rt[i])))
+    assert not unexplained, f"{len(unexplained)} rays differ from the brute-force marcher and nothing explains it: {unexplained[:5]}"
+    return len(bad), coplanar, ties
+
+
+def test_hdda_against_dense_marcher_multi_instance(oracle):
+    """Rotated (all 24 axis rotations occur in castle_like), translated and SHEARED instances of several models, 10^5 world rays."""
+    s = BuiltScene(scenes.castle_like(tiles=2, tile=64, height=96, props=9), oracle)
+    insts, scene_list = [], []
+    dense_of = {m: oracle.Dense(s.omodels[m].tree) for m in s.omodels}
+    pos_of = {m: s.omodels[m].tree.iter_leaf()[0].astype(np.int64) for m in s.omodels}
+    for k, (mid, mat) in enumerate(s.ovox.instances):
+        m = np.array(mat, np.float32).copy()
+        if k % 3 == 1:                                  # shear + non-uniform scale on every third instance
+            A = m.reshape(3, 4)[:, :3].astype(np.float64) @ np.array([[1.0, 0.25, 0.0], [0.0, 1.0, -0.125], [0.0625, 0.0, 1.5]])
+            m.reshape(3, 4)[:, :3] = A.astype(np.float32)
+        insts.append((m, dense_of[mid], pos_of[mid]))
+        scene_list.append((m, s.omodels[mid].tree._h, s.omodels[mid].materials, s.ovox.palette))
+    osc = oracle.Scene(scene_list)
+    lo, hi = s.bounds()
+    rng = np.random.default_rng(21)
+    n = 100_000
+    rays = np.zeros(n, oracle.RAY_DTYPE)
+    ext = (hi - lo)
+    rays["o"] = (lo - 0.5 * ext + rng.random((n, 3)) * 2.0 * ext).astype(np.float32)
+    target = lo + rng.random((n, 3)) * ext
+    d = target - rays["o"]
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmin"], rays["tmax"] = 0.0, 1e4
+    n_bad, coplanar, ties = _check_against_dense(oracle, osc, insts, rays, min_hits=30_000)
+    assert coplanar + ties == n_bad and ties <= 0.001 * n, (n_bad, coplanar, ties)
+    print(f"multi-instance: {n_bad} of {n} rays differ from the brute force: {coplanar} coplanar-instance ties, {ties} float ties")
+
+
+def test_hdda_against_dense_marcher_four_levels(oracle, host):
+    """hierarchy!(4,4,2,2): the synthetic sphere domain (256 leaves across, so its occupied bounds fit a dense grid), one identity
+    and one rotated + sheared instance, 10^5 rays."""
+    dom = host.SynthDomain(seed=7, fill=0.03, domain_leaves=128)
+    otree = oracle.TreeView(dom.describe())
+    dense = oracle.Dense(otree)
+    pos = otree.iter_leaf()[0].astype(np.int64)
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    sheared = np.array([0, 0, 1.25, 700, 1, 0.125, 0, -40, 0, 1, 0.25, 30], np.float32)
+    insts = [(ident, dense, pos), (sheared, dense, pos)]
+    osc = oracle.Scene([(m, otree._h, dom.materials, dom.palette) for m, _, _ in insts])
+    rng = np.random.default_rng(22)
+    n = 100_000
+    rays = np.zeros(n, oracle.RAY_DTYPE)
+    # half of the rays aim into the identity instance's box, half into the sheared one's (world box of its object box [0, 512)^3)
+    M = sheared.astype(np.float64).reshape(3, 4)
+    tgt_obj = rng.random((n, 3)) * 512.0
+    target = np.where((np.arange(n) % 2 == 0)[:, None], tgt_obj, tgt_obj @ M[:, :3].T + M[:, 3])
+    rays["o"] = (target + (rng.random((n, 3)) * 2 - 1) * 600.0).astype(np.float32)
+    d = target - rays["o"]
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmin"], rays["tmax"] = 0.0, 1e4
+    n_bad, coplanar, ties = _check_against_dense(oracle, osc, insts, rays, min_hits=20_000)
+    assert coplanar + ties == n_bad and ties <= 0.001 * n, (n_bad, coplanar, ties)
+    print(f"four levels: {n_bad} of {n} rays differ from the brute force: {coplanar} coplanar-instance ties, {ties} float ties")
