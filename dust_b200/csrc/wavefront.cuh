@@ -287,6 +287,67 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
 
 enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
 
+// ---- TMA staging of the ray queue (BASELINE.json north_star: "stages ... through TMA into shared memory") --------------------------
+// EXPERIMENT, compiled only with -DDUST_TMA_QUEUE (off in the shipped library): parity-green (the whole GPU suite passes with it),
+// but 2.2 % slower on configs[2] and 6 % slower on configs[4] than per-lane __ldg + one atomic per trip (A/B in
+// profiles/r02_history.md).  The tracer is bound by instruction issue on the ALU pipe: a claim's latency is already hidden by the
+// other seven warps of the scheduler, while the mbarrier waits, the proxy fence and the slot arithmetic are instructions it
+// has to issue.  A round-1 experiment that staged the root node words the same way (-DDUST_TMA_TOP) lost 5.6 %.
+// The queues are the one thing on this path that STREAMS: every ray record is read once, in queue order.  Each warp of the
+// persistent tracer therefore owns two half-buffers of WF_STAGE rays in shared memory.  One lane claims WF_STAGE consecutive
+// queue slots with ONE atomic and issues bulk copies (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP) of
+// their origin / direction / path / candidate records; lanes whose ray is finished take the next staged ray with a ballot prefix —
+// no per-lane global loads, no per-trip atomic — and the half that ran empty is refilled while the other one is consumed.
+// (The node words of the walk are NOT staged: they are data-dependent single 16-byte reads that hit L1; measured in round 1.)
+#ifndef WF_STAGE
+#define WF_STAGE 16                   // rays per half-buffer (multiple of 4: the path words of a copy are a multiple of 16 bytes)
+#endif
+#define WF_STAGE_BYTES (WF_STAGE * (16 + 16 + 4 * WF_CANDS + 4))     // a | b | cand | path of one half-buffer
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Claim the next WF_STAGE queue slots and start their copies into half-buffer `half` of this warp (called by ONE lane).
+// stage layout: [a: WF_STAGE x 16 | b: WF_STAGE x 16 | cand: WF_STAGE x 4 WF_CANDS | path: WF_STAGE x 4]; interleaved DustRay records
+// (stride 2) land in the a|b region as they are.  `meta` = {first queue slot, rays} of the half, read by the consumers after the wait.
+template <bool CAND>
+__device__ __forceinline__ void wf_stage_refill(const WfParams &p, const WfQueue &q, uint32_t n, unsigned long long *work,
+                                                uint8_t *stage, uint32_t bar, uint2 *meta)
+{
+    const unsigned long long base = atomicAdd(work, (unsigned long long)WF_STAGE);
+    const uint32_t c = base >= n ? 0u : min((uint32_t)WF_STAGE, n - (uint32_t)base);
+    *meta = make_uint2((uint32_t)base, c);
+    if (c == 0u) { mbar_arrive(bar); return; }                          // queue exhausted: the phase completes with nothing in flight
+    const uint32_t b32 = (uint32_t)base, dst = smem_u32(stage);
+    const uint32_t c4 = (c + 3u) & ~3u;                                 // path words: whole 16-byte units (the arrays are padded to 256 bytes)
+    uint32_t bytes = c * 32u;
+    if (CAND) bytes += c * (4u * WF_CANDS);
+    if (q.path) bytes += c4 * 4u;
+    mbar_expect_tx(bar, bytes);
+    if (q.stride == 2u) bulk_g2s(dst, q.a + 2u * (size_t)b32, c * 32u, bar);
+    else {
+        bulk_g2s(dst, q.a + b32, c * 16u, bar);
+        bulk_g2s(dst + WF_STAGE * 16u, q.b + b32, c * 16u, bar);
+    }
+    if (CAND) bulk_g2s(dst + WF_STAGE * 32u, p.cand + WF_CVECS * (size_t)b32, c * (4u * WF_CANDS), bar);
+    if (q.path) bulk_g2s(dst + WF_STAGE * (32u + 4u * WF_CANDS), q.path + b32, c4 * 4u, bar);
+}
+#ifndef DUST_FAST_VOTE_LANES
+#define DUST_FAST_VOTE_LANES 16u
+#endif
+
 // CAND: the queue comes with pre-culled candidate records (p.cand, multi-instance scenes); without them the only candidate is the
 // scene box and the truncated-list logic compiles away.
 template <int NL, bool STATS, bool CAND, bool ROUGH = false>
@@ -313,6 +374,28 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
     float e_trunc = CUDART_INF_F;                                      // truncated candidate list: entry distance of its last key (+inf: complete list)
     Walk w;
     w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
+
+#ifdef DUST_PAD_SMEM
+    __shared__ uint8_t s_pad[DUST_PAD_SMEM];                           // A/B only: what does the L1 / shared carve-out cost?
+    if (n == 0xFFFFFFFFu) s_pad[threadIdx.x] = 1;
+    if (n == 0xFFFFFFFEu && s_pad[threadIdx.x ^ 1]) return;
+#endif
+#ifdef DUST_TMA_QUEUE
+    // per warp: two half-buffers of staged rays, their mbarriers and {first slot, count} words; `taken` = staged slots this warp
+    // has handed out so far (slot g lives in half (g / WF_STAGE) & 1, generation g / (2 WF_STAGE))
+    __shared__ __align__(128) uint8_t s_stage[DUST_THREADS / 32][2][WF_STAGE_BYTES];
+    __shared__ __align__(8) unsigned long long s_bar[DUST_THREADS / 32][2];
+    __shared__ uint2 s_meta[DUST_THREADS / 32][2];
+    const unsigned wid = threadIdx.x >> 5;
+    uint32_t taken = 0;
+    if (lane == 0) {
+        mbar_init(smem_u32(&s_bar[wid][0]), 1u); mbar_init(smem_u32(&s_bar[wid][1]), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        wf_stage_refill<CAND>(p, q, n, work, s_stage[wid][0], smem_u32(&s_bar[wid][0]), &s_meta[wid][0]);
+        wf_stage_refill<CAND>(p, q, n, work, s_stage[wid][1], smem_u32(&s_bar[wid][1]), &s_meta[wid][1]);
+    }
+    __syncwarp();
+#endif
 
 #ifdef DUST_TMA_TOP
     // Experiment (profiles/r01_history.md): single-instance scenes stage the root 16^3 node (64 x 16 B) and its
@@ -342,17 +425,26 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 
 #pragma unroll 1
     for (;;) {
-        const uint32_t packed = __reduce_add_sync(full, mode < W_DEAD ? (1u << (8 * mode)) : 0u);
-        if (packed == 0u) break;
-        const uint32_t n_next = packed & 255u, n_walk = (packed >> 8) & 255u, n_leaf = packed >> 16;
         int op = W_WALK;
-        uint32_t cnt = n_walk;
-        if (n_next > cnt) { op = W_NEXT; cnt = n_next; }
-        if (n_leaf > cnt) { op = W_LEAF; cnt = n_leaf; }
+        uint32_t n_next = 0, n_walk = 0, n_leaf = 0, cnt = 0;
+#ifndef DUST_NO_FAST_VOTE
+        // fast path: half of the warp or more waits for WALK — it is the plurality whatever the others want (one ballot + popc
+        // instead of the REDUX and its decoding: the vote was 12 % of this kernel's instructions, profiles/r01_v8_*)
+        n_walk = (uint32_t)__popc(__ballot_sync(full, mode == W_WALK));
+        if (n_walk < DUST_FAST_VOTE_LANES)
+#endif
+        {
+            const uint32_t packed = __reduce_add_sync(full, mode < W_DEAD ? (1u << (8 * mode)) : 0u);
+            if (packed == 0u) break;
+            n_next = packed & 255u; n_walk = (packed >> 8) & 255u; n_leaf = packed >> 16;
+            cnt = n_walk;
+            if (n_next > cnt) { op = W_NEXT; cnt = n_next; }
+            if (n_leaf > cnt) { op = W_LEAF; cnt = n_leaf; }
+        }
         if (STATS && lane == 0) {
+            if (op == W_WALK) cnt = n_walk;
             st.dbg[op == W_WALK ? 0 : (op == W_LEAF ? 1 : 2)]++;
             st.dbg[op == W_WALK ? 3 : (op == W_LEAF ? 4 : 5)] += cnt;
-            st.dbg[6] += 32u - (n_next + n_walk + n_leaf);
         }
 
         if (op == W_WALK) {
@@ -406,6 +498,68 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                         else wf_store_hit(p, ri, hit, cur, b_inst, b_leaf, b_pos, b_vox);
                     }
                 }
+#ifdef DUST_TMA_QUEUE
+                // hand staged rays out: the lanes that need one take consecutive staged slots (ballot prefix) — from the current
+                // half-buffer and, past its end, from the other one (lanes beyond both are served by the next NEXT operation);
+                // a half that ran empty is refilled at once (one atomic + bulk copies) while the other half is consumed
+                if (need) have_ray = false;
+                const uint32_t pos = taken % WF_STAGE, half0 = (taken / WF_STAGE) & 1u;
+                const uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
+                const uint32_t take = min((uint32_t)__popc(want), 2u * WF_STAGE - pos);
+                const bool second = rank + pos >= (uint32_t)WF_STAGE;                 // this lane's slot lies in the other half
+                const uint32_t half = half0 ^ (second ? 1u : 0u), sl = second ? rank + pos - WF_STAGE : rank + pos;
+                // generations: slot g = taken + rank lives in generation g / (2 WF_STAGE); both copies were issued long ago
+                while (!mbar_try_wait(smem_u32(&s_bar[wid][half0]), (taken / (2u * WF_STAGE)) & 1u)) { }
+                if (pos + take > (uint32_t)WF_STAGE)
+                    while (!mbar_try_wait(smem_u32(&s_bar[wid][half0 ^ 1u]), ((taken + WF_STAGE) / (2u * WF_STAGE)) & 1u)) { }
+                if (need && rank < take) {
+                    const uint2 meta = s_meta[wid][half];
+                    if (sl >= meta.y) mode = W_DEAD;                                 // past the end of the queue
+                    else {
+                        const uint8_t *st_ = s_stage[wid][half];
+                        ri = meta.x + sl;
+                        float4 a, b;
+                        if (q.stride == 2u) { a = *reinterpret_cast<const float4 *>(st_ + sl * 32u); b = *reinterpret_cast<const float4 *>(st_ + sl * 32u + 16u); }
+                        else { a = *reinterpret_cast<const float4 *>(st_ + sl * 16u); b = *reinterpret_cast<const float4 *>(st_ + WF_STAGE * 16u + sl * 16u); }
+                        uint32_t first_key;
+                        if (CAND) {
+                            e_trunc = CUDART_INF_F;
+#pragma unroll
+                            for (int v = 0; v < WF_CVECS; v++) {
+                                uint4 c = *reinterpret_cast<const uint4 *>(st_ + WF_STAGE * 32u + sl * (4u * WF_CANDS) + 16u * v);
+                                if (v == 0) first_key = c.x;
+                                if (v == WF_CVECS - 1 && (c.w >> 31) && c.w < 0xFFFFFFFEu) { c.w &= 0x7FFFFFFFu; e_trunc = __uint_as_float(c.w & ~id_mask); }
+                                sm[(4 * v + 0) * DUST_THREADS] = c.x; sm[(4 * v + 1) * DUST_THREADS] = c.y;
+                                sm[(4 * v + 2) * DUST_THREADS] = c.z; sm[(4 * v + 3) * DUST_THREADS] = c.w;
+                            }
+                        } else {
+                            // single-instance scene (no wf_cull pass): the candidate list is the scene box test
+                            const float te = sc.n_inst ? box_entry(sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1], sc.root_hi[2],
+                                                                   mk3(a.x, a.y, a.z), cull_inverse(mk3(b.x, b.y, b.z)), a.w, b.w) : CUDART_INF_F;
+                            first_key = te != CUDART_INF_F ? cand_key(te, 0u, id_mask) : 0xFFFFFFFFu;
+                            sm[0] = first_key; sm[DUST_THREADS] = 0xFFFFFFFFu;
+                        }
+                        if (first_key != 0xFFFFFFFEu) {                                // else: wf_cull could not pre-cull it, wf_trace_slow does it
+                            pw = q.path ? *reinterpret_cast<const uint32_t *>(st_ + WF_STAGE * (32u + 4u * WF_CANDS) + sl * 4u) : ri;
+                            ro = mk3(a.x, a.y, a.z); tmin = a.w; rd = mk3(b.x, b.y, b.z); cur = b.w;
+                            hit = false; b_inst = 0xFFFFFFFFu;
+                            j = 0; exhausted = false;
+                            have_ray = true;
+                        }
+                    }
+                }
+                taken += take;
+                if (pos + take >= (uint32_t)WF_STAGE) {                               // half0 (and maybe the other half too) is used up: refill
+                    __syncwarp();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the reads above before the async-proxy writes below
+                    if (lane == 0) {
+                        wf_stage_refill<CAND>(p, q, n, work, s_stage[wid][half0], smem_u32(&s_bar[wid][half0]), &s_meta[wid][half0]);
+                        if (pos + take == 2u * WF_STAGE)
+                            wf_stage_refill<CAND>(p, q, n, work, s_stage[wid][half0 ^ 1u], smem_u32(&s_bar[wid][half0 ^ 1u]), &s_meta[wid][half0 ^ 1u]);
+                    }
+                    __syncwarp();
+                }
+#else
                 const int leader = __ffs(want) - 1;
                 unsigned long long base = 0;
                 if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(want));
@@ -448,6 +602,7 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                         }
                     }
                 }
+#endif
             }
         }
     }
