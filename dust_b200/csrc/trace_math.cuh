@@ -103,15 +103,37 @@ __device__ __forceinline__ f3 xyz2acescg(f3 v)
     return mat3_mul(m, v);
 }
 
+// exp / acos as FIXED mul / add / sqrt expressions (deviation (6)) — the same operations in the same order as
+// the CPU checker's, so that sky radiance (and everything accumulated or cached from it) is
+// bit-identical on both sides; CUDA's expf / acosf and glibc's round differently.
+__device__ __forceinline__ float exp2_fixed(float x)
+{
+    const float nf = floorf(x + 0.5f);
+    const float f = (x - nf) * 0.693147181f;
+    const float p = 1.0f + f * (1.0f + f * (0.5f + f * (0.166666667f + f * (0.0416666667f + f * (0.00833333333f + f * (0.00138888889f + f * 0.000198412698f))))));
+    if (!(nf >= -126.0f)) return 0.0f;
+    if (nf > 127.0f) return CUDART_INF_F;
+    return p * __uint_as_float((uint32_t)((int32_t)nf + 127) << 23);
+}
+__device__ __forceinline__ float exp_fixed(float x) { return exp2_fixed(x * 1.44269504f); }
+__device__ __forceinline__ float acos_fixed(float x)
+{
+    const float a = fabsf(x);
+    const float p = 1.5707963050f + a * (-0.2145988016f + a * (0.0889789874f + a * (-0.0501743046f + a * (0.0308918810f + a * (-0.0170881256f + a * (0.0066700901f + a * -0.0012624911f))))));
+    const float r = sqrtf(1.0f - a) * p;
+    return x < 0.0f ? 3.14159265358979f - r : r;
+}
+
 // headers/sky.glsl:1-16
 __device__ __forceinline__ float sky_channel(const DustSkyChannel &ch, float cos_theta, float gamma, float cos_gamma)
 {
     const float *c = ch.config;
-    float expM = expf(c[4] * gamma);
+    float expM = exp_fixed(c[4] * gamma);
     float rayM = cos_gamma * cos_gamma;
-    float mieM = (1.0f + rayM) / powf((1.0f + c[8] * c[8]) - (2.0f * c[8]) * cos_gamma, 1.5f);
+    float mb = (1.0f + c[8] * c[8]) - (2.0f * c[8]) * cos_gamma;
+    float mieM = (1.0f + rayM) / (mb * sqrtf(mb));                       // pow(x, 1.5) = x sqrt(x)
     float zenith = sqrtf(cos_theta);
-    return (1.0f + c[0] * expf(c[1] / (cos_theta + 0.01f))) *
+    return (1.0f + c[0] * exp_fixed(c[1] / (cos_theta + 0.01f))) *
            ((((c[2] + c[3] * expM) + c[5] * rayM) + c[6] * mieM) + c[7] * zenith);
 }
 
@@ -127,7 +149,7 @@ __device__ __noinline__ void sky_eval(const DustSky &sky, float ar2, float dx, f
     const float cos_gamma = (dx * sky.direction[0] + dy * sky.direction[1]) + dz * sky.direction[2];
     if (sky.direction[1] > 0.0f) {
         const float cos_theta = fminf(fmaxf(dy, 0.0f), 1.0f);
-        const float gamma = acosf(fminf(fmaxf(cos_gamma, -1.0f), 1.0f));
+        const float gamma = acos_fixed(fminf(fmaxf(cos_gamma, -1.0f), 1.0f));
         float xyz[3];
         const DustSkyChannel *ch = &sky.r;
 #pragma unroll 1

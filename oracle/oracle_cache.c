@@ -1,6 +1,7 @@
 /* ORACLE — test infrastructure only.  See oracle_cache.h: groundwork for SURVEY.md 8f rank 2, no CUDA counterpart yet. */
 #include "oracle_cache.h"
 #include "oracle_post.h"      /* o_post_log2: the fixed-expression log2 */
+#include "oracle_sky.h"       /* o_sky_exp2: the fixed-expression exp2 */
 #include <math.h>
 #include <string.h>
 
@@ -40,20 +41,8 @@ uint32_t o_cache_location(const OSpatialHashKey *key, uint32_t capacity)    /* :
     return hash % capacity;
 }
 
-/* 2^x from mul / add only: x = n + f, f in [-0.5, 0.5], 2^f by a degree-7 Taylor polynomial in f ln 2 (|error| < 2e-8 relative) */
-static float exp2_fixed(float x)
-{
-    float nf = floorf(x + 0.5f);
-    float f = (x - nf) * 0.693147181f;
-    float p = 1.0f + f * (1.0f + f * (0.5f + f * (0.166666667f + f * (0.0416666667f + f * (0.00833333333f + f * (0.00138888889f + f * 0.000198412698f))))));
-    int32_t n = (int32_t)nf;
-    if (n < -126) return 0.0f;
-    if (n > 127) return INFINITY;
-    uint32_t bits = (uint32_t)(n + 127) << 23;
-    float scale;
-    memcpy(&scale, &bits, 4);
-    return p * scale;
-}
+/* 2^x from mul / add only: oracle_sky.c's o_sky_exp2 (x = n + f, f in [-0.5, 0.5], 2^f by a degree-7 Taylor polynomial in f ln 2) */
+#define exp2_fixed o_sky_exp2
 
 static void mat3_mul_cols(const float m[9], const float v[3], float out[3])     /* GLSL mat3(c0, c1, c2) * v */
 {

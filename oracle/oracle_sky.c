@@ -149,14 +149,42 @@ void o_xyz2acescg(const float in[3], float out[3])
 
 /* --------------------------------------------------------------------- sky */
 
+/* exp / acos as FIXED mul / add / sqrt expressions (deviation (6)): GLSL leaves their precision to the implementation,
+ * glibc and CUDA round differently, and the radiance cache (oracle_gi.c) quantises what the sky returns — so that cache tables
+ * and frames can be compared bit for bit, both sides evaluate these two functions with the same operations in the same order
+ * (relative error < 1e-7, below the float32 rounding of the surrounding expression).  o_sky_exp2 is oracle_cache.c's exp2_fixed. */
+float o_sky_exp2(float x)
+{
+    float nf = floorf(x + 0.5f);
+    float f = (x - nf) * 0.693147181f;
+    float p = 1.0f + f * (1.0f + f * (0.5f + f * (0.166666667f + f * (0.0416666667f + f * (0.00833333333f + f * (0.00138888889f + f * 0.000198412698f))))));
+    if (!(nf >= -126.0f)) return 0.0f;                                  /* also NaN */
+    if (nf > 127.0f) return INFINITY;
+    int32_t n = (int32_t)nf;
+    uint32_t bits = (uint32_t)(n + 127) << 23;
+    float scale;
+    memcpy(&scale, &bits, 4);
+    return p * scale;
+}
+float o_sky_exp(float x) { return o_sky_exp2(x * 1.44269504f); }
+/* Abramowitz & Stegun 4.4.46: acos(x) = sqrt(1 - x) * P7(x) on [0, 1] (|error| <= 2e-8), acos(-x) = pi - acos(x) */
+float o_sky_acos(float x)
+{
+    float a = fabsf(x);
+    float p = 1.5707963050f + a * (-0.2145988016f + a * (0.0889789874f + a * (-0.0501743046f + a * (0.0308918810f + a * (-0.0170881256f + a * (0.0066700901f + a * -0.0012624911f))))));
+    float r = sqrtf(1.0f - a) * p;
+    return x < 0.0f ? 3.14159265358979f - r : r;
+}
+
 /* sky.glsl:1-16 */
 static float radiance_internal(const float c[9], float cos_theta, float gamma, float cos_gamma)
 {
-    float expM = expf(c[4] * gamma);
+    float expM = o_sky_exp(c[4] * gamma);
     float rayM = cos_gamma * cos_gamma;
-    float mieM = (1.0f + rayM) / powf((1.0f + c[8] * c[8]) - (2.0f * c[8]) * cos_gamma, 1.5f);
+    float mb = (1.0f + c[8] * c[8]) - (2.0f * c[8]) * cos_gamma;
+    float mieM = (1.0f + rayM) / (mb * sqrtf(mb));                       /* pow(x, 1.5) = x sqrt(x): exact operations */
     float zenith = sqrtf(cos_theta);
-    return (1.0f + c[0] * expf(c[1] / (cos_theta + 0.01f))) *
+    return (1.0f + c[0] * o_sky_exp(c[1] / (cos_theta + 0.01f))) *
            ((((c[2] + c[3] * expM) + c[5] * rayM) + c[6] * mieM) + c[7] * zenith);
 }
 
@@ -167,7 +195,7 @@ void o_sky_radiance(const OSky *sky, const float dir[3], float out[3])
     if (sky->direction[1] <= 0.0f) { out[0] = out[1] = out[2] = 0.0f; return; }
     float cos_theta = fminf(fmaxf(dir[1], 0.0f), 1.0f);
     float cos_gamma = (dir[0] * sky->direction[0] + dir[1] * sky->direction[1]) + dir[2] * sky->direction[2];
-    float gamma = acosf(fminf(fmaxf(cos_gamma, -1.0f), 1.0f));
+    float gamma = o_sky_acos(fminf(fmaxf(cos_gamma, -1.0f), 1.0f));
     float xyz[3];
     xyz[0] = radiance_internal(sky->r.config, cos_theta, gamma, cos_gamma) * sky->r.radiance;
     xyz[1] = radiance_internal(sky->g.config, cos_theta, gamma, cos_gamma) * sky->g.radiance;

@@ -34,6 +34,10 @@ typedef struct OSky {
 /* Sunlight::bake, sky.rs:90-133 */
 void o_sunlight_bake(float turbidity, const float albedo[3], const float direction[3], OSky *out);
 /* sky.glsl:21-78 — `dir` normalised; result in ACEScg */
+/* fixed-expression exp2 / exp / acos (deviation (6)): the kernel evaluates the same operations in the same order */
+float o_sky_exp2(float x);
+float o_sky_exp(float x);
+float o_sky_acos(float x);
 void o_sky_radiance(const OSky *sky, const float dir[3], float out[3]);
 /* sky.glsl:80-113 */
 void o_sun_radiance(const OSky *sky, const float dir[3], float out[3]);

@@ -185,7 +185,7 @@ void o_scene_set_cull(OScene *s, int enabled) { s->cull = enabled; }
 
 /* Block-granular leaves (assets/shaders/final_gather/rough.rint:46-58, the reference's far-field intersection shader): a
  * non-empty leaf is hit where the ray enters its 4x4x4 box, no DDA.  Process-wide switch, set around a call by the tests. */
-static int g_rough_blocks;
+static int g_rough_blocks;      /* leaf mode: 0 = hit.rint (precise DDA), 1 = rough.rint (solid block), 2 = ambient_occlusion.rint */
 void o_set_rough_blocks(int enabled) { g_rough_blocks = enabled; }
 
 void o_scene_set_previous(OScene *s, const float *obj2world_prev)
@@ -238,12 +238,20 @@ static void intersect_aabb(const float origin[3], const float dir[3], float box_
 /* assets/shaders/primary/hit.rint:43-131 with scale = 1.0.  `origin` is leaf-local
  * (gl_ObjectRayOriginEXT - block.position, :139-141).  Returns 1 and (t, voxelId) when the DDA
  * reaches a set bit; acceptance against [tmin, tmax] is the caller's (reportIntersectionEXT). */
-int o_leaf_dda(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t_out, uint32_t *voxel_out)
+static int leaf_dda_mode(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t_out, uint32_t *voxel_out, int ao)
 {
     float tb[2];
     intersect_aabb(origin, dir, 0.0f, 4.0f, tb);                       /* :52 */
     if (tb[0] >= tb[1]) return 0;                                       /* :53-56 */
     if (tb[1] <= 0.0f) return 0;                                        /* :57-59 */
+    if (ao && tb[0] <= 8.0f && 8.0f <= tb[1]) {
+        /* ambient_occlusion.rint:62-73 — AMBIENT_OCCLUSION_THRESHOLD lies inside this leaf's box: a non-empty leaf is reported as
+         * a solid block at its entry (voxelId 0xFF, hit kind 1), an empty one is skipped; no DDA either way */
+        if (grid == 0) return 0;
+        *t_out = tb[0] + 0.0f;
+        *voxel_out = 0xFFu;
+        return 1;
+    }
     float hitDistance = fmaxf(tb[0], ray_tmin);                         /* :71 */
     int pos[3];
     float step[3], t_coef[3], t_bias[3], tMax[3], tDelta[3];
@@ -276,6 +284,18 @@ int o_leaf_dda(const float origin[3], const float dir[3], uint64_t grid, float r
     *t_out = hitDistance / 1.0f + 0.0f;
     *voxel_out = hit;
     return 1;
+}
+
+int o_leaf_dda(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t_out, uint32_t *voxel_out)
+{
+    return leaf_dda_mode(origin, dir, grid, ray_tmin, t_out, voxel_out, 0);
+}
+
+/* assets/shaders/final_gather/ambient_occlusion.rint:46-134: hit.rint's DDA plus the threshold rule above (the intersection
+ * shader of the ambient-occlusion pass' two rays) */
+int o_leaf_ao(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t_out, uint32_t *voxel_out)
+{
+    return leaf_dda_mode(origin, dir, grid, ray_tmin, t_out, voxel_out, 1);
 }
 
 /* ------------------------------------------------------- instance traversal */
@@ -372,7 +392,8 @@ static int trace_instance(const OInstance *in, const float ow[3], const float dw
             float lo_[3] = { o[0] - (float)cmin[0], o[1] - (float)cmin[1], o[2] - (float)cmin[2] };   /* hit.rint:140 */
             float th; uint32_t vox;
             int reported;
-            if (g_rough_blocks) {
+            if (g_rough_blocks == 2) reported = o_leaf_ao(lo_, d, grid, tmin, &th, &vox);
+            else if (g_rough_blocks) {
                 float tb[2];
                 intersect_aabb(lo_, d, 0.0f, 4.0f, tb);                 /* rough.rint:46 */
                 reported = !(tb[0] >= tb[1]) && grid != 0;              /* :47-53 */
@@ -813,3 +834,5 @@ void o_trace_rays(const OScene *s, const ORay *rays, uint64_t n, OHitRec *hits, 
     run_jobs(jobs, n_threads, rays_worker, stats);
     free(jobs);
 }
+
+#include "oracle_gi.c"    /* the GI passes use this file's static traversal and shading functions */

@@ -118,6 +118,7 @@ uint32_t o_debug_pixel(const OScene *s, const OCamera *cam, const OSky *sky, con
 
 /* building blocks exposed for unit tests */
 int   o_leaf_dda(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t, uint32_t *voxel);
+int   o_leaf_ao(const float origin[3], const float dir[3], uint64_t grid, float ray_tmin, float *t, uint32_t *voxel);
 void  o_camera_ray(const OCamera *cam, uint32_t width, uint32_t height, uint32_t px, uint32_t py,
                    float jx, float jy, float o[3], float d[3]);
 uint32_t o_pcg(uint32_t v);

@@ -70,6 +70,36 @@ class OHistogram(C.Structure):
     _fields_ = [("histogram", C.c_uint32 * 256), ("avg", C.c_float)]
 
 
+class OGiState(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("capacity", C.c_uint32), ("pool", C.c_void_p), ("pool_size", C.c_uint32)]
+
+
+class OGiStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("near_hits", "far_hits", "far_misses", "cache_found", "surfels_scheduled", "surfel_rays",
+                                          "cache_inserts", "insert_segments")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+CACHE_ENTRY_DTYPE = np.dtype([("fingerprint", "<u4"), ("radiance", "<u4"), ("last_accessed_frame", "<u2"), ("sample_count", "<u2")])
+SURFEL_DTYPE = np.dtype([("position", "<f4", 3), ("direction", "<u4")])
+
+
+class GiState:
+    """Persistent state of the reference's GI (standard.rs:334-358): the spatial-hash table (capacity + 2 entries, zeroed) and the
+    surfel pool (filled with 0xFF = invalid), as numpy arrays the oracle works on in place."""
+
+    def __init__(self, capacity, pool_size):
+        self.capacity, self.pool_size = int(capacity), int(pool_size)
+        self.table = np.zeros(self.capacity + 2, CACHE_ENTRY_DTYPE)
+        self.pool = np.zeros(self.pool_size, SURFEL_DTYPE)
+        self.pool.view(np.uint8)[:] = 0xFF
+
+    def c(self):
+        return OGiState(self.table.ctypes.data, self.capacity, self.pool.ctypes.data, self.pool_size)
+
+
 class OStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded")]
 
@@ -152,6 +182,9 @@ def lib() -> C.CDLL:
         "o_cache_key_of": (None, [pf32, pf32, C.POINTER(OSpatialHashKey)]),
         "o_cache_insert": (None, [vp, u32, C.POINTER(OSpatialHashKey), pf32, u32]),
         "o_cache_get": (i32, [vp, u32, C.POINTER(OSpatialHashKey), u32, pf32, pu32]),
+        "o_gi_frame": (None, [vp, C.POINTER(OCamera), C.POINTER(OSky), C.POINTER(OTraceConfig), C.POINTER(OGiState), vp, C.POINTER(OGBuffer),
+                              C.POINTER(OGiStats), u32]),
+        "o_gi_unpack_normal": (None, [u32, pf32]), "o_leaf_ao": (i32, [pf32, pf32, u64, f32, pf32, pu32]),
         "o_dense_from_tree": (vp, [vp]), "o_dense_free": (None, [vp]),
         "o_dense_march": (i32, [vp, C.POINTER(f64), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
         "o_dense_march_batch": (None, [vp, vp, vp, u64, f64, f64, i32, vp, vp, vp]),
@@ -412,6 +445,24 @@ class Scene:
                            C.byref(st), threads or os.cpu_count() or 1)
         res["stats"] = st.as_dict()
         return res
+
+    def gi_frame(self, camera, sky, width, height, state: "GiState", seed=0, frame_index=0, threads=None):
+        """One frame of the reference's own GI (oracle_gi.h).  Returns illuminance [H, W, 4] float16 (YCoCg + normHitDist), the
+        G-buffer of the primary hit and the pass statistics; `state` (cache table + surfel pool) is updated in place."""
+        cam = camera if isinstance(camera, OCamera) else as_struct(OCamera, camera)
+        sk = sky if isinstance(sky, OSky) else as_struct(OSky, sky)
+        cfg = OTraceConfig(width, height, 1, 0, seed, frame_index, 0, height, 0)
+        img = np.zeros((height, width, 4), np.uint16)
+        g = {"albedo": np.zeros((height, width), np.uint32), "depth": np.zeros((height, width), np.float32),
+             "normal": np.zeros((height, width), np.uint32), "voxel_id": np.full((height, width), 0xFFFFFFFF, np.uint32)}
+        motion = np.zeros((height, width, 4), np.float32)
+        gb = OGBuffer(g["albedo"].ctypes.data, g["depth"].ctypes.data, g["normal"].ctypes.data, motion.ctypes.data, g["voxel_id"].ctypes.data)
+        st = OGiStats()
+        cs = state.c()
+        lib().o_gi_frame(self._h, C.byref(cam), C.byref(sk), C.byref(cfg), C.byref(cs), img.ctypes.data, C.byref(gb), C.byref(st),
+                         threads or os.cpu_count() or 1)
+        g["motion"] = motion.astype(np.float16)
+        return {"illuminance": img.view(np.float16), "gbuffer": g, "stats": st.as_dict()}
 
     def debug_pixel(self, camera, sky, width, height, px, py, spp=1, max_bounces=0, seed=0, frame_index=0, cap=256):
         """All rays of one pixel's paths and the oracle's answers (voxel bit 31 = any-hit shadow ray)."""
