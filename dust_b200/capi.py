@@ -110,6 +110,22 @@ class DustLaunchInfo(C.Structure):
                [(n, C.c_uint64) for n in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded", "mask_words_strict")]
 
 
+class DustCacheEntry(C.Structure):
+    _fields_ = [("fingerprint", C.c_uint32), ("radiance", C.c_uint32), ("last_accessed_frame", C.c_uint16), ("sample_count", C.c_uint16)]
+
+
+class DustSurfel(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("direction", C.c_uint32)]
+
+
+class DustGiStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("near_hits", "far_hits", "far_misses", "cache_found", "surfels_scheduled", "surfel_rays",
+                                          "cache_inserts", "insert_segments")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 class DustExposureParams(C.Structure):
     _fields_ = [("min_log_luminance", C.c_float), ("log_luminance_range", C.c_float), ("time_coefficient", C.c_float)]
 
@@ -167,6 +183,13 @@ SYMBOLS = {
                                        C.POINTER(DustExposureParams), C.POINTER(C.c_float)]),
     "dust_tone_map": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.POINTER(DustToneMapParams), C.c_void_p]),
+    "dust_cache_create": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "dust_cache_destroy": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "dust_cache_clear": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "dust_cache_download": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "dust_cache_upload": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "dust_trace_gi": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(DustCamera), C.POINTER(DustSky), C.POINTER(DustTraceConfig),
+                                  C.POINTER(DustFrame), C.POINTER(DustGiStats)]),
     "dust_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(DustStats)]),
     "dust_get_launch_info": (C.c_int32, [C.c_void_p, C.POINTER(DustLaunchInfo), C.c_uint32, C.POINTER(C.c_uint32)]),
 }

@@ -14,7 +14,7 @@
 //       16^3 node : 64 words (word w = bits 64w..64w+63 of child_mask, base = slot of the first
 //                   child of that word)                                = 1024 B  (was 16 896 B)
 //       4^3 node  : 1 word, base = slot of its first leaf               = 16 B    (was 264 B)
-//       leaf      : 1 word, mask = occupancy, base = material_ptr       = 16 B    (was 24 B)
+//       leaf      : 1 word, mask = occupancy, base = material_ptr, w = GPUVoxNode.avg_albedo (geometry.rs:86-113)   = 16 B    (was 24 B)
 //
 //   * per 16^3 node one extra 64-bit BLOCK mask (bit per 4x4x4 block of children): the walk asks it first
 //     and leaves an empty block as one cell of 4x the edge (64 voxels under a 256^3 root).
@@ -44,9 +44,10 @@ struct alignas(16) DInstance {
     const uint2 *blocks;           // per 16^3 node: 64-bit block mask, bit bx<<4|by<<2|bz = "some child in that 4x4x4 block of children"
     const uchar4 *palette_raw;     // 256 x RGBA8 as uploaded (G-buffer albedo)
     float o2w[9];                  // linear part of object -> world (normals)
-    uint32_t _pad1[1];
+    float o2w_t[3];                // its translation (block centres of the far-field gather, final_gather.rchit:42)
+    uint32_t _pad1[2];
 };
-static_assert(sizeof(DInstance) == 160, "DInstance layout");
+static_assert(sizeof(DInstance) == 176, "DInstance layout");
 
 // Binary BVH over instance world boxes (replaces the TLAS).  A node holds the padded boxes of BOTH
 // children, so one node fetch (4 x 128 bit) decides both.  child >= 0: inner node index;

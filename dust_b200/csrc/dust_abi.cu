@@ -1,8 +1,7 @@
 // C ABI of libdust_b200.so (include/dust_b200.h): context, one-time tree re-layout + upload,
 // instance BVH, kernel launches.  No CPU compute path exists in this library: every trace call
 // launches sm_100a kernels or fails.
-#include "wavefront.cuh"
-#include "post.cuh"
+#include "abi_internal.h"
 #include "build.cuh"
 
 #include <cstdlib>
@@ -19,89 +18,13 @@
 
 using namespace dust;
 
-struct DustCtx {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t side[2] = { nullptr, nullptr };   // dust_trace_rays(DUST_MEM_HOST): copy / compute overlap across chunks
-    cudaEvent_t ev_join = nullptr;                 // fork / join of the side streams (created once, lives with the context)
-    std::string err;
-    // scratch for DUST_MEM_HOST frames / ray batches
-    void *scratch = nullptr;
-    size_t scratch_bytes = 0;
-    DCounters *d_counters = nullptr;
-    // wavefront pipeline: path state + ray queues (grown on demand), queue / bin counters (fixed size)
-    void *wf_scratch = nullptr;
-    size_t wf_scratch_bytes = 0;
-    uint32_t *d_wf_counters = nullptr;
-    int sms = 148;
-    DustStats stats{};
-    // DUST_TRACE_TIMING: one event after every launch of the last dust_trace call (+ a counter snapshot with DUST_TRACE_STATS)
-    struct LaunchRec { const char *name; cudaEvent_t ev; };
-    bool timing_on = false;
-    cudaEvent_t ev_begin = nullptr;
-    std::vector<LaunchRec> launch_recs;
-    uint32_t launch_dropped = 0;             // launches past kMaxLaunchRecs of the last timed call (reported, not silently lost)
-    std::vector<cudaEvent_t> ev_pool;
-    DCounters *h_snaps = nullptr;            // pinned, kMaxLaunchRecs entries
-    bool snaps_valid = false;
-    // dust_trace_async: frames in flight (the reference keeps up to 3, crates/rhyolite_bevy/src/lib.rs:58): each slot owns a device
-    // staging buffer; the D2H copy of frame k runs on `copy_stream` behind the event `traced` while frame k+1 traces
-    struct FrameSlot { void *scratch = nullptr; size_t scratch_bytes = 0; cudaEvent_t traced = nullptr, done = nullptr; uint64_t ticket = 0; bool busy = false; };
-    FrameSlot slots[3];
-    cudaStream_t copy_stream = nullptr;
-    uint64_t next_ticket = 1;
-    // multi-GPU: NCCL communicator of the shard group (dust_comm_init); NCCL is dlopen'ed on first use
-    void *nccl_comm = nullptr;
-    int comm_rank = 0, comm_size = 1;
-};
-
-struct DustTree {
-    uint32_t n_levels = 0;
-    void *blob = nullptr;            // one device allocation
-    size_t blob_bytes = 0;
-    const DNode16 *n16 = nullptr;
-    const uint2 *blocks = nullptr;
-    const uint4 *mids = nullptr;
-    const uint4 *leaves = nullptr;
-    const uint8_t *materials = nullptr;
-    const float4 *palette_lin = nullptr;
-    const uchar4 *palette_raw = nullptr;
-    uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0, n_materials = 0;
-    int32_t bmin[3] = { 0, 0, 0 }, bmax[3] = { 0, 0, 0 };   // occupied bounds in object voxels
-};
-
-struct DustExposure {
-    DHistogram *d = nullptr;
-};
-
-struct DustScene {
-    DInstance *d_inst = nullptr;
-    DBvhNode *d_bvh = nullptr;
-    float4 *d_prev = nullptr;        // last frame's object -> world rows (3 per instance)
-    DSceneView view{};               // device pointers + root box, passed to the kernels by value
-    uint32_t n_inst = 0, n_bvh = 0, max_levels = 3, min_levels = 3;
-    std::vector<const DustTree *> trees;   // per instance, for dust_scene_update_transforms
-    std::vector<float> o2w;                // current object -> world rows (12 per instance)
-};
-
-namespace {
-
-int32_t fail(DustCtx *ctx, int32_t code, const std::string &msg)
+int32_t dust_fail(DustCtx *ctx, int32_t code, const std::string &msg)
 {
     if (ctx) ctx->err = msg;
     return code;
 }
 
-#define CU_TRY(ctx, expr)                                                                         \
-    do {                                                                                          \
-        cudaError_t e_ = (expr);                                                                  \
-        if (e_ != cudaSuccess)                                                                    \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? DUST_ERR_OUT_OF_MEMORY : DUST_ERR_CUDA, \
-                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
-    } while (0)
-
-int32_t ensure_scratch(DustCtx *ctx, size_t bytes)
+int32_t dust_ensure_scratch(DustCtx *ctx, size_t bytes)
 {
     if (bytes <= ctx->scratch_bytes) return DUST_OK;
     if (ctx->scratch) { CU_TRY(ctx, cudaFree(ctx->scratch)); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
@@ -109,6 +32,11 @@ int32_t ensure_scratch(DustCtx *ctx, size_t bytes)
     ctx->scratch_bytes = bytes;
     return DUST_OK;
 }
+
+namespace {
+
+inline int32_t fail(DustCtx *ctx, int32_t code, const std::string &msg) { return dust_fail(ctx, code, msg); }
+inline int32_t ensure_scratch(DustCtx *ctx, size_t bytes) { return dust_ensure_scratch(ctx, bytes); }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }   // 128-bit loads / stores (include/dust_b200.h "Alignment")
@@ -218,6 +146,28 @@ void relayout(const HostTree &ht, Relayout &r)
 inline float srgb_to_linear(float c)
 {
     return c < 0.04045f ? c / 12.92f : powf(fabsf(c + 0.055f) / 1.055f, 2.4f);
+}
+
+// GPUVoxNode.avg_albedo (crates/vox/src/geometry.rs:86-113): mean palette colour of a leaf's voxels, sRGB-encoded, packed
+// R10G10B10A2 — the `Block.avg_albedo` the far-field gather multiplies cached radiance with (final_gather.rchit:68-80).
+// Stored in the spare fourth word of the leaf's device word.  Host arithmetic (libm powf, like the Rust `powf`) for both build paths.
+inline uint32_t leaf_avg_albedo(uint64_t mask, const uint8_t *materials, const uint8_t *palette)
+{
+    uint32_t col[4] = { 0, 0, 0, 0 };
+    const uint32_t nv = (uint32_t)__builtin_popcountll(mask);
+    if (!nv) return 0;
+    for (uint32_t i = 0; i < nv; i++) {
+        const uint8_t *c = palette + 4 * (size_t)materials[i];
+        for (int k = 0; k < 4; k++) col[k] += c[k];
+    }
+    const float denom = (float)nv * 255.0f;
+    float e[3];
+    for (int k = 0; k < 3; k++) {
+        const float c = (float)col[k] / denom;
+        e[k] = c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+    }
+    const float cw = (float)col[3] / denom;
+    return ((uint32_t)(e[0] * 1023.0f) << 22) | ((uint32_t)(e[1] * 1023.0f) << 12) | ((uint32_t)(e[2] * 1023.0f) << 2) | (uint32_t)(cw * 3.0f);
 }
 
 // ---- instance transforms and BVH ----------------------------------------------------------------
@@ -352,11 +302,36 @@ void sun_radiance_host(const DustSky &sky, float ar2, const float dir[3], float 
     for (int r = 0; r < 3; r++) out[r] = (m[r] * xyz[0] + m[3 + r] * xyz[1]) + m[6 + r] * xyz[2];
 }
 
+}  // namespace
+
+// uniform-only terms hoisted out of the shaders (ambient_occlusion.rgen:45, nee.rmiss:18-19, sky.glsl:88-89): normalize(sky.direction),
+// 1 / sin^2(solar radius), and sun_radiance(normalize(sun_dir)) * (1 - cos(solar radius)), which does not depend on the hit
+void dust_sun_terms(const DustSky *sky, float sun_dir[3], float *sun_ar2, float sun_nee[3])
+{
+    const float *d = sky->direction;
+    const float l = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    sun_dir[0] = d[0] / l; sun_dir[1] = d[1] / l; sun_dir[2] = d[2] / l;
+    const float sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
+    const float sn = sinf(sky->sunlight_intensity[3]);
+    *sun_ar2 = 1.0f / (sn * sn);
+    const float sl = sqrtf((sun_dir[0] * sun_dir[0] + sun_dir[1] * sun_dir[1]) + sun_dir[2] * sun_dir[2]);
+    const float sdn[3] = { sun_dir[0] / sl, sun_dir[1] / sl, sun_dir[2] / sl };
+    float su[3];
+    sun_radiance_host(*sky, *sun_ar2, sdn, su);
+    for (int a = 0; a < 3; a++) sun_nee[a] = su[a] * sun_cone;
+}
+
+namespace {
+
 constexpr size_t kMaxLaunchRecs = 1024;                              // a 64-bounce wavefront frame issues ~7 launches per depth
 
 // called after every kernel launch; with DUST_TRACE_TIMING it also drops an event behind the launch (launches of one call are
 // back to back on one stream, so consecutive events bracket one kernel) and, in a STATS pass, snapshots the counters
-void count_launch(DustCtx *ctx, const char *name = nullptr)
+void count_launch(DustCtx *ctx, const char *name = nullptr) { dust_count_launch(ctx, name); }
+
+}  // namespace
+
+void dust_count_launch(DustCtx *ctx, const char *name)
 {
     ctx->stats.kernel_launches++;
     if (!ctx->timing_on || !name) return;
@@ -368,6 +343,8 @@ void count_launch(DustCtx *ctx, const char *name = nullptr)
     cudaEventRecord(ev, ctx->stream);
     ctx->launch_recs.push_back({ name, ev });
 }
+
+namespace {
 
 int32_t fetch_counters(DustCtx *ctx)
 {
@@ -645,6 +622,7 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     float4 pal[256];
     uint8_t praw[1024];
     palette_tables(desc->palette, pal, praw);
+    for (uint4 &l : r.leaves) l.w = leaf_avg_albedo(((uint64_t)l.y << 32) | l.x, desc->materials + l.z, praw);   // praw: 256 entries, the last one zero
 
     // block masks: bit bx<<4|by<<2|bz of node n = "some child bit set in the 4x4x4 block (bx,by,bz) of its 16^3 children"
     std::vector<uint2> blocks(r.n16.size());
@@ -776,6 +754,20 @@ int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n
         cudaFree(t->blob); delete t;
         return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "leaf material_ptr runs past the material array (duplicate voxels in the model)");
     }
+    if (h_counts.n_leaves) {
+        // avg_albedo of every leaf: integer sums + libm powf on the host, so that both build paths store the same word
+        std::vector<uint4> hl(h_counts.n_leaves);
+        std::vector<uint8_t> hm((size_t)h_counts.n_materials + 16);
+        e = cudaMemcpyAsync(hl.data(), base + L.leaves, hl.size() * sizeof(uint4), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hm.data(), base + L.mat, (size_t)h_counts.n_materials, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) {
+            for (uint4 &l : hl) l.w = leaf_avg_albedo(((uint64_t)l.y << 32) | l.x, hm.data() + l.z, praw);
+            e = cudaMemcpyAsync(base + L.leaves, hl.data(), hl.size() * sizeof(uint4), cudaMemcpyHostToDevice, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, DUST_ERR_CUDA, cudaGetErrorString(e)); }
+    }
     t->n_levels = 3;
     t->n_leaves = h_counts.n_leaves; t->n_mids = h_counts.n_mids; t->n_n16 = 1; t->n_materials = h_counts.n_materials;
     for (int a = 0; a < 3; a++) { t->bmin[a] = h_counts.n_leaves ? h_counts.bmin[a] : 0; t->bmax[a] = h_counts.n_leaves ? h_counts.bmax[a] : 0; }
@@ -842,12 +834,12 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         DInstance &d = inst[k];
         const float *m = o2w + 12 * (size_t)k;
         if (!world2obj(m, d.w2o)) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "instance transform is singular or not finite");
-        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c];
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) d.o2w[3 * r + c] = m[4 * r + c]; d.o2w_t[r] = m[4 * r + 3]; }
         d.n_levels = t->n_levels;
         d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin; d.palette_raw = t->palette_raw;
         // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
         for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
-        d._pad1[0] = 0;
+        for (uint32_t &w : d._pad1) w = 0;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove
@@ -1018,21 +1010,7 @@ static int32_t trace_impl(DustCtx *ctx, const DustScene *scene, const DustCamera
     memset(&p, 0, sizeof p);
     p.scene = scene->view;
     p.cam = *camera; p.sky = *sky; p.cfg = cfg;
-    {
-        // uniform-only terms hoisted out of the shaders (ambient_occlusion.rgen:45, nee.rmiss:18-19, sky.glsl:88-89)
-        const float *d = sky->direction;
-        const float l = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
-        p.sun_dir[0] = d[0] / l; p.sun_dir[1] = d[1] / l; p.sun_dir[2] = d[2] / l;
-        const float sun_cone = 1.0f - cosf(sky->sunlight_intensity[3]);
-        const float sn = sinf(sky->sunlight_intensity[3]);
-        p.sun_ar2 = 1.0f / (sn * sn);
-        // nee.rmiss:18-21: sun_radiance(normalize(sun_dir)) * (1 - cos(solar radius)) does not depend on the hit
-        const float sl = sqrtf((p.sun_dir[0] * p.sun_dir[0] + p.sun_dir[1] * p.sun_dir[1]) + p.sun_dir[2] * p.sun_dir[2]);
-        const float sdn[3] = { p.sun_dir[0] / sl, p.sun_dir[1] / sl, p.sun_dir[2] / sl };
-        float su[3];
-        sun_radiance_host(*sky, p.sun_ar2, sdn, su);
-        for (int a = 0; a < 3; a++) p.sun_nee[a] = su[a] * sun_cone;
-    }
+    dust_sun_terms(sky, p.sun_dir, &p.sun_ar2, p.sun_nee);
     p.tiles_x = (cfg.width + 31) / 32; p.tiles_y = (cfg.height + 31) / 32; p.n_local_tiles = tiles_per_shard;
     p.ycocg = frame->radiance_format == DUST_FMT_YCOCG16F;
 
@@ -1591,3 +1569,6 @@ int32_t dust_get_stats(DustCtx *ctx, DustStats *out)
 }
 
 }  // extern "C"
+
+// the radiance cache + dust_trace_gi: same translation unit (the kernels of the shared headers are defined once)
+#include "dust_gi.cu"

@@ -321,13 +321,16 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
 // Leaf step on leaf w.leaf_i: one 128-bit load (occupancy + material_ptr), then hit.rint's DDA.  Returns
 // true with (t, voxel) when a voxel is reached; the caller applies reportIntersectionEXT's [tmin, tmax].
 // (A resumable DDA — at most K iterations per voted LEAF operation — was tried: more trips, slower.)
+// leaf_mode (uniform per launch): 0 = hit.rint (precise DDA), 1 = rough.rint (solid block), 2 = ambient_occlusion.rint
+enum : int { LEAF_PRECISE = 0, LEAF_ROUGH = 1, LEAF_AO = 2 };
 template <bool STATS>
-__device__ __forceinline__ bool walk_leaf(const Walk &w, float tmin, float &th, uint32_t &vox, Counters &st, const bool rough = false)
+__device__ __forceinline__ bool walk_leaf(const Walk &w, float tmin, float &th, uint32_t &vox, Counters &st, const int leaf_mode = LEAF_PRECISE)
 {
     const uint4 leaf = __ldg(&w.leaves[w.leaf_i]);
     if (STATS) { st.dbg[10]++; st.mask_words_strict++; }
     const f3 lo = mk3(w.o.x - (float)(w.jx << 2), w.o.y - (float)(w.jy << 2), w.o.z - (float)(w.jz << 2));   // hit.rint:140
-    if (rough) return leaf_rough(lo, w.d, leaf.x, leaf.y, th, vox);     // block-granular far rays (rough.rint); uniform per launch
+    if (leaf_mode == LEAF_ROUGH) return leaf_rough(lo, w.d, leaf.x, leaf.y, th, vox);     // block-granular far rays (rough.rint)
+    if (leaf_mode == LEAF_AO) return leaf_dda_inv<STATS, true>(lo, w.d, w.inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]);
     return leaf_dda_inv<STATS>(lo, w.d, w.inv, leaf.x, leaf.y, tmin, th, vox, st.dbg[11]);
 }
 
@@ -342,7 +345,7 @@ __device__ __forceinline__ uint32_t walk_pos(const Walk &w) { return (uint32_t)w
 // `sm` = this lane's column of the block's scratch: word k lives at sm[k * DUST_THREADS].
 template <int NL, bool STATS>
 __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, const f3 rd, const float tmin, const float tmax,
-                                            const bool any, const bool live, uint32_t *sm, Hit &best, Counters &st, const bool rough = false)
+                                            const bool any, const bool live, uint32_t *sm, Hit &best, Counters &st, const int leaf_mode = LEAF_PRECISE)
 {
     const unsigned full = 0xffffffffu;
     best.hit = false; best.inst = 0xFFFFFFFFu; best.t = tmax;
@@ -385,7 +388,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
             } else if (op == M_LEAF) {
                 if (mode == M_LEAF) {
                     float th; uint32_t vox;
-                    if (walk_leaf<STATS>(w, tmin, th, vox, st, rough) && tmin <= th && th <= cur) {       // reportIntersectionEXT
+                    if (walk_leaf<STATS>(w, tmin, th, vox, st, leaf_mode) && tmin <= th && th <= cur) {       // reportIntersectionEXT
                         if (any) { best.hit = true; best.inst = w.inst; mode = M_DONE; pend = -1; sp = DUST_SCRATCH_WORDS; }
                         else {
                             if (!best.hit || th < cur || w.inst < best.inst) {                     // (t, instance) lexicographic

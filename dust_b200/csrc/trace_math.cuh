@@ -187,7 +187,10 @@ __device__ __noinline__ void sky_eval(const DustSky &sky, float ar2, float dx, f
 // leaves with one ray compute it once.  dir has no zero component (deviation (1)), so step = sign(dir)
 // is +-1 and is carried as a predicate; the 0/1 `comp` factors of hit.rint:102-110 are carried as
 // predicates too: x + d * 1.0f == x + d and x + d * 0.0f == x + 0.0f for finite d, bit for bit.
-template <bool COUNT>
+// AO: assets/shaders/final_gather/ambient_occlusion.rint:46-134, the intersection shader of the ambient-occlusion pass' two rays — the
+// same DDA plus one rule (:62-73): when AMBIENT_OCCLUSION_THRESHOLD (8.0) lies inside this leaf's box along the ray, a non-empty leaf
+// is reported as a solid block at its entry (voxelId 0xFF) and an empty one is skipped, without a DDA.
+template <bool COUNT, bool AO = false>
 __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t grid_lo, uint32_t grid_hi, float ray_tmin,
                                              float &t_out, uint32_t &voxel, uint32_t &iterations)
 {
@@ -199,6 +202,12 @@ __device__ __forceinline__ bool leaf_dda_inv(f3 origin, f3 dir, f3 inv, uint32_t
     float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     if (t_min >= t_max) return false;                                   // :53
     if (t_max <= 0.0f) return false;                                    // :57
+    if (AO && t_min <= 8.0f && 8.0f <= t_max) {
+        if ((grid_lo | grid_hi) == 0u) return false;
+        t_out = t_min + 0.0f;
+        voxel = 0xFFu;
+        return true;
+    }
     float hitDistance = fmaxf(t_min, ray_tmin);                         // :71
     int px = __float2int_rd(origin.x + dir.x * hitDistance);            // :72-74
     int py = __float2int_rd(origin.y + dir.y * hitDistance);

@@ -127,7 +127,7 @@ __device__ __forceinline__ void wf_store_hit(const WfParams &p, uint32_t i, bool
 // `list` != NULL: trace only the queue slots list[0 .. *count) (the rays wf_cull could not pre-cull).
 // ROUGH (ray batches only, DUST_RAYS_ROUGH): block-granular leaves; a compile-time flag — as a run-time one the cold branch cost the
 // hot path registers (-2.5 % on config 5).
-template <int NL, bool STATS, bool ROUGH = false>
+template <int NL, bool STATS, int ROUGH = 0>          // ROUGH: the leaf mode (LEAF_PRECISE / LEAF_ROUGH / LEAF_AO)
 __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count,
                                                                           const uint32_t *list)
 {

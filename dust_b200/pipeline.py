@@ -292,6 +292,72 @@ class Scene:
                                              DUST_TRACE_STATS if stats else 0), "dust_trace_rays")
 
 
+CACHE_ENTRY_DTYPE = np.dtype([("fingerprint", "<u4"), ("radiance", "<u4"), ("last_accessed_frame", "<u2"), ("sample_count", "<u2")])
+SURFEL_DTYPE = np.dtype([("position", "<f4", 3), ("direction", "<u4")])
+
+
+class RadianceCache:
+    """The persistent state of the reference's GI on the device (dust_cache_*): the spatial-hash radiance cache and the surfel pool
+    (standard.rs:334-358).  gi_frame = dust_trace_gi: one frame of primary + ambient-occlusion + final-gather + surfel passes."""
+
+    def __init__(self, ctx: Context, capacity=32 * 1024 * 1024, surfel_pool_size=720 * 480):
+        self.ctx, self.capacity, self.pool_size = ctx, int(capacity), int(surfel_pool_size)
+        h = C.c_void_p()
+        check(ctx.h, ctx.lib.dust_cache_create(ctx.h, self.capacity, self.pool_size, C.byref(h)), "dust_cache_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.dust_cache_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def clear(self):
+        check(self.ctx.h, self.ctx.lib.dust_cache_clear(self.ctx.h, self.h), "dust_cache_clear")
+
+    def download(self):
+        """(table[capacity + 2], pool[pool_size]) as structured numpy arrays"""
+        t, p = np.zeros(self.capacity + 2, CACHE_ENTRY_DTYPE), np.zeros(self.pool_size, SURFEL_DTYPE)
+        check(self.ctx.h, self.ctx.lib.dust_cache_download(self.ctx.h, self.h, t.ctypes.data, len(t), p.ctypes.data, len(p)), "dust_cache_download")
+        return t, p
+
+    def upload(self, table=None, pool=None):
+        t = None if table is None else np.ascontiguousarray(table, CACHE_ENTRY_DTYPE)
+        p = None if pool is None else np.ascontiguousarray(pool, SURFEL_DTYPE)
+        check(self.ctx.h, self.ctx.lib.dust_cache_upload(self.ctx.h, self.h, None if t is None else t.ctypes.data, 0 if t is None else len(t),
+                                                         None if p is None else p.ctypes.data, 0 if p is None else len(p)), "dust_cache_upload")
+
+    def gi_frame(self, scene: "Scene", camera, sky, width, height, seed=0, frame_index=0, gbuffer=True, stats=True):
+        """Host-buffer call.  Returns dict(illuminance[H, W, 4] float16 = YCoCg + normHitDist, gbuffer, stats)."""
+        ctx = self.ctx
+        cfg = DustTraceConfig(width, height, 1, 0, seed, frame_index, 0, 1, 0)
+        img = np.zeros((height, width, 4), np.float16)
+        fr = DustFrame(_ptr(img), None, None, None, None, DUST_MEM_HOST, capi.DUST_FMT_YCOCG16F)
+        res = {"illuminance": img}
+        if gbuffer:
+            g = {"albedo": np.zeros((height, width), np.uint32), "depth": np.zeros((height, width), np.float32),
+                 "normal": np.zeros((height, width), np.uint32), "motion": np.zeros((height, width, 4), np.float16),
+                 "voxel_id": np.full((height, width), 0xFFFFFFFF, np.uint32)}
+            gb = DustGBuffer(*[_ptr(g[k]) for k in ("albedo", "depth", "normal", "motion", "voxel_id")])
+            fr.gbuffer = C.pointer(gb)
+            res["gbuffer"] = g
+        st = capi.DustGiStats()
+        check(ctx.h, ctx.lib.dust_trace_gi(ctx.h, scene.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr),
+                                           C.byref(st) if stats else None), "dust_trace_gi")
+        if stats:
+            res["stats"] = st.as_dict()
+        return res
+
+    def gi_frame_device(self, scene: "Scene", camera, sky, width, height, illuminance, seed=0, frame_index=0):
+        """Device-buffer call (no copies, no sync): `illuminance` is a CUDA float16 tensor [H, W, 4]."""
+        ctx = self.ctx
+        cfg = DustTraceConfig(width, height, 1, 0, seed, frame_index, 0, 1, 0)
+        fr = DustFrame(_ptr(illuminance), None, None, None, None, DUST_MEM_DEVICE, capi.DUST_FMT_YCOCG16F)
+        check(ctx.h, ctx.lib.dust_trace_gi(ctx.h, scene.h, self.h, C.byref(camera), C.byref(sky), C.byref(cfg), C.byref(fr), None), "dust_trace_gi")
+
+
 class Exposure:
     """The reference's Histogram buffer + the two post passes (dust_auto_exposure, dust_tone_map).
     Images are numpy arrays (host) or torch CUDA tensors (device): illuminance [H,W,4] float16 in

@@ -297,6 +297,56 @@ int32_t dust_auto_exposure(DustCtx *ctx, DustExposure *exposure, const void *ill
 int32_t dust_tone_map(DustCtx *ctx, const DustExposure *exposure, const void *illuminance, const uint32_t *albedo,
                       uint32_t width, uint32_t height, uint32_t memory, const DustToneMapParams *params, void *dst);
 
+/* ---- the reference's own global illumination ------------------------------------------------------------
+ * StandardPipeline::render's four ray-tracing dispatches for one frame (crates/render/src/pipeline/standard.rs:477-789) with their
+ * persistent state (standard.rs:334-358): the world-space radiance cache `spatial_hash` (SpatialHashEntry, 3-probe open addressing,
+ * LogLuv radiance, capped running mean, LRU eviction: assets/shaders/headers/spatial_hash.glsl:128-220) and the `surfel_pool`.
+ *   primary            primary/{primary.rgen, hit.rchit, miss.rmiss}                      -> G-buffer, illuminance = 0
+ *   ambient occlusion  final_gather/ambient_occlusion.{rgen, rint, rchit, rmiss}, nee.rmiss -> sun term + the near segment [0.1, 8]
+ *   final gather       final_gather/final_gather.{rgen, rchit, rmiss}, rough.rint          -> the far segment [8, far]: block-granular hit,
+ *                                                                                            cache look-up, surfel scheduling, sky on a miss
+ *   surfel             surfel/{surfel.rgen, surfel.rchit, surfel.rmiss, nee.rmiss}         -> one ray per pool entry, cache inserts
+ * The reference's invocations race on the cache and the pool; this library runs ONE of the admitted interleavings, the same on every
+ * run: look-ups of a pass see the table as the previous pass left it, the inserts of the surfel pass are applied in ascending surfel
+ * index (sorted by probe window, independent windows in parallel), the highest pixel that maps to a pool slot wins.  Noise comes from
+ * pcg streams seeded by DustTraceConfig.seed / frame_index instead of the STBN textures (Git-LFS pointers in the reference).
+ *
+ * dust_trace_gi: `config` = width, height, seed (push_constants.rand), frame_index (spp, max_bounces, shards, flags are ignored).
+ * `frame->radiance` must be DUST_FMT_YCOCG16F: the reference's img_illuminance (YCoCg + normHitDist, half floats) for pixels with a
+ * primary hit and img_illuminance_denoised = pack((sky + sun) / 3.14, 100000) for the others; `frame->gbuffer` (optional) receives
+ * the primary-hit images; hit arrays are not written.  `stats_out` may be NULL (passing it synchronises). */
+typedef struct DustRadianceCache DustRadianceCache;
+typedef struct DustCacheEntry {          /* SpatialHashEntry, headers/layout.playout (scalar layout, 12 bytes) */
+    uint32_t fingerprint;                /* 0 = empty */
+    uint32_t radiance;                   /* LogLuv: 14 bits log2 Y, 9 + 9 bits chroma */
+    uint16_t last_accessed_frame;
+    uint16_t sample_count;
+} DustCacheEntry;
+typedef struct DustSurfel {              /* SurfelEntry, headers/layout.playout (16 bytes) */
+    float position[3];                   /* world-space centre of the 4x4x4 block */
+    uint32_t direction;                  /* face 0..5; >= 6: empty slot (the pool starts filled with 0xFF bytes, standard.rs:347-349) */
+} DustSurfel;
+typedef struct DustGiStats {
+    uint64_t near_hits;                  /* pixels resolved by the ambient-occlusion ray */
+    uint64_t far_hits, far_misses;       /* final-gather rays */
+    uint64_t cache_found;                /* look-ups (final gather + surfel pass) that found their key */
+    uint64_t surfels_scheduled;          /* pool write requests of this frame */
+    uint64_t surfel_rays;                /* valid pool entries traced */
+    uint64_t cache_inserts;
+    uint64_t insert_segments;            /* independent probe-window groups the inserts were applied in */
+} DustGiStats;
+/* capacity: SpatialHashCapacity (reference: 32 * 1024 * 1024, spatial_hash.glsl:1); surfel_pool_size: SurfelPoolSize (720 * 480) */
+int32_t dust_cache_create(DustCtx *ctx, uint32_t capacity, uint32_t surfel_pool_size, DustRadianceCache **out);
+int32_t dust_cache_destroy(DustCtx *ctx, DustRadianceCache *cache);
+int32_t dust_cache_clear(DustCtx *ctx, DustRadianceCache *cache);
+/* host copies of the state (tests compare it with the CPU checker): n_entries <= capacity + 2 entries, n_surfels <= pool size */
+int32_t dust_cache_download(DustCtx *ctx, const DustRadianceCache *cache, DustCacheEntry *entries_out, uint64_t n_entries,
+                            DustSurfel *surfels_out, uint64_t n_surfels);
+int32_t dust_cache_upload(DustCtx *ctx, DustRadianceCache *cache, const DustCacheEntry *entries, uint64_t n_entries,
+                          const DustSurfel *surfels, uint64_t n_surfels);
+int32_t dust_trace_gi(DustCtx *ctx, const DustScene *scene, DustRadianceCache *cache, const DustCamera *camera, const DustSky *sky,
+                      const DustTraceConfig *config, const DustFrame *frame, DustGiStats *stats_out);
+
 int32_t dust_get_stats(DustCtx *ctx, DustStats *out);
 /* The launches of the last dust_trace call made with DUST_TRACE_TIMING, in order: kernel name, device time between the
  * event behind the previous launch and the one behind this launch, and (when that call also had DUST_TRACE_STATS) what

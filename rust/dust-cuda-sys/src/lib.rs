@@ -33,6 +33,7 @@ pub const DUST_COMM_ID_BYTES: usize = 128;
 #[repr(C)] pub struct DustTree { _p: [u8; 0] }
 #[repr(C)] pub struct DustScene { _p: [u8; 0] }
 #[repr(C)] pub struct DustExposure { _p: [u8; 0] }
+#[repr(C)] pub struct DustRadianceCache { _p: [u8; 0] }
 
 /// `dust_vdb::Tree<hierarchy!(..)>` as it lies in host memory (crates/vdb/src/tree.rs:7-13, pool.rs:3-17).
 #[repr(C)]
@@ -216,6 +217,37 @@ pub struct DustLaunchInfo {
     pub mask_words_strict: u64,
 }
 
+/// == `SpatialHashEntry` of assets/shaders/headers/layout.playout (scalar layout).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct DustCacheEntry {
+    pub fingerprint: u32,
+    pub radiance: u32,
+    pub last_accessed_frame: u16,
+    pub sample_count: u16,
+}
+
+/// == `SurfelEntry` (vec3 position + u32 direction, 16 bytes; standard.rs:334-346 allocates 720 * 480 of them).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct DustSurfel {
+    pub position: [f32; 3],
+    pub direction: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct DustGiStats {
+    pub near_hits: u64,
+    pub far_hits: u64,
+    pub far_misses: u64,
+    pub cache_found: u64,
+    pub surfels_scheduled: u64,
+    pub surfel_rays: u64,
+    pub cache_inserts: u64,
+    pub insert_segments: u64,
+}
+
 extern "C" {
     pub fn dust_abi_version() -> i32;
     pub fn dust_ctx_create(device: i32, out: *mut *mut DustCtx) -> i32;
@@ -258,4 +290,13 @@ extern "C" {
                          width: u32, height: u32, memory: u32, params: *const DustToneMapParams, dst: *mut c_void) -> i32;
     pub fn dust_get_stats(ctx: *mut DustCtx, out: *mut DustStats) -> i32;
     pub fn dust_get_launch_info(ctx: *mut DustCtx, out: *mut DustLaunchInfo, capacity: u32, n_out: *mut u32) -> i32;
+    pub fn dust_cache_create(ctx: *mut DustCtx, capacity: u32, surfel_pool_size: u32, out: *mut *mut DustRadianceCache) -> i32;
+    pub fn dust_cache_destroy(ctx: *mut DustCtx, cache: *mut DustRadianceCache) -> i32;
+    pub fn dust_cache_clear(ctx: *mut DustCtx, cache: *mut DustRadianceCache) -> i32;
+    pub fn dust_cache_download(ctx: *mut DustCtx, cache: *const DustRadianceCache, entries_out: *mut DustCacheEntry, n_entries: u64,
+                               surfels_out: *mut DustSurfel, n_surfels: u64) -> i32;
+    pub fn dust_cache_upload(ctx: *mut DustCtx, cache: *mut DustRadianceCache, entries: *const DustCacheEntry, n_entries: u64,
+                             surfels: *const DustSurfel, n_surfels: u64) -> i32;
+    pub fn dust_trace_gi(ctx: *mut DustCtx, scene: *const DustScene, cache: *mut DustRadianceCache, camera: *const DustCamera,
+                         sky: *const DustSky, config: *const DustTraceConfig, frame: *const DustFrame, stats_out: *mut DustGiStats) -> i32;
 }

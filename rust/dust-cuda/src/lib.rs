@@ -4,6 +4,8 @@
 //!   CudaVoxGeometry::from_voxels    <- VoxLoader::load_model             crates/vox/src/loader.rs:238-308 (built on the device)
 //!   CudaScene::new / update         <- tlas_system                       crates/render/src/accel_struct/tlas.rs:79-132
 //!   CudaPipeline::render            <- StandardPipeline::render          crates/render/src/pipeline/standard.rs:228-240
+//!   CudaPipeline::render_gi         <- the same call with the reference's own GI (ambient occlusion + final gather + surfel pass
+//!                                      over the world-space radiance cache, standard.rs:334-358, 564-789)
 //! NOT compiled in the build container (no Rust toolchain).  The generic `Tree` / `Pool` accessors are the
 //! ones INTEGRATION.md section 2 asks dust_vdb to make `pub`.
 use dust_cuda_sys as sys;
@@ -105,10 +107,10 @@ pub struct CudaGBuffer { pub width: u32, pub height: u32, pub frame: sys::DustFr
 
 pub struct RenderParams<'a> { pub sunlight: &'a dust_render::Sunlight, pub spp: u32, pub max_bounces: u32, pub rand: u32 }
 
-pub struct CudaPipeline { ctx: Arc<CudaCtx>, frame_index: u32 }
+pub struct CudaPipeline { ctx: Arc<CudaCtx>, frame_index: u32, cache: *mut sys::DustRadianceCache }
 
 impl CudaPipeline {
-    pub fn new(ctx: &Arc<CudaCtx>) -> Self { Self { ctx: ctx.clone(), frame_index: 0 } }
+    pub fn new(ctx: &Arc<CudaCtx>) -> Self { Self { ctx: ctx.clone(), frame_index: 0, cache: std::ptr::null_mut() } }
 
     fn config(&self, g: &CudaGBuffer, p: &RenderParams, flags: u32) -> sys::DustTraceConfig {
         sys::DustTraceConfig { width: g.width, height: g.height, spp: p.spp, max_bounces: p.max_bounces, seed: p.rand,
@@ -128,6 +130,25 @@ impl CudaPipeline {
         Some(())
     }
 
+    /// The reference's own GI for this frame: primary + ambient-occlusion + final-gather + surfel passes over the persistent
+    /// world-space radiance cache (32 Mi entries, 720 x 480 surfels: standard.rs:334-358).
+    pub fn render_gi(&mut self, gbuffer: &mut CudaGBuffer, scene: &CudaScene, params: &RenderParams,
+                     camera: (&dust_render::PinholeProjection, &bevy::transform::components::GlobalTransform)) -> Option<sys::DustGiStats> {
+        if self.cache.is_null() {
+            let rc = unsafe { sys::dust_cache_create(self.ctx.raw, 32 * 1024 * 1024, 720 * 480, &mut self.cache) };
+            if rc != sys::DUST_OK { return None; }
+        }
+        let cam = dust_render::CameraSettings::new(camera.0, camera.1, gbuffer.width, gbuffer.height);
+        let sky = params.sunlight.bake();
+        let cfg = self.config(gbuffer, params, 0);
+        let mut stats = sys::DustGiStats::default();
+        let rc = unsafe { sys::dust_trace_gi(self.ctx.raw, scene.raw, self.cache, &cam as *const _ as *const sys::DustCamera,
+                                             &sky as *const _ as *const sys::DustSky, &cfg, &gbuffer.frame, &mut stats) };
+        if rc != sys::DUST_OK { return None; }
+        self.frame_index += 1;
+        Some(stats)
+    }
+
     /// Frames in flight (crates/rhyolite_bevy/src/lib.rs:58): queue the frame and its download into pinned host memory, get a ticket.
     pub fn render_async(&mut self, host_frame: &sys::DustFrame, width: u32, height: u32, scene: &CudaScene, params: &RenderParams,
                         cam: &sys::DustCamera, sky: &sys::DustSky) -> Result<u64, DustError> {
@@ -139,4 +160,7 @@ impl CudaPipeline {
         Ok(ticket)
     }
     pub fn wait(&self, ticket: u64) -> Result<(), DustError> { self.ctx.check(unsafe { sys::dust_frame_wait(self.ctx.raw, ticket) }) }
+}
+impl Drop for CudaPipeline {
+    fn drop(&mut self) { if !self.cache.is_null() { unsafe { sys::dust_cache_destroy(self.ctx.raw, self.cache); } } }
 }
