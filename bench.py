@@ -16,7 +16,8 @@ The one JSON line carries, beside the contract's keys:
                     of the FULL frame on rank 0
   extra             records of the other BASELINE configs the driver cannot ask for by flag: configs[3] (3840x2160, 2 bounces,
                     8 spp; split over the ranks) and configs[4] (10^8 pcg rays on the 4096^3 synthetic VDB; split over the ranks),
-                    each with value, roofline, e2e, parity
+                    each with value, roofline, e2e, parity; and (N = 1) "gi": one frame of the reference's own GI (radiance cache +
+                    surfels) at the reference's sizes, with its parity against the oracle
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4] [--no-extras]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -696,6 +697,77 @@ def rays_record(env, n_total, steps, warmup, *, cpu=True, e2e=True, clocks=True,
     }
 
 
+def gi_record(env, S, steps, warmup, *, cpu=True):
+    """The reference's own GI at its own sizes: 1920x1080, 1 sample per pixel per frame, radiance cache of
+    32 Mi entries, 720 x 480 surfels (standard.rs:334-358).  A step = one dust_trace_gi frame (primary + ambient-occlusion +
+    final-gather + surfel passes + the deterministic insert) on a warm cache, device-resident illuminance image.  N = 1 only: the
+    cache is one sequentially-consistent table; sharding it is out of scope."""
+    torch = env.torch
+    from dust_b200 import host
+    from dust_b200.pipeline import RadianceCache
+    ctx, scene, sky = S["ctx"], S["scene"], S["sky"]
+    W, H = 1920, 1080
+    CAP, POOL = 32 * 1024 * 1024, 720 * 480
+    cam = host.camera_look_at(width=W, height=H, **S["camkw"])
+    cache = RadianceCache(ctx, CAP, POOL)
+    ctx.use_torch_stream()
+    img = torch.zeros((H, W, 4), dtype=torch.float16, device="cuda")
+    # frame 0 on the fresh cache through the host call: statistics, and the frame the parity check below compares
+    ctx.set_stream(None)
+    first = cache.gi_frame(scene, cam, sky, W, H, seed=SEED, frame_index=0)
+    t0_table, t0_pool = cache.download() if cpu else (None, None)
+    ctx.use_torch_stream()
+    frame_index = 1
+    for _ in range(max(3, warmup) + 4):                              # a few frames until the pool is full and the cache answers
+        cache.gi_frame_device(scene, cam, sky, W, H, img, seed=SEED, frame_index=frame_index); frame_index += 1
+    torch.cuda.synchronize()
+    launches0 = ctx.stats()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        env.flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        cache.gi_frame_device(scene, cam, sky, W, H, img, seed=SEED, frame_index=frame_index); frame_index += 1
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    launches = ctx.stats()["kernel_launches"] - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    ctx.set_stream(None)
+    last = cache.gi_frame(scene, cam, sky, W, H, seed=SEED, frame_index=frame_index)          # statistics of a warm frame
+    st = last["stats"]
+    hit_px = int(np.isfinite(last["gbuffer"]["depth"]).sum())
+    closest = W * H + hit_px + st["far_hits"] + st["far_misses"] + st["surfel_rays"]
+    rec = {"metric": "Mrays/s, one frame of the reference's GI (primary + near + far + surfel rays) on castle.vox", "value": closest / (ms * 1e-3) / 1e6,
+           "unit": "Mrays/s", "ms_per_step": ms, "frames_per_s": 1e3 / ms, "steps": steps, "n_gpus": 1,
+           "config": {"workload": "SURVEY 8f rank 2: StandardPipeline::render's four dispatches, 1920x1080, cache 32 Mi entries, 345 600 surfels",
+                      "scene": S["label"], "rays_counted": "closest-hit rays: primary + ambient-occlusion + final-gather + surfel (sun shadow rays traced, not counted)"},
+           "rays_per_step": closest, "warm_frame_stats": st, "gpu_launches": int(launches),
+           "cache": {"entries_used_after_frame_0": None, "table_bytes": (CAP + 2) * 12, "pool_bytes": POOL * 16}}
+    if cpu:
+        from oracle import pyoracle as po
+        osc = oracle_scene(S["data"])
+        ost = po.GiState(CAP, POOL)
+        t0 = time.perf_counter()
+        o = osc.gi_frame(cam, sky, W, H, ost, seed=SEED, frame_index=0)
+        dt = time.perf_counter() - t0
+        os_ = o["stats"]
+        o_hit = int(np.isfinite(o["gbuffer"]["depth"]).sum())
+        o_closest = W * H + o_hit + os_["far_hits"] + os_["far_misses"] + os_["surfel_rays"]
+        same_img = bool(np.array_equal(first["illuminance"].view(np.uint16), o["illuminance"].view(np.uint16)))
+        same_table = bool(np.array_equal(t0_table.view(np.uint8), ost.table.view(np.uint8)))
+        same_pool = bool(np.array_equal(t0_pool.view(np.uint8), ost.pool.view(np.uint8)))
+        gs = dict(first["stats"]); gs.pop("insert_segments")
+        os2 = dict(os_); os2.pop("insert_segments")
+        rec["cache"]["entries_used_after_frame_0"] = int((t0_table["fingerprint"] != 0).sum())
+        rec["cpu_baseline"] = {"value": o_closest / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": f"frame 0 of the same sequence on a fresh cache, {dt:.1f} s"}
+        rec["parity"] = {"frame": 0, "illuminance_bit_exact": same_img, "cache_table_bit_exact": same_table, "surfel_pool_bit_exact": same_pool,
+                         "stats_equal": gs == os2, "ok": bool(same_img and same_table and same_pool and gs == os2),
+                         "against": "oracle/oracle_gi.c (all 2 073 600 pixels, all 33 554 434 cache entries, all 345 600 surfels compared as bytes)"}
+    cache.close()
+    ctx.use_torch_stream()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -732,8 +804,11 @@ def main():
     extra = {}
     if cfg_id == 2 and not args.no_extras:
         k = max(2, min(args.steps, 5))
-        for name, fn in (("config3", lambda: castle_record(env, S, CONFIGS[3], 3, "strong", k, 3, kernels=False, cpu=cpu, clocks=True, max_cpu_s=8.0)),
-                         ("config4", lambda: rays_record(env, int(args.rays or CONFIGS[4]["rays"]), k, 3, cpu=cpu))):
+        jobs = [("config3", lambda: castle_record(env, S, CONFIGS[3], 3, "strong", k, 3, kernels=False, cpu=cpu, clocks=True, max_cpu_s=8.0)),
+                ("config4", lambda: rays_record(env, int(args.rays or CONFIGS[4]["rays"]), k, 3, cpu=cpu))]
+        if env.world == 1:
+            jobs.append(("gi", lambda: gi_record(env, S, k, 3, cpu=cpu)))
+        for name, fn in jobs:
             try:
                 r = fn()
             except Exception as e:                                  # an extra must not take the headline down with it

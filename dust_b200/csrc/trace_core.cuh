@@ -366,17 +366,25 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
         // the warp votes and executes the ONE operation most lanes wait for (ties to the cheaper one).
         int mode = nc > 0 ? M_NEXT : M_DONE, j = 0;
         for (;;) {
-            // one REDUX of three packed 8-bit counters instead of three ballots + popcounts
-            const uint32_t packed = __reduce_add_sync(full, mode < M_DONE ? (1u << (8 * mode)) : 0u);
-            if (packed == 0u) break;
-            const int n_next = (int)(packed & 255u), n_walk = (int)((packed >> 8) & 255u), n_leaf = (int)(packed >> 16);
-            int op = M_WALK, cnt = n_walk;
-            if (n_next > cnt) { op = M_NEXT; cnt = n_next; }
-            if (n_leaf > cnt) { op = M_LEAF; cnt = n_leaf; }
+            int op = M_WALK, cnt = 0, n_next = 0, n_walk = 0, n_leaf = 0;
+#ifndef DUST_NO_FAST_VOTE_TS
+            // fast path: half of the warp or more waits for WALK — the plurality whatever the others want (one ballot + popc)
+            n_walk = __popc(__ballot_sync(full, mode == M_WALK));
+            cnt = n_walk;
+            if (n_walk < 16)
+#endif
+            {
+                // one REDUX of three packed 8-bit counters instead of three ballots + popcounts
+                const uint32_t packed = __reduce_add_sync(full, mode < M_DONE ? (1u << (8 * mode)) : 0u);
+                if (packed == 0u) break;
+                n_next = (int)(packed & 255u); n_walk = (int)((packed >> 8) & 255u); n_leaf = (int)(packed >> 16);
+                cnt = n_walk;
+                if (n_next > cnt) { op = M_NEXT; cnt = n_next; }
+                if (n_leaf > cnt) { op = M_LEAF; cnt = n_leaf; }
+            }
             if (STATS && (threadIdx.x & 31u) == 0) {
                 st.dbg[op == M_WALK ? 0 : (op == M_LEAF ? 1 : 2)]++;
                 st.dbg[op == M_WALK ? 3 : (op == M_LEAF ? 4 : 5)] += cnt;
-                st.dbg[6] += 32 - n_walk - n_leaf - n_next;
             }
             if (op == M_WALK) {
 #pragma unroll 1
