@@ -104,7 +104,21 @@ def case_post(oracle):
             "hit_depth": g["depth"].view(np.uint32), "hit_histogram": bins, "adapted_luminance": np.float32(avg).reshape(1), "ldr": ldr}
 
 
-CASES = {"two_models_primary": case_primary, "two_models_gi": case_gi, "sky_bake": case_sky, "two_models_rays": case_rays,
+def case_gi_cache(oracle):
+    """Three frames of the reference's own GI (ambient-occlusion / final-gather / surfel passes over the radiance cache, oracle_gi.c) on a
+    small cache: keys, sample counts and LRU stamps of the table, the surfel pool and the last frame's illuminance image."""
+    s = _built(oracle)
+    W, H = 48, 40
+    st = oracle.GiState(4096, 512)
+    cam, sky = _camera(s, W, H), s.host.sunlight_bake()
+    for f in range(3):
+        r = s.oscene.gi_frame(cam, sky, W, H, st, seed=31, frame_index=f)
+    return {"illuminance": r["illuminance"].view(np.uint16), "hit_cache_fingerprint": st.table["fingerprint"].copy(),
+            "hit_cache_sample_count": st.table["sample_count"].copy(), "hit_cache_frame": st.table["last_accessed_frame"].copy(),
+            "hit_pool_direction": st.pool["direction"].copy(), "hit_gi_stats": np.array([r["stats"][k] for k in sorted(r["stats"])], np.uint64)}
+
+
+CASES = {"two_models_gi_cache": case_gi_cache, "two_models_primary": case_primary, "two_models_gi": case_gi, "sky_bake": case_sky, "two_models_rays": case_rays,
          "two_models_post": case_post}
 
 

@@ -379,6 +379,20 @@ def test_cuda_matches_committed_golden_fixtures(oracle, host, ctx):
     ldr = ex.tone_map(wp["illuminance"].view(np.float16), wp["hit_albedo"], W, H, np.empty((H, W, 4), np.float32))
     assert np.abs(ldr - wp["ldr"]).max() <= 1e-4
     ex.close()
+    # the reference's own GI: three frames over a small radiance cache
+    from dust_b200.pipeline import RadianceCache
+    wc = want["two_models_gi_cache"]
+    cache = RadianceCache(ctx, 4096, 512)
+    W, H = 48, 40
+    for f in range(3):
+        g = cache.gi_frame(loaded.scene, make_golden._camera(s, W, H), host.sunlight_bake(), W, H, seed=31, frame_index=f)
+    t, p = cache.download()
+    assert np.array_equal(t["fingerprint"], wc["hit_cache_fingerprint"]) and np.array_equal(t["sample_count"], wc["hit_cache_sample_count"])
+    assert np.array_equal(t["last_accessed_frame"], wc["hit_cache_frame"]) and np.array_equal(p["direction"], wc["hit_pool_direction"])
+    a, b = g["illuminance"].astype(np.float32), wc["illuminance"].view(np.float16).astype(np.float32)
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin) and np.allclose(a[fin], b[fin], rtol=1.5e-3, atol=1e-6)
+    cache.close()
 
 
 def test_launch_info_timing_and_counter_deltas(castle_small, host):

@@ -1,0 +1,27 @@
+#!/bin/bash
+# round 2 profiling call: launch lists, DRAM traffic, ncu --set full of the dominant kernel, sanitizer logs
+mkdir -p gpurun_out
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_v9_launches.csv $B > gpurun_out/r02_ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:wf_trace_pt -s 2 -c 1 -o gpurun_out/r02_v9_trace_pt $B > gpurun_out/r02_ncu_full.log 2>&1
+cat > /tmp/gi_prof.py <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import bench
+from dust_b200 import host
+from dust_b200.pipeline import RadianceCache
+class A: gpus=1
+env = bench.Env(A)
+S = bench.load_castle(env)
+cam = host.camera_look_at(width=1920, height=1080, **S["camkw"])
+cache = RadianceCache(S["ctx"], 32*1024*1024, 720*480)
+img = torch.zeros((1080,1920,4), dtype=torch.float16, device="cuda")
+for f in range(6):
+    cache.gi_frame_device(S["scene"], cam, S["sky"], 1920, 1080, img, seed=2, frame_index=f)
+torch.cuda.synchronize()
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_gi_launches.csv python /tmp/gi_prof.py > gpurun_out/r02_ncu_gi.log 2>&1
+SEL="castle_small_gi or gi_frames_bit_exact or ray_batch_small_domain or frames_in_flight or ray_batch_many_instances or teapot_bounces"
+timeout 900 compute-sanitizer --tool memcheck --log-file gpurun_out/r02_memcheck.log python -m pytest tests/test_gpu_parity.py tests/test_gi.py -m gpu -x -q -k "$SEL" > gpurun_out/r02_memcheck_pytest.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/r02_racecheck.log python -m pytest tests/test_gpu_parity.py tests/test_gi.py -m gpu -x -q -k "castle_small_gi or gi_frames_bit_exact or ray_batch_many_instances" > gpurun_out/r02_racecheck_pytest.log 2>&1
+tail -3 gpurun_out/r02_memcheck.log gpurun_out/r02_racecheck.log gpurun_out/r02_memcheck_pytest.log gpurun_out/r02_racecheck_pytest.log
