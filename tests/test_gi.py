@@ -154,3 +154,36 @@ def test_gi_device_frame_and_errors(ctx, gi_scene):
     with pytest.raises(DustError):
         RadianceCache(ctx, 0, 16)
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_gi_mixed_levels_small_frame_large_pool(oracle, ctx, host):
+    """A 4-level tree (hierarchy!(4,4,2,2)) next to a sheared 3-level instance (the NL = 0 kernel instantiations), a frame with fewer
+    pixels than pool slots, three frames bit for bit; then the 4-level tree alone (NL = 4) and an empty scene."""
+    from dust_b200.pipeline import RadianceCache, Scene
+    dom = host.SynthDomain(seed=7, fill=0.03, domain_leaves=128)
+    otree = oracle.TreeView(dom.describe())
+    dtree = ctx.upload_tree(dom.describe())
+    tea = BuiltScene(scenes.teapot_like(), oracle, ctx)
+    tea_tree = next(iter(tea.loaded.trees.values()))
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    sheared = np.array([1.5, 0.25, 0, 200, 0, 1, 0.125, 330, 0.0625, 0, 1, 150], np.float32)
+    om = tea.omodels[0]
+    W, H = 40, 30
+    cam = host.camera_look_at((700.0, 620.0, 760.0), (256.0, 256.0, 256.0), width=W, height=H)
+    sky = host.sunlight_bake()
+    for insts_o, insts_d in (([(ident, otree._h, dom.materials, dom.palette), (sheared, om.tree._h, om.materials, tea.ovox.palette)],
+                              [(ident, dtree), (sheared, tea_tree)]),
+                             ([(ident, otree._h, dom.materials, dom.palette)], [(ident, dtree)]),
+                             ([], [])):
+        osc, dsc = oracle.Scene(insts_o), Scene(ctx, insts_d)
+        cache, ost = RadianceCache(ctx, 1 << 13, 4096), oracle.GiState(1 << 13, 4096)          # 1200 pixels, 4096 pool slots
+        for f in range(3):
+            g = cache.gi_frame(dsc, cam, sky, W, H, seed=5, frame_index=f)
+            o = osc.gi_frame(cam, sky, W, H, ost, seed=5, frame_index=f)
+            assert np.array_equal(g["illuminance"].view(np.uint16), o["illuminance"].view(np.uint16)), (len(insts_d), f)
+            t, p = cache.download()
+            assert np.array_equal(t.view(np.uint8), ost.table.view(np.uint8)) and np.array_equal(p.view(np.uint8), ost.pool.view(np.uint8)), (len(insts_d), f)
+        if insts_d:
+            assert g["stats"]["far_hits"] + g["stats"]["near_hits"] > 0
+        cache.close()
