@@ -2,7 +2,8 @@
 //   Sunlight::bake                 crates/render/src/pipeline/sky.rs:90-268
 //   PinholeProjection              crates/render/src/projection.rs:3-29
 //   CameraSettings construction    crates/render/src/pipeline/standard.rs:277-302
-//   StandardPipeline::render       crates/render/src/pipeline/standard.rs:228-240  -> CudaPipeline::render
+//   StandardPipeline::render       crates/render/src/pipeline/standard.rs:228-240  -> CudaPipeline::render (path-traced bounces) /
+//                                                                                      CudaPipeline::render_gi (the reference's own radiance-cache GI)
 #pragma once
 #include "../../../include/dust_b200.h"
 #include "hosek_wilkie_xyz_tables.h"
@@ -211,11 +212,34 @@ public:
         if (last_status_ == DUST_OK) ++frame_index_;                      // standard.rs:252
         return last_status_ == DUST_OK;
     }
+    // The same frame with the reference's own GI (the ambient-occlusion, final-gather and surfel dispatches of StandardPipeline::render,
+    // standard.rs:564-789).  The pipeline owns the persistent state — spatial_hash_buffer (32 Mi entries) and surfel_pool_buffer
+    // (720 x 480) — for its lifetime, the way use_shared_state keeps them across frames (standard.rs:334-358).  `gbuffer.radiance`
+    // receives img_illuminance (DUST_FMT_YCOCG16F), `gbuffer.gbuffer` the primary-hit images.
+    bool render_gi(const DustFrame &gbuffer, uint32_t width, uint32_t height, const DustScene *scene, const RenderParams &params,
+                   const PinholeProjection &projection, const CameraTransform &camera, DustGiStats *stats = nullptr,
+                   uint32_t cache_capacity = 32u * 1024u * 1024u, uint32_t surfel_pool_size = 720u * 480u)
+    {
+        if (!cache_) {
+            last_status_ = dust_cache_create(ctx_, cache_capacity, surfel_pool_size, &cache_);
+            if (last_status_ != DUST_OK) return false;
+        }
+        const DustCamera cam = camera_settings(projection, camera, width, height);
+        const DustSky sky = params.sunlight.bake();
+        DustTraceConfig cfg{ width, height, 1, 0, params.rand, params.frame_index, 0, 1, 0 };
+        last_status_ = dust_trace_gi(ctx_, scene, cache_, &cam, &sky, &cfg, &gbuffer, stats);
+        if (last_status_ == DUST_OK) ++frame_index_;
+        return last_status_ == DUST_OK;
+    }
+    ~CudaPipeline() { if (cache_) dust_cache_destroy(ctx_, cache_); }
+    CudaPipeline(const CudaPipeline &) = delete;
+    CudaPipeline &operator=(const CudaPipeline &) = delete;
     int32_t last_status() const { return last_status_; }
     uint32_t frames_rendered() const { return frame_index_; }
 
 private:
     DustCtx *ctx_;
+    DustRadianceCache *cache_ = nullptr;
     int32_t last_status_ = DUST_OK;
     uint32_t frame_index_ = 0;
 };

@@ -6,7 +6,7 @@
 //   StandardPipeline::render   (crates/render/src/pipeline/standard.rs:228-240)  CudaPipeline::render
 //   AutoExposurePipeline / ToneMappingPipeline (examples/castle.rs:200-222)      the two post passes
 //
-//   castle <scene.vox> <out-prefix> [frames] [width] [height] [--device-build]
+//   castle <scene.vox> <out-prefix> [frames] [width] [height] [--device-build] [--gi]
 //
 // Every frame one instance (the first one, standing in for castle.rs's moving teapot, :287-292) is translated, the
 // frame is traced demodulated into the img_illuminance encoding with a G-buffer, exposure adapts, the tone-mapped
@@ -36,11 +36,15 @@ using namespace dust;
 
 int main(int argc, char **argv)
 {
-    if (argc < 3) { std::fprintf(stderr, "usage: castle <scene.vox> <out-prefix> [frames] [width] [height] [--device-build]\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: castle <scene.vox> <out-prefix> [frames] [width] [height] [--device-build] [--gi]\n"); return 2; }
     const uint32_t frames = argc > 3 ? (uint32_t)std::atoi(argv[3]) : 3, W = argc > 4 ? (uint32_t)std::atoi(argv[4]) : 320,
                    H = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 180;
     bool device_build = false, verbose = false;
-    for (int i = 3; i < argc; i++) { device_build |= std::strcmp(argv[i], "--device-build") == 0; verbose |= std::strcmp(argv[i], "--verbose") == 0; }
+    bool gi = false;                                                        // --gi: the reference's own GI (radiance cache + surfels) instead of path-traced bounces
+    for (int i = 3; i < argc; i++) {
+        device_build |= std::strcmp(argv[i], "--device-build") == 0; verbose |= std::strcmp(argv[i], "--verbose") == 0;
+        gi |= std::strcmp(argv[i], "--gi") == 0;
+    }
     auto note = [&](const char *what) { if (verbose) std::fprintf(stderr, "[castle] %s\n", what); };
 
     std::ifstream in(argv[1], std::ios::binary);
@@ -112,7 +116,13 @@ int main(int argc, char **argv)
         }
         note("frame");
         params.rand = f * 7919u; params.frame_index = f;
-        if (!pipeline.render(frame, W, H, scene, params, projection, camera)) { std::fprintf(stderr, "render: %s\n", dust_last_error_string(ctx)); return 1; }
+        DustGiStats gs{};
+        const bool ok = gi ? pipeline.render_gi(frame, W, H, scene, params, projection, camera, &gs, 1u << 20, 16384u)
+                           : pipeline.render(frame, W, H, scene, params, projection, camera);
+        if (!ok) { std::fprintf(stderr, "render: %s\n", dust_last_error_string(ctx)); return 1; }
+        if (gi) std::printf("gi frame %u: near %llu far %llu miss %llu cache hits %llu inserts %llu surfels %llu\n", f, (unsigned long long)gs.near_hits,
+                            (unsigned long long)gs.far_hits, (unsigned long long)gs.far_misses, (unsigned long long)gs.cache_found,
+                            (unsigned long long)gs.cache_inserts, (unsigned long long)gs.surfel_rays);
         DustExposure *buffer = exposure.render(d_illum, W, H, exposure_settings);
         if (!buffer) { std::fprintf(stderr, "auto exposure: %s\n", dust_last_error_string(ctx)); return 1; }
         if (!tone_map.render(d_illum, static_cast<const uint32_t *>(d_albedo), d_ldr, DUST_FMT_RGBA32F, W, H, buffer)) {

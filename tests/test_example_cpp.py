@@ -69,3 +69,17 @@ def test_example_frames(tmp_path, ctx, host):
     want = (np.clip(ldr[..., :3], 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
     assert np.array_equal(want, outs["host"][0])
     ex.close()
+    # --gi: the same loop with the reference's own GI; frames equal the ctypes path (same cache sizes, seeds and frame indices)
+    from dust_b200.pipeline import RadianceCache
+    prefix = str(tmp_path / "gi")
+    r = subprocess.run([EXE, scene_file, prefix, "2", str(W), str(H), "--gi"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("gi frame") == 2 and "cache hits 0" not in r.stdout.splitlines()[-2]
+    cache = RadianceCache(ctx, 1 << 20, 16384)
+    g = cache.gi_frame(loaded.scene, cam, sky, W, H, seed=0, frame_index=0)
+    ex = Exposure(ctx)
+    ex.update(g["illuminance"], W, H)
+    ldr = ex.tone_map(g["illuminance"], g["gbuffer"]["albedo"], W, H, np.empty((H, W, 4), np.float32))
+    want = (np.clip(ldr[..., :3], 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    assert np.array_equal(want, _read_ppm(f"{prefix}_0.ppm"))
+    ex.close(); cache.close()
