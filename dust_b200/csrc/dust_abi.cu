@@ -405,7 +405,14 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         qs[q]->a = reinterpret_cast<float4 *>(base + o_q[q][0]); qs[q]->b = reinterpret_cast<float4 *>(base + o_q[q][1]);
         qs[q]->path = reinterpret_cast<uint32_t *>(base + o_q[q][2]);
         qs[q]->stride = 1;
+        qs[q]->kind = 0; qs[q]->utmin = 0.1f; qs[q]->ub = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+#ifndef DUST_TMA_QUEUE
+    // compact records: the path word rides in the origin's fourth lane; tmin (0.1: ambient_occlusion.rgen:44, final_gather.rgen:47) is a uniform of
+    // the queue, and so are the direction and tmax of the sun shadow rays.  (The TMA staging experiment keeps the separate arrays it copies.)
+    p.qc.kind = 2; p.qn.kind = 2;
+    p.qs.kind = 1; p.qs.ub = make_float4(fp.sun_dir[0], fp.sun_dir[1], fp.sun_dir[2], 10000.0f);
+#endif
     const WfQueue q_even = p.qc, q_odd = p.qn;                         // closest queues of even / odd depths
     p.hits = reinterpret_cast<uint4 *>(base + o_hits); p.acc = reinterpret_cast<float4 *>(base + o_acc);
     p.vis = base + o_vis;
@@ -435,9 +442,16 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
             const uint32_t pgrid = std::min<uint32_t>(grid, (uint32_t)(ctx->sms * std::max(pt_blocks, 1)));
             kernel<<<pgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, count, work + slot, ovf_counts + slot);
         };
-        if (nl == 3) { if (stats) launch(wf_trace_pt<3, true, true>); else launch(wf_trace_pt<3, false, true>); }
-        else if (nl == 4) { if (stats) launch(wf_trace_pt<4, true, true>); else launch(wf_trace_pt<4, false, true>); }
-        else { if (stats) launch(wf_trace_pt<0, true, true>); else launch(wf_trace_pt<0, false, true>); }
+#define DUST_PT_BY_KIND(NL_, STATS_)                                                                                         \
+        do {                                                                                                                 \
+            if (q.kind == 2u) launch(wf_trace_pt<NL_, STATS_, true, false, 2>);                                              \
+            else if (q.kind == 1u) launch(wf_trace_pt<NL_, STATS_, true, false, 1>);                                         \
+            else launch(wf_trace_pt<NL_, STATS_, true, false, 0>);                                                           \
+        } while (0)
+        if (nl == 3) { if (stats) DUST_PT_BY_KIND(3, true); else DUST_PT_BY_KIND(3, false); }
+        else if (nl == 4) { if (stats) DUST_PT_BY_KIND(4, true); else DUST_PT_BY_KIND(4, false); }
+        else { if (stats) DUST_PT_BY_KIND(0, true); else DUST_PT_BY_KIND(0, false); }
+#undef DUST_PT_BY_KIND
         count_launch(ctx, "wf_trace_pt");
         // rays that wf_cull could not pre-cull: one warp per ray, persistent grid (the list length lives on the device)
         const uint32_t sgrid = std::min<uint32_t>(grid, (uint32_t)ctx->sms * 8u);
@@ -461,7 +475,8 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         for (uint32_t depth = 0; depth <= cfg.max_bounces; depth++) {
             p.depth = depth;
             p.qc = depth & 1 ? q_odd : q_even; p.qn = depth & 1 ? q_even : q_odd;
-            if (depth == 0 && implicit0) { p.qc.a = nullptr; p.qc.b = nullptr; p.qc.path = nullptr; p.qc.stride = 0; }
+            p.qc.utmin = depth == 0 ? fp.cam.near : 0.1f;                  // (a materialised depth-0 queue holds camera rays: tmin = near)
+            if (depth == 0 && implicit0) { p.qc.a = nullptr; p.qc.b = nullptr; p.qc.path = nullptr; p.qc.stride = 0; p.qc.kind = 0; }
             // queue sizes live on the device: launch for the largest possible queue, surplus CTAs exit at once
             const uint32_t *n_closest = depth ? p.counts + 4 * (depth - 1) + 2 : (implicit0 ? nullptr : p.counts + 3);
             if (depth == 0 && implicit0 && fuse0) {
@@ -1180,7 +1195,7 @@ static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const 
     p.f.counters = ctx->d_counters;
     p.n_paths = cn;
     p.hits_out = d_hits;
-    WfQueue q;
+    WfQueue q{};
     q.a = reinterpret_cast<float4 *>(const_cast<DustRay *>(d_rays)); q.b = q.a + 1; q.path = nullptr; q.stride = 2;
     const uint32_t grid = (cn + DUST_THREADS - 1) / DUST_THREADS;
     uint32_t *ovf_count = counters;

@@ -35,7 +35,31 @@ struct WfQueue {
     uint32_t *path;     // path index; bit 31: any-hit (shadow) ray.  NULL: closest-hit rays, path = i (ray batches)
     uint32_t stride;    // 1: separate arrays; 2: interleaved DustRay records (a = rays, b = rays + 1);
                         // 0: no arrays at all — slot i is the camera ray of path i (wf_primary_ray), the depth-0 queue of a frame
+    // Compact records of the frame's own queues (everything a consumer can know from the launch is not stored per ray):
+    //   kind 0  as described by `stride`
+    //   kind 1  any-hit (sun shadow) rays: a[i] = (origin, path word); direction and tmax are the uniform `ub`, tmin is `utmin` — 16 bytes per ray
+    //   kind 2  closest-hit (bounce) rays: a[i] = (origin, path word), b[i] = (direction, tmax); tmin is `utmin`        — 32 bytes per ray
+    // (36 bytes each before: 0.6 GB less DRAM traffic per configs[2] frame, profiles/r02_history.md)
+    uint32_t kind;
+    float utmin;
+    float4 ub;
 };
+
+// ray i of a queue: origin + tmin, direction + tmax, path word (bit 31: any-hit ray).  KIND >= 0: the queue's kind is known at compile time.
+template <int KIND = -1>
+__device__ __forceinline__ void wf_fetch(const WfQueue &q, uint32_t i, float4 &a, float4 &b, uint32_t &pw)
+{
+    const uint32_t kind = KIND >= 0 ? (uint32_t)KIND : q.kind;
+    if (kind == 0u) {
+        a = __ldg(&q.a[(size_t)i * q.stride]); b = __ldg(&q.b[(size_t)i * q.stride]);
+        pw = q.path ? __ldg(&q.path[i]) : i;
+        return;
+    }
+    const float4 r = __ldg(&q.a[i]);
+    pw = __float_as_uint(r.w);
+    a = make_float4(r.x, r.y, r.z, q.utmin);
+    if (kind == 1u) b = q.ub; else b = __ldg(&q.b[i]);
+}
 
 struct WfParams {
     FrameParams f;
@@ -108,7 +132,9 @@ __global__ void __launch_bounds__(256) wf_gen_primary(const __grid_constant__ Wf
     float4 a, b;
     uint32_t s1, smp, px, py, oi;
     wf_primary_ray(p, i, a, b, s1, smp, px, py, oi);
-    p.qc.a[i] = a; p.qc.b[i] = b; p.qc.path[i] = i;
+    p.qc.b[i] = b;
+    if (p.qc.kind == 2u) p.qc.a[i] = make_float4(a.x, a.y, a.z, __uint_as_float(i));     // compact closest queue (utmin = camera near)
+    else { p.qc.a[i] = a; p.qc.path[i] = i; }
     if (i == 0) p.counts[3] = p.n_paths;                               // size of the depth-0 closest queue, for kernels that read it from memory
 }
 
@@ -141,7 +167,7 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
     uint32_t pw = 0;
     if (live) {
         if (q.stride == 0u) { uint32_t s1, smp, px, py, oi; wf_primary_ray(p, i, a, b, s1, smp, px, py, oi); pw = i; }
-        else { a = __ldg(&q.a[(size_t)i * q.stride]); b = __ldg(&q.b[(size_t)i * q.stride]); pw = q.path ? __ldg(&q.path[i]) : i; }
+        else wf_fetch(q, i, a, b, pw);
     }
     Counters st = {};
     Hit h;
@@ -181,7 +207,9 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
     Counters st = {};
     bool over = false;
     if (i < n) {
-        const float4 a = __ldg(&q.a[(size_t)i * q.stride]), b = __ldg(&q.b[(size_t)i * q.stride]);
+        float4 a, b;
+        uint32_t pw_unused;
+        wf_fetch(q, i, a, b, pw_unused);
         const f3 ro = mk3(a.x, a.y, a.z), rd = mk3(b.x, b.y, b.z);
         const float tmin = a.w, tmax = b.w;
         const f3 winv = cull_inverse(rd);
@@ -234,8 +262,9 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
     Counters st = {};
     for (uint32_t k = blockIdx.x * (DUST_THREADS / 32u) + (threadIdx.x >> 5); k < n; k += warps) {
         const uint32_t i = __ldg(&list[k]);
-        const float4 a = __ldg(&q.a[(size_t)i * q.stride]), b = __ldg(&q.b[(size_t)i * q.stride]);
-        const uint32_t pw = q.path ? __ldg(&q.path[i]) : i;
+        float4 a, b;
+        uint32_t pw;
+        wf_fetch(q, i, a, b, pw);
         const f3 ro = mk3(a.x, a.y, a.z), rd = mk3(b.x, b.y, b.z);
         const float tmin = a.w, tmax = b.w;
         const bool any = (pw >> 31) != 0u;
@@ -350,7 +379,7 @@ __device__ __forceinline__ void wf_stage_refill(const WfParams &p, const WfQueue
 
 // CAND: the queue comes with pre-culled candidate records (p.cand, multi-instance scenes); without them the only candidate is the
 // scene box and the truncated-list logic compiles away.
-template <int NL, bool STATS, bool CAND, bool ROUGH = false>
+template <int NL, bool STATS, bool CAND, bool ROUGH = false, int KIND = 0>     // KIND: WfQueue::kind of the queue (compile-time: the claim is hot)
 __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : DUST_PT_MIN_BLOCKS4) wf_trace_pt(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, unsigned long long *work,
                                                                                                                   uint32_t *overflow_count)
 {
@@ -570,7 +599,9 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                     if (idx >= n) mode = W_DEAD;
                     else {
                         ri = (uint32_t)idx;
-                        const float4 a = __ldg(&q.a[(size_t)ri * q.stride]), b = __ldg(&q.b[(size_t)ri * q.stride]);
+                        float4 a, b;
+                        uint32_t pw_new;
+                        wf_fetch<KIND>(q, ri, a, b, pw_new);
                         uint4 c0, cv[WF_CVECS];
 #pragma unroll
                         for (int v = 0; v < WF_CVECS; v++) cv[v] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -589,7 +620,7 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
                             cv[0] = c0;
                         }
                         if (c0.x != 0xFFFFFFFEu) {                                     // else: overflow ray, wf_trace does it
-                            pw = q.path ? __ldg(&q.path[ri]) : ri;
+                            pw = pw_new;
                             ro = mk3(a.x, a.y, a.z); tmin = a.w; rd = mk3(b.x, b.y, b.z); cur = b.w;
 #pragma unroll
                             for (int v = 0; v < WF_CVECS; v++) {
@@ -635,8 +666,7 @@ __device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_
             path = i;
             valid = wf_primary_ray(p, i, a, b, s1, smp, px, py, oi);
         } else {
-            path = __ldg(&p.qc.path[i]);
-            a = __ldg(&p.qc.a[i]); b = __ldg(&p.qc.b[i]);
+            wf_fetch(p.qc, i, a, b, path);
             if (p.depth == 0) { float4 a2, b2; valid = wf_primary_ray(p, path, a2, b2, s1, smp, px, py, oi); }
             else {
                 const float4 s0 = p.ps0[path], s1v = p.ps1[path];
@@ -709,9 +739,12 @@ __device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_
             base = __shfl_sync(full, base, __ffs(m) - 1);
             if (emit_shadow) {
                 const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
-                p.qs.b[k] = make_float4(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2], 10000.0f);
-                p.qs.path[k] = path | 0x80000000u;
+                if (p.qs.kind == 1u) p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(path | 0x80000000u));   // direction, tmin, tmax: uniforms of the queue
+                else {
+                    p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
+                    p.qs.b[k] = make_float4(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2], 10000.0f);
+                    p.qs.path[k] = path | 0x80000000u;
+                }
             }
         }
     }
@@ -723,9 +756,9 @@ __device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_
             base = __shfl_sync(full, base, __ffs(m) - 1);
             if (emit_bounce) {
                 const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
                 p.qn.b[k] = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
-                p.qn.path[k] = path;
+                if (p.qn.kind == 2u) p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(path));                 // tmin: uniform of the queue
+                else { p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f); p.qn.path[k] = path; }
             }
         }
     }
