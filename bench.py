@@ -194,7 +194,7 @@ def reference_arm(args, cfg, cfg_id):
         "config": workload_config(cfg, cfg_id, label, args.gpus, spp, "weak"),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU port of the reference semantics (oracle/: scalar C, instances tested linearly behind a box early-out); "
+        "note": "CPU port of the reference semantics (oracle/: scalar C, instances visited front to back by box entry time); "
                 "the reference's own Vulkan-RT path cannot run here",
     }
     print(json.dumps(line), flush=True)
@@ -532,7 +532,7 @@ def castle_record(env, S, cfg, cfg_id, scaling, steps, warmup, *, kernels=True, 
         r, dt, o = run_cpu_rows(osc, cam, sky, cfg, rows, spp, hits=True)
         cpu_rec = {"value": r / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                    "sample": f"{n_rows} of {H} rows (evenly spread) of the same frame, {spp} spp, {dt:.1f} s",
-                   "note": "scalar C port, instances tested linearly behind a box early-out: a checker first, a baseline second"}
+                   "note": "scalar C port, instances visited front to back by box entry time (no SIMD): a checker first, a baseline second"}
         ctx.set_stream(None)
         g = scene.trace(cam, sky, W, H, spp=spp, max_bounces=cfg["max_bounces"], seed=SEED, hits=True)
         ctx.use_torch_stream()

@@ -456,7 +456,22 @@ static void record_ray(const OScene *s, const float o[3], const float d[3], floa
     else { h->t = INFINITY; h->instance = O_MISS; h->leaf = O_MISS; h->voxel |= 0xFFu; }
 }
 
-/* Closest hit over all instances: lexicographic minimum of (t, instance index). */
+/* entry time of the ray into a padded box within [tmin, tmax], or +inf (conservative like box_may_hit) */
+static float box_entry_time(const float *b, const float o[3], const float inv[3], float tmin, float tmax)
+{
+    float t0 = tmin, t1 = tmax;
+    for (int a = 0; a < 3; a++) {
+        float ta = (b[a] - o[a]) * inv[a], tb = (b[3 + a] - o[a]) * inv[a];
+        t0 = fmaxf(t0, fminf(ta, tb));
+        t1 = fminf(t1, fmaxf(ta, tb));
+    }
+    return t0 <= t1 ? t0 : INFINITY;
+}
+
+/* Closest hit over all instances: lexicographic minimum of (t, instance index) — an order-independent minimum, so the instances may be
+ * visited in any order.  With culling on they are visited FRONT TO BACK by box entry time and the loop ends at the first box that starts
+ * behind the best hit (a plain speed-up of the CPU baseline: the boxes only cull, tests check cull on == off and order independence). */
+#define O_SORT_MAX 256
 static void trace_closest(const OScene *s, const float o[3], const float d[3], float tmin, float tmax,
                           SceneHit *best, OStats *st)
 {
@@ -464,11 +479,31 @@ static void trace_closest(const OScene *s, const float o[3], const float d[3], f
     float cur = tmax;
     float inv[3];
     cull_inv(d, inv);
-    for (uint32_t k = 0; k < s->n; k++) {
-        InstHit ih;
-        if (s->cull && !box_may_hit(s->boxes + 6 * k, o, inv, tmin, cur)) continue;
-        if (trace_instance(&s->inst[k], o, d, tmin, cur, &ih, st)) {
-            if (!best->hit || ih.t < best->ih.t) { best->hit = 1; best->instance = k; best->ih = ih; cur = ih.t; }
+    if (s->cull && s->n <= O_SORT_MAX) {
+        float te[O_SORT_MAX];
+        uint32_t id[O_SORT_MAX], m = 0;
+        for (uint32_t k = 0; k < s->n; k++) {
+            float t = box_entry_time(s->boxes + 6 * k, o, inv, tmin, tmax);
+            if (t == INFINITY) continue;
+            uint32_t j = m++;
+            while (j > 0 && te[j - 1] > t) { te[j] = te[j - 1]; id[j] = id[j - 1]; j--; }      /* stable: equal times stay in index order */
+            te[j] = t; id[j] = k;
+        }
+        for (uint32_t j = 0; j < m; j++) {
+            if (te[j] > cur) break;                                    /* every remaining box starts behind the best hit */
+            InstHit ih;
+            uint32_t k = id[j];
+            if (trace_instance(&s->inst[k], o, d, tmin, cur, &ih, st)) {
+                if (!best->hit || ih.t < best->ih.t || (ih.t == best->ih.t && k < best->instance)) { best->hit = 1; best->instance = k; best->ih = ih; cur = ih.t; }
+            }
+        }
+    } else {
+        for (uint32_t k = 0; k < s->n; k++) {
+            InstHit ih;
+            if (s->cull && !box_may_hit(s->boxes + 6 * k, o, inv, tmin, cur)) continue;
+            if (trace_instance(&s->inst[k], o, d, tmin, cur, &ih, st)) {
+                if (!best->hit || ih.t < best->ih.t) { best->hit = 1; best->instance = k; best->ih = ih; cur = ih.t; }
+            }
         }
     }
     record_ray(s, o, d, tmin, tmax, 0, best->hit, best->instance, &best->ih);
@@ -479,6 +514,23 @@ static int trace_any(const OScene *s, const float o[3], const float d[3], float 
 {
     float inv[3];
     cull_inv(d, inv);
+    if (s->cull && s->n <= O_SORT_MAX) {                               /* nearest boxes first: an occluder is found sooner; the answer (any hit?) is the same */
+        float te[O_SORT_MAX];
+        uint32_t id[O_SORT_MAX], m = 0;
+        for (uint32_t k = 0; k < s->n; k++) {
+            float t = box_entry_time(s->boxes + 6 * k, o, inv, tmin, tmax);
+            if (t == INFINITY) continue;
+            uint32_t j = m++;
+            while (j > 0 && te[j - 1] > t) { te[j] = te[j - 1]; id[j] = id[j - 1]; j--; }
+            te[j] = t; id[j] = k;
+        }
+        for (uint32_t j = 0; j < m; j++) {
+            InstHit ih;
+            if (trace_instance(&s->inst[id[j]], o, d, tmin, tmax, &ih, st)) { record_ray(s, o, d, tmin, tmax, 1, 1, id[j], &ih); return 1; }
+        }
+        record_ray(s, o, d, tmin, tmax, 1, 0, O_MISS, NULL);
+        return 0;
+    }
     for (uint32_t k = 0; k < s->n; k++) {
         InstHit ih;
         if (s->cull && !box_may_hit(s->boxes + 6 * k, o, inv, tmin, tmax)) continue;
