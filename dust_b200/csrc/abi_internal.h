@@ -24,6 +24,8 @@ struct DustCtx {
     void *wf_scratch = nullptr;
     size_t wf_scratch_bytes = 0;
     uint32_t *d_wf_counters = nullptr;
+    uint32_t *d_tile_lists = nullptr;        // per local tile: candidate instances of its camera frustum (wf_tile_cull)
+    size_t tile_lists_words = 0;
     int sms = 148;
     DustStats stats{};
     // DUST_TRACE_TIMING: one event after every launch of the last dust_trace call (+ a counter snapshot with DUST_TRACE_STATS)
@@ -68,6 +70,7 @@ struct DustExposure {
 struct DustScene {
     DInstance *d_inst = nullptr;
     DBvhNode *d_bvh = nullptr;
+    float4 *d_boxes = nullptr;       // padded world boxes, 2 float4 per instance
     float4 *d_prev = nullptr;        // last frame's object -> world rows (3 per instance)
     DSceneView view{};               // device pointers + root box, passed to the kernels by value
     uint32_t n_inst = 0, n_bvh = 0, max_levels = 3, min_levels = 3;

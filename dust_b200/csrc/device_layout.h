@@ -64,6 +64,7 @@ struct DSceneView {
     const DInstance *inst;
     const DBvhNode *bvh;           // n_inst - 1 inner nodes (none for 0 / 1 instances)
     const float4 *prev_o2w;        // 3 rows per instance: last frame's object -> world (G-buffer motion)
+    const float4 *inst_boxes;      // 2 per instance: padded world box lo.xyz, hi.xyz (the boxes the BVH is built over; per-tile candidate lists test them directly)
     float root_lo[3], root_hi[3];  // padded world box of the whole scene
     int32_t root_ref;              // >= 0 inner node, < 0 instance ~root_ref
     uint32_t n_inst;

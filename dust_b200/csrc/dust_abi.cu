@@ -585,6 +585,7 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
     if (ctx->d_wf_counters) cudaFree(ctx->d_wf_counters);
+    if (ctx->d_tile_lists) cudaFree(ctx->d_tile_lists);
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->h_snaps) cudaFreeHost(ctx->h_snaps);
@@ -838,7 +839,8 @@ int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out)
 
 // Instance records, padded world boxes and the SAH BVH over them for `n` (tree, transform) pairs.
 static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *trees, const float *o2w, std::vector<DInstance> &inst,
-                            std::vector<DBvhNode> &nodes, Box &root_box, int &root_ref, uint32_t &max_levels, uint32_t &min_levels)
+                            std::vector<DBvhNode> &nodes, Box &root_box, int &root_ref, uint32_t &max_levels, uint32_t &min_levels,
+                            std::vector<float4> &iboxes)
 {
     inst.assign(n, DInstance{});
     std::vector<Box> boxes(n);
@@ -876,6 +878,11 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         boxes[k] = b;
     }
     if (n > (1u << 20)) return fail(ctx, DUST_ERR_UNSUPPORTED, "more than 2^20 instances");
+    iboxes.resize(2 * (size_t)n);                                       // the same padded boxes, for the per-tile candidate lists
+    for (uint32_t k = 0; k < n; k++) {
+        iboxes[2 * (size_t)k] = make_float4(boxes[k].lo[0], boxes[k].lo[1], boxes[k].lo[2], 0.0f);
+        iboxes[2 * (size_t)k + 1] = make_float4(boxes[k].hi[0], boxes[k].hi[1], boxes[k].hi[2], 0.0f);
+    }
     nodes.clear();
     root_box = Box{};
     root_ref = -1;
@@ -892,7 +899,7 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
 
 static void scene_set_view(DustScene *s, const Box &root_box, int root_ref)
 {
-    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh; s->view.prev_o2w = s->d_prev;
+    s->view.inst = s->d_inst; s->view.bvh = s->d_bvh; s->view.prev_o2w = s->d_prev; s->view.inst_boxes = s->d_boxes;
     for (int a = 0; a < 3; a++) { s->view.root_lo[a] = root_box.lo[a]; s->view.root_hi[a] = root_box.hi[a]; }
     s->view.root_ref = root_ref; s->view.n_inst = s->n_inst;
     s->view.id_bits = 8;                                   // candidate key = entry t (high bits) | instance (low id_bits)
@@ -911,7 +918,8 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     Box root_box{};
     int root_ref = -1;
     uint32_t max_levels = 3, min_levels = 4;
-    const int32_t rc = scene_arrays(ctx, n, trees.data(), o2w.data(), inst, nodes, root_box, root_ref, max_levels, min_levels);
+    std::vector<float4> iboxes;
+    const int32_t rc = scene_arrays(ctx, n, trees.data(), o2w.data(), inst, nodes, root_box, root_ref, max_levels, min_levels, iboxes);
     if (rc != DUST_OK) return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     DustScene *s = new (std::nothrow) DustScene();
@@ -924,8 +932,11 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
         if (e == cudaSuccess) e = cudaMalloc(&s->d_prev, sizeof(float) * 12 * n);
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_prev, o2w.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess && !nodes.empty()) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_boxes, sizeof(float4) * iboxes.size());
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_boxes, iboxes.data(), sizeof(float4) * iboxes.size(), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
+            if (s->d_boxes) cudaFree(s->d_boxes);
             if (s->d_inst) cudaFree(s->d_inst);
             if (s->d_bvh) cudaFree(s->d_bvh);
             if (s->d_prev) cudaFree(s->d_prev);
@@ -950,13 +961,15 @@ int32_t dust_scene_update_transforms(DustCtx *ctx, DustScene *scene, const float
     Box root_box{};
     int root_ref = -1;
     uint32_t max_levels = 3, min_levels = 4;
-    const int32_t rc = scene_arrays(ctx, n, scene->trees.data(), obj2world, inst, nodes, root_box, root_ref, max_levels, min_levels);
+    std::vector<float4> iboxes;
+    const int32_t rc = scene_arrays(ctx, n, scene->trees.data(), obj2world, inst, nodes, root_box, root_ref, max_levels, min_levels, iboxes);
     if (rc != DUST_OK) return rc;                                        // the scene is unchanged on error
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     // this frame's transforms become "last frame" for DustGBuffer.motion (PreviousFrameGlobalTransform, standard.rs:845-854)
     CU_TRY(ctx, cudaMemcpyAsync(scene->d_prev, scene->o2w.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(scene->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (!nodes.empty()) CU_TRY(ctx, cudaMemcpyAsync(scene->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(scene->d_boxes, iboxes.data(), sizeof(float4) * iboxes.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));                     // stream-ordered after the frames in flight; host arrays die at return
     memcpy(scene->o2w.data(), obj2world, sizeof(float) * 12 * n);
     scene->n_bvh = (uint32_t)nodes.size();
@@ -971,6 +984,7 @@ int32_t dust_scene_destroy(DustCtx *ctx, DustScene *scene)
     cudaStreamSynchronize(ctx->stream);
     if (scene->d_inst) cudaFree(scene->d_inst);
     if (scene->d_bvh) cudaFree(scene->d_bvh);
+    if (scene->d_boxes) cudaFree(scene->d_boxes);
     if (scene->d_prev) cudaFree(scene->d_prev);
     delete scene;
     return DUST_OK;
@@ -1107,6 +1121,20 @@ static int32_t trace_impl(DustCtx *ctx, const DustScene *scene, const DustCamera
     if (cfg.flags & DUST_TRACE_PIPELINE_WAVEFRONT) wavefront = true;
     if (cfg.flags & DUST_TRACE_PIPELINE_MEGAKERNEL) wavefront = false;
     if (ctx->timing_on) CU_TRY(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+#ifndef DUST_NO_TILE_LISTS
+    if (scene->n_inst > 1 && scene->d_boxes) {
+        // camera rays: one conservative frustum test per tile and instance instead of a BVH walk per ray (trace_core.cuh cull_from_list)
+        const size_t words = (size_t)tiles_per_shard * DUST_TILE_LIST_WORDS;
+        if (words > ctx->tile_lists_words) {
+            if (ctx->d_tile_lists) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CU_TRY(ctx, cudaFree(ctx->d_tile_lists)); ctx->d_tile_lists = nullptr; ctx->tile_lists_words = 0; }
+            CU_TRY(ctx, cudaMalloc(&ctx->d_tile_lists, words * sizeof(uint32_t)));
+            ctx->tile_lists_words = words;
+        }
+        wf_tile_cull<<<(tiles_per_shard + 3) / 4, 128, 0, ctx->stream>>>(p, ctx->d_tile_lists);
+        count_launch(ctx, "wf_tile_cull");
+        p.tile_lists = ctx->d_tile_lists;
+    }
+#endif
     if (wavefront) {
         const int32_t rc = trace_wavefront(ctx, p, tiles_per_shard, nl, stats);
         if (rc != DUST_OK) { ctx->timing_on = false; return rc; }

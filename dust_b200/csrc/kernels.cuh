@@ -39,6 +39,7 @@ struct FrameParams {
     float *hit_t;
     DustGBuffer gb;            // optional G-buffer of the sample-0 primary hit (NULL members are skipped)
     DCounters *counters;
+    const uint32_t *tile_lists;   // per local tile: DUST_TILE_LIST_WORDS words (wf_tile_cull), or NULL
 };
 
 enum : int { RAY_NONE = 0, RAY_PRIMARY = 1, RAY_SHADOW = 2, RAY_BOUNCE = 3 };
@@ -195,6 +196,69 @@ __device__ __forceinline__ uint32_t even_bits(uint32_t v)      // bits 0,2,4,6,8
     return v;
 }
 
+// One warp per local tile: the instances whose padded world box can be touched by ANY camera ray of the tile (any jitter), by a
+// conservative frustum test — four planes through the camera position spanned by the tile's corner directions (camera.glsl:1-16 is linear
+// in the pixel coordinate), widened by a relative epsilon; a box is dropped only when all eight corners lie outside one plane.
+// list[0] = count (0xFFFFFFFF: more than DUST_TILE_LIST_MAX, the rays walk the BVH), list[1..] = instance indices.
+__global__ void __launch_bounds__(128) wf_tile_cull(const __grid_constant__ FrameParams p, uint32_t *__restrict__ lists)
+{
+    const unsigned full = 0xffffffffu;
+    const uint32_t lt = blockIdx.x * 4u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (lt >= p.n_local_tiles) return;
+    uint32_t *list = lists + (size_t)lt * DUST_TILE_LIST_WORDS;
+    const DustTraceConfig &cfg = p.cfg;
+    const uint32_t t = lt * cfg.shard_count + cfg.shard_index;
+    const uint32_t tile_x = t % p.tiles_x, tile_y = t / p.tiles_x;
+    if (tile_y >= p.tiles_y) { if (lane == 0) list[0] = 0u; return; }
+    // pixel coordinate + jitter spans [x0, x0 + 32] x [y0, y0 + 32]
+    const float W = (float)cfg.width, H = (float)cfg.height, tanf_ = p.cam.tan_half_fov;
+    const float xa = (float)(tile_x * 32u), xb = xa + 32.0f, ya = (float)(tile_y * 32u), yb = ya + 32.0f;
+    float cx0 = ((2.0f * (xa / W) - 1.0f) * (W / H)) * tanf_, cx1 = ((2.0f * (xb / W) - 1.0f) * (W / H)) * tanf_;
+    float cy0 = ((2.0f * (ya / H) - 1.0f) * -1.0f) * tanf_, cy1 = ((2.0f * (yb / H) - 1.0f) * -1.0f) * tanf_;
+    if (cx0 > cx1) { const float s_ = cx0; cx0 = cx1; cx1 = s_; }
+    if (cy0 > cy1) { const float s_ = cy0; cy0 = cy1; cy1 = s_; }
+    const float ex = 1e-4f * (fabsf(cx0) + fabsf(cx1) + 1.0f), ey = 1e-4f * (fabsf(cy0) + fabsf(cy1) + 1.0f);
+    cx0 -= ex; cx1 += ex; cy0 -= ey; cy1 += ey;
+    const f3 c0 = mk3(p.cam.camera_view_col0[0], p.cam.camera_view_col0[1], p.cam.camera_view_col0[2]);
+    const f3 c1 = mk3(p.cam.camera_view_col1[0], p.cam.camera_view_col1[1], p.cam.camera_view_col1[2]);
+    const f3 c2 = mk3(p.cam.camera_view_col2[0], p.cam.camera_view_col2[1], p.cam.camera_view_col2[2]);
+    auto dir = [&](float cx, float cy) { return mk3(c0.x * cx + c1.x * cy - c2.x, c0.y * cx + c1.y * cy - c2.y, c0.z * cx + c1.z * cy - c2.z); };
+    auto cross = [](f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); };
+    const f3 d00 = dir(cx0, cy0), d10 = dir(cx1, cy0), d11 = dir(cx1, cy1), d01 = dir(cx0, cy1), dc = dir(0.5f * (cx0 + cx1), 0.5f * (cy0 + cy1));
+    f3 n[4] = { cross(d00, d10), cross(d10, d11), cross(d11, d01), cross(d01, d00) };
+    float nl[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (dot3(n[k], dc) > 0.0f) n[k] = mk3(-n[k].x, -n[k].y, -n[k].z);        // inside: dot(n, v) <= 0
+        nl[k] = sqrtf(dot3(n[k], n[k]));
+    }
+    const f3 o = mk3(p.cam.position_x, p.cam.position_y, p.cam.position_z);
+    uint32_t count = 0;
+    for (uint32_t base = 0; base < p.scene.n_inst; base += 32u) {
+        const uint32_t inst = base + lane;
+        bool keep = false;
+        if (inst < p.scene.n_inst) {
+            const float4 lo = __ldg(&p.scene.inst_boxes[2u * inst]), hi = __ldg(&p.scene.inst_boxes[2u * inst + 1u]);
+            const float far_ = fmaxf(fmaxf(fmaxf(fabsf(lo.x - o.x), fabsf(hi.x - o.x)), fmaxf(fabsf(lo.y - o.y), fabsf(hi.y - o.y))), fmaxf(fabsf(lo.z - o.z), fabsf(hi.z - o.z)));
+            keep = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                // the corner that lies deepest inside (smallest dot): if even that one is outside by more than the margin, all eight are
+                const float vx = (n[k].x > 0.0f ? lo.x : hi.x) - o.x, vy = (n[k].y > 0.0f ? lo.y : hi.y) - o.y, vz = (n[k].z > 0.0f ? lo.z : hi.z) - o.z;
+                const float dmin = (n[k].x * vx + n[k].y * vy) + n[k].z * vz;
+                if (dmin > 1e-4f * nl[k] * (far_ * 3.0f + 1.0f)) keep = false;
+            }
+        }
+        const unsigned m = __ballot_sync(full, keep);
+        if (keep) {
+            const uint32_t k = count + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (k < DUST_TILE_LIST_MAX) list[1u + k] = inst;
+        }
+        count += (uint32_t)__popc(m);
+    }
+    if (lane == 0) list[0] = count > DUST_TILE_LIST_MAX ? 0xFFFFFFFFu : count;
+}
+
 // Thread mapping: 2^slot_log2 consecutive threads share a pixel (one sample each per round); pixels
 // follow a Morton curve inside 32x32 tiles, so a warp covers a compact patch (4x2 pixels x 4 samples
 // at 4 spp, 8x4 pixels at 1 spp).  32x32 tiles are the sharding unit: tile t -> shard t % shard_count.
@@ -236,10 +300,13 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_FRAME_MIN_BLOCKS) frame_ker
         f3 L = mk3(0.0f, 0.0f, 0.0f), T = mk3(1.0f, 1.0f, 1.0f);                      // linear sRGB primaries
         uint32_t v = 0;
 
+        // the first ray of every sample is the camera ray of a pixel of this CTA's tile: the tile's candidate list replaces its BVH walk
+        const uint32_t *tl = p.tile_lists ? p.tile_lists + (size_t)min(lt, p.n_local_tiles - 1u) * DUST_TILE_LIST_WORDS : nullptr;
 #pragma unroll 1
         while (__any_sync(full, kind != RAY_NONE)) {
             Hit h;
-            trace_scene<NL, STATS>(p.scene, ro, rd, tmin, tmax, kind == RAY_SHADOW, kind != RAY_NONE, sm, h, st);
+            trace_scene<NL, STATS>(p.scene, ro, rd, tmin, tmax, kind == RAY_SHADOW, kind != RAY_NONE, sm, h, st, LEAF_PRECISE, tl);
+            tl = nullptr;
 
             bool to_vertex = false, to_bounce = false, need_sky = false;
             if (kind == RAY_SHADOW) {

@@ -114,6 +114,32 @@ __device__ __forceinline__ bool cull_begin(const DSceneView &sc, f3 ro, f3 winv,
     return true;
 }
 
+// Per-tile candidate lists (wf_tile_cull, kernels.cuh): the rays of a 32x32 tile share the camera origin, so ONE conservative frustum
+// test per tile and instance replaces every ray's BVH walk (26 % of the primary pass' instructions, profiles/r02_history.md); a ray then
+// runs the same exact box test on the few listed instances.  The candidate set is the one the BVH walk finds (box tests only cull).
+#define DUST_TILE_LIST_MAX 15                  // entries per tile (+ 1 count word = 64 bytes); a longer list marks the tile "walk the BVH"
+#define DUST_TILE_LIST_WORDS (DUST_TILE_LIST_MAX + 1)
+
+__device__ __forceinline__ void cull_from_list(const DSceneView &sc, const uint32_t *list, f3 ro, f3 winv, float tmin, float tmax, uint32_t id_mask,
+                                               uint32_t *sm, int &nc)
+{
+    const uint32_t n = __ldg(&list[0]);
+    for (uint32_t e = 0; e < n; e++) {
+        const uint32_t inst = __ldg(&list[1u + e]);
+        const float4 lo = __ldg(&sc.inst_boxes[2u * inst]), hi = __ldg(&sc.inst_boxes[2u * inst + 1u]);
+        const float te = box_entry(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, ro, winv, tmin, tmax);
+        if (te == CUDART_INF_F) continue;
+        const uint32_t key = cand_key(te, inst, id_mask);
+        int k = nc++;
+        while (k > 0) {
+            const uint32_t prev = sm[(k - 1) * DUST_THREADS];
+            if (prev <= key) break;
+            sm[k * DUST_THREADS] = prev; --k;
+        }
+        sm[k * DUST_THREADS] = key;
+    }
+}
+
 // room for one more expansion (2 candidates + 1 stack entry)?
 __device__ __forceinline__ bool cull_room(int sp, int nc) { return nc + 3 <= sp; }
 
@@ -345,7 +371,8 @@ __device__ __forceinline__ uint32_t walk_pos(const Walk &w) { return (uint32_t)w
 // `sm` = this lane's column of the block's scratch: word k lives at sm[k * DUST_THREADS].
 template <int NL, bool STATS>
 __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, const f3 rd, const float tmin, const float tmax,
-                                            const bool any, const bool live, uint32_t *sm, Hit &best, Counters &st, const int leaf_mode = LEAF_PRECISE)
+                                            const bool any, const bool live, uint32_t *sm, Hit &best, Counters &st, const int leaf_mode = LEAF_PRECISE,
+                                            const uint32_t *tile_list = nullptr)
 {
     const unsigned full = 0xffffffffu;
     best.hit = false; best.inst = 0xFFFFFFFFu; best.t = tmax;
@@ -354,7 +381,11 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     if (STATS && (threadIdx.x & 31u) == 0) st.dbg[15]++;
     const f3 winv = cull_inverse(rd);
     int sp = DUST_SCRATCH_WORDS, pend = -1, nc = 0;
-    if (live) cull_begin(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc);
+    if (live) {
+        // warp-uniform: a tile list (camera rays of one tile) replaces the BVH walk unless the tile overflowed its list
+        if (tile_list && __ldg(&tile_list[0]) != 0xFFFFFFFFu) cull_from_list(sc, tile_list, ro, winv, tmin, cur, id_mask, sm, nc);
+        else cull_begin(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc);
+    }
 
     Walk w;
     w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;

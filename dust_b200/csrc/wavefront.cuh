@@ -171,7 +171,13 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
     }
     Counters st = {};
     Hit h;
-    trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st, ROUGH);
+    // implicit depth-0 queue: the 32 rays of a warp are camera rays of ONE tile (1024 * batch_spp consecutive slots per tile)
+    const uint32_t *tl = nullptr;
+    if (q.stride == 0u && p.f.tile_lists) {
+        const uint32_t i0 = blockIdx.x * DUST_THREADS + (threadIdx.x & ~31u);
+        tl = p.f.tile_lists + (size_t)min((i0 / p.batch_spp) >> 10, p.f.n_local_tiles - 1u) * DUST_TILE_LIST_WORDS;
+    }
+    trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st, ROUGH, tl);
     if (live) {
         if (STATS && q.stride == 2u) st.primary_rays++;
         if (pw >> 31) p.vis[pw & 0x7FFFFFFFu] = h.hit ? 1 : 0;

@@ -406,16 +406,17 @@ def test_launch_info_timing_and_counter_deltas(castle_small, host):
     out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     ctx.use_torch_stream()
     try:
-        for pipeline, names in (("wavefront", {"wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace_slow"}), ("megakernel", {"frame_kernel"})):
+        for pipeline, names in (("wavefront", {"wf_tile_cull", "wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace_slow"}),
+                                ("megakernel", {"wf_tile_cull", "frame_kernel"})):
             castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1, stats=True, timing=True, pipeline=pipeline)
             info = ctx.launch_info()
             tot = ctx.stats()
             assert {r["kernel"] for r in info} == names and all(r["ms"] > 0 for r in info)
-            assert len(info) == (11 if pipeline == "wavefront" else 1)
+            assert len(info) == (12 if pipeline == "wavefront" else 2)          # + wf_tile_cull (the camera-ray candidate lists)
             for k in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded"):
                 assert sum(r[k] for r in info) == tot[k], k
         castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1)     # no flag: the records of the last timed call stay
-        assert len(ctx.launch_info()) == 1
+        assert len(ctx.launch_info()) == 2
     finally:
         ctx.set_stream(None)
 
@@ -574,3 +575,25 @@ def test_bad_transforms_and_misaligned_device_buffers_are_rejected(teapot, host,
     with pytest.raises(DustError, match="aligned"):
         good.trace_rays_device(d[2:], hits, 4)
     assert np.array_equal(good.trace_rays(rays), before)
+
+
+def test_tile_candidate_lists_do_not_change_frames(castle_small, teapot, host, ctx, oracle):
+    """wf_tile_cull: per-tile frustum candidate lists replace the camera rays' BVH walk.  Boxes only cull, so frames must be bit-identical
+    to the oracle for cameras that see the scene from outside, from INSIDE an instance box, with a narrow and a very wide field of view,
+    looking away from the scene, and for a 2 000-instance scene where most tiles overflow their list and fall back to the BVH."""
+    s = castle_small
+    lo, hi = s.bounds()
+    c = (lo + hi) / 2
+    W, H = 200, 120                                                  # 7 x 4 tiles, the last column / row partial
+    cams = [host.camera_look_at(c + np.array((0.9, 0.5, 0.7)) * (hi - lo).max(), c, width=W, height=H),
+            host.camera_look_at(c + np.array((0.05, 0.02, 0.03)) * (hi - lo).max(), hi, width=W, height=H),           # inside the scene
+            host.camera_look_at(c + np.array((1.5, 1.0, 1.2)) * (hi - lo).max(), c, fov=np.float32(0.08), width=W, height=H),
+            host.camera_look_at(c + np.array((0.4, 0.3, 0.2)) * (hi - lo).max(), c, fov=np.float32(2.9), width=W, height=H),
+            host.camera_look_at(hi + 20.0, hi + 40.0, width=W, height=H)]                                              # looking away
+    sky = host.sunlight_bake()
+    for k, cam in enumerate(cams):
+        for pipeline in ("megakernel", "wavefront"):
+            g = s.loaded.scene.trace(cam, sky, W, H, spp=2, max_bounces=1, seed=k, hits=True, pipeline=pipeline)
+            o = s.oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=k)
+            _assert_hits_equal(g, o)
+            assert np.array_equal(g["radiance"].view(np.uint32), o["radiance"].view(np.uint32)), (k, pipeline)
