@@ -205,7 +205,26 @@ int32_t dust_trace_gi(DustCtx *ctx, const DustScene *scene, DustRadianceCache *c
 
     // primary
     {
-        const uint32_t grid = (npx + DUST_THREADS - 1) / DUST_THREADS;
+        const uint32_t tiles_x = (W + 31) / 32, tiles_y = (H + 31) / 32, n_tiles = tiles_x * tiles_y;
+        p.tiles_x = tiles_x;
+        if (scene->n_inst > 1 && scene->d_boxes) {
+            // the camera rays' candidate lists, per tile (kernels.cuh wf_tile_cull: only the camera, the frame size and the tile grid are read)
+            const size_t words = (size_t)n_tiles * DUST_TILE_LIST_WORDS;
+            if (words > ctx->tile_lists_words) {
+                if (ctx->d_tile_lists) { CU_TRY(ctx, cudaStreamSynchronize(st)); CU_TRY(ctx, cudaFree(ctx->d_tile_lists)); ctx->d_tile_lists = nullptr; ctx->tile_lists_words = 0; }
+                CU_TRY(ctx, cudaMalloc(&ctx->d_tile_lists, words * sizeof(uint32_t)));
+                ctx->tile_lists_words = words;
+            }
+            FrameParams fp;
+            memset(&fp, 0, sizeof fp);
+            fp.scene = scene->view; fp.cam = *camera;
+            fp.cfg.width = W; fp.cfg.height = H; fp.cfg.shard_count = 1; fp.cfg.shard_index = 0;
+            fp.tiles_x = tiles_x; fp.tiles_y = tiles_y; fp.n_local_tiles = n_tiles;
+            wf_tile_cull<<<(n_tiles + 3) / 4, 128, 0, st>>>(fp, ctx->d_tile_lists);
+            dust_count_launch(ctx, "wf_tile_cull");
+            p.tile_lists = ctx->d_tile_lists;
+        }
+        const uint32_t grid = n_tiles * (1024u / DUST_THREADS);
         if (nl == 3) gi_primary<3><<<grid, DUST_THREADS, 0, st>>>(p); else if (nl == 4) gi_primary<4><<<grid, DUST_THREADS, 0, st>>>(p); else gi_primary<0><<<grid, DUST_THREADS, 0, st>>>(p);
         dust_count_launch(ctx, "gi_primary");
     }

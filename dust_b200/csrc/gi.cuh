@@ -50,6 +50,8 @@ struct GiParams {
     uint32_t *ins_loc, *ins_fp;       // the insert of surfel invocation i: probe location (0xFFFFFFFF: none), fingerprint
     float4 *ins_val;
     unsigned long long *stats; // GI_N_STATS counters
+    const uint32_t *tile_lists;    // per 32x32 tile of the row-major frame: candidate instances of its camera rays (wf_tile_cull), or NULL
+    uint32_t tiles_x;
     const float *srgb_lut;     // SRGBToLinear(v / 1023) for the 1024 UNORM10 levels of Block.avg_albedo (host libm powf, like palette_lin)
 };
 
@@ -287,13 +289,17 @@ template <int NL>
 __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) gi_primary(const __grid_constant__ GiParams p)
 {
     __shared__ uint32_t s_scratch[DUST_SCRATCH_WORDS * DUST_THREADS];
-    const uint32_t pi = blockIdx.x * DUST_THREADS + threadIdx.x, npx = p.width * p.height;
-    const bool live = pi < npx;
+    // thread -> pixel: 32x32 tiles, row-major inside a tile, so that a warp is one tile row and shares the tile's candidate list
+    const uint32_t item = blockIdx.x * DUST_THREADS + threadIdx.x, tile = item >> 10, q = item & 1023u;
+    const uint32_t px = (tile % p.tiles_x) * 32u + (q & 31u), py = (tile / p.tiles_x) * 32u + (q >> 5);
+    const bool live = px < p.width && py < p.height;
+    const uint32_t pi = py * p.width + px;
+    const uint32_t *tl = p.tile_lists ? p.tile_lists + (size_t)tile * DUST_TILE_LIST_WORDS : nullptr;
     f3 ro = mk3(0.0f, 0.0f, 0.0f), rd = mk3(1.0f, 1.0f, 1.0f);
-    if (live) camera_ray(p.cam, p.width, p.height, pi % p.width, pi / p.width, 0.5f, 0.5f, ro, rd);
+    if (live) camera_ray(p.cam, p.width, p.height, px, py, 0.5f, 0.5f, ro, rd);
     Counters st = {};
     Hit h;
-    trace_scene<NL, false>(p.scene, ro, rd, live ? p.cam.near : 1.0f, live ? p.cam.far : 0.0f, false, live, s_scratch + threadIdx.x, h, st);
+    trace_scene<NL, false>(p.scene, ro, rd, live ? p.cam.near : 1.0f, live ? p.cam.far : 0.0f, false, live, s_scratch + threadIdx.x, h, st, LEAF_PRECISE, tl);
     if (!live) return;
     if (h.hit) {
         f3 sn, x = ro;
