@@ -58,10 +58,18 @@ __device__ __forceinline__ void cossin_2pi(float u, float &c, float &s)
     float cs = 1.0f + t2 * (-0.5f + t2 * (1.0f / 24.0f + t2 * (-1.0f / 720.0f + t2 * (1.0f / 40320.0f + t2 * (-1.0f / 3628800.0f)))));
     float c45 = (cs - sn) * 0.70710678118654752440f;
     float s45 = (cs + sn) * 0.70710678118654752440f;
-    if (q == 0)      { c = c45;  s = s45; }
-    else if (q == 1) { c = -s45; s = c45; }
-    else if (q == 2) { c = -c45; s = -s45; }
-    else             { c = s45;  s = -c45; }
+    const float cc = (q & 1) ? s45 : c45, ss = (q & 1) ? c45 : s45;     // quadrant rotation as selects: the four-way branch split every warp
+    c = (q == 1 || q == 2) ? -cc : cc;
+    s = (q >= 2) ? -ss : ss;
+}
+
+// x / l for a finite l > 0.  A zero numerator — every axis-aligned normal has two — is answered without the divider: FCHK sends
+// x == 0 to the ~100-instruction slow path of the IEEE division (profiles/r02_history.md 9), and +-0 / l is +-0 bit for bit.
+__device__ __forceinline__ float div_pos(float x, float l)
+{
+    const bool z = x == 0.0f;
+    const float r = (z ? 1.0f : x) / l;
+    return z ? x : r;
 }
 
 // headers/normal.glsl:31-37
@@ -69,7 +77,7 @@ __device__ __forceinline__ f3 rotate_by_normal(f3 n, f3 v)
 {
     float q0 = -n.y, q1 = n.x, q2 = 0.0f, q3 = 1.0f + n.z;
     float l = sqrtf(((q0 * q0 + q1 * q1) + q2 * q2) + q3 * q3);
-    q0 = q0 / l; q1 = q1 / l; q2 = q2 / l; q3 = q3 / l;
+    q0 = div_pos(q0, l); q1 = div_pos(q1, l); q2 = div_pos(q2, l); q3 = div_pos(q3, l);   // l == 0 only for n = -z, replaced below
     if (n.z < -0.99999f) { q0 = -1.0f; q1 = 0.0f; q2 = 0.0f; q3 = 0.0f; }
     f3 q = mk3(q0, q1, q2);
     float d = dot3(q, v);

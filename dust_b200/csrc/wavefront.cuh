@@ -651,8 +651,8 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 #ifndef DUST_SHADE_MIN_BLOCKS
 #define DUST_SHADE_MIN_BLOCKS 8
 #endif
-// All 32 lanes of a warp call this together (the emitted rays are compacted with warp votes); lanes without a ray
-// pass live = false.  `hw_in` != NULL: the hit record of slot i is passed in registers instead of read from p.hits
+// All threads of a CTA of DUST_THREADS call this together (the emitted rays are compacted with warp votes and one
+// reservation per CTA); threads without a ray pass live = false.  `hw_in` != NULL: the hit record of slot i is passed in registers instead of read from p.hits
 // (the fused depth-0 kernel below).
 template <bool STATS>
 __device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_t i, const bool live, const uint4 *hw_in, Counters &st)
@@ -690,12 +690,16 @@ __device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_
         if (valid) {
             const bool hit = hw.y != 0xFFFFFFFFu;
             if (STATS) { if (p.depth == 0) st.primary_rays++; else st.bounce_rays++; }
-            if (p.depth == 0 && smp == 0 && (cfg.flags & DUST_TRACE_WRITE_HITS) && p.f.hit_instance) {
+            // uniform tests first, the per-lane `smp == 0` innermost: as one short-circuit chain ptxas split the warp at smp == 0 and
+            // ran everything below twice, with 8 and with 24 lanes (profiles/r02_history.md 9)
+            const bool hits_on = p.depth == 0 && (cfg.flags & DUST_TRACE_WRITE_HITS) && p.f.hit_instance;
+            const bool gb_on = p.depth == 0 && gbuffer_wanted(p.f.gb);
+            if (hits_on && smp == 0) {
                 const uint32_t pi = py * cfg.width + px;
                 p.f.hit_instance[pi] = hit ? (hw.y & 0xFFFFFu) : 0xFFFFFFFFu; p.f.hit_leaf[pi] = hit ? hw.z : 0xFFFFFFFFu;
                 p.f.hit_voxel[pi] = hit ? (uint8_t)(hw.y >> 20) : (uint8_t)0xFF; p.f.hit_t[pi] = hit ? __uint_as_float(hw.x) : CUDART_INF_F;
             }
-            const bool want_gb = p.depth == 0 && smp == 0 && gbuffer_wanted(p.f.gb);
+            const bool want_gb = gb_on && smp == 0;
             if (want_gb && !hit) gbuffer_store(p.f.gb, p.f.scene, py * cfg.width + px, false, 0.0f, 0u, 0u, 0u, ro, rd, ro);
             if (hit) {
                 Hit h;
@@ -736,36 +740,40 @@ __device__ __forceinline__ void wf_shade_vertex(const WfParams &p, const uint32_
         p.ps0[path] = make_float4(T.x, T.y, T.z, __uint_as_float(s1));
         p.ps1[path] = make_float4(L.x, L.y, L.z, pend_ndl);
     }
-    // ---- compact the emitted rays into the queues: one atomic per warp and queue
+    // ---- compact the emitted rays into the queues: one atomic per CTA and queue.  (One per warp was 518 400 atomics on two
+    // words of one L2 sector per depth-0 launch: 56 % of the kernel's stall samples sat on them, profiles/r02_history.md 9.)
+    // Every thread of the CTA gets here (callers exit CTA-uniformly), so the two barriers are safe.
     {
-        const unsigned m = __ballot_sync(full, emit_shadow);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&p.counts[4 * p.depth + 1], (uint32_t)__popc(m));
-            base = __shfl_sync(full, base, __ffs(m) - 1);
-            if (emit_shadow) {
-                const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                if (p.qs.kind == 1u) p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(path | 0x80000000u));   // direction, tmin, tmax: uniforms of the queue
-                else {
-                    p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
-                    p.qs.b[k] = make_float4(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2], 10000.0f);
-                    p.qs.path[k] = path | 0x80000000u;
-                }
+        __shared__ uint32_t s_cnt[2][DUST_THREADS / 32], s_base[2];
+        const unsigned w = threadIdx.x >> 5;
+        const unsigned ms = __ballot_sync(full, emit_shadow), mb = __ballot_sync(full, emit_bounce);
+        if (lane == 0) { s_cnt[0][w] = (uint32_t)__popc(ms); s_cnt[1][w] = (uint32_t)__popc(mb); }
+        __syncthreads();
+        if (lane == 0 && w < 2u) {                                      // warp 0 reserves the shadow records, warp 1 the bounce records
+            uint32_t tot = 0;
+#pragma unroll
+            for (int k = 0; k < DUST_THREADS / 32; k++) tot += s_cnt[w][k];
+            s_base[w] = tot ? atomicAdd(&p.counts[4 * p.depth + 1 + w], tot) : 0u;
+        }
+        __syncthreads();
+        uint32_t pre_s = s_base[0], pre_b = s_base[1];
+#pragma unroll
+        for (int k = 0; k < DUST_THREADS / 32; k++) if ((unsigned)k < w) { pre_s += s_cnt[0][k]; pre_b += s_cnt[1][k]; }
+        const unsigned below = (1u << lane) - 1u;
+        if (emit_shadow) {
+            const uint32_t k = pre_s + (uint32_t)__popc(ms & below);
+            if (p.qs.kind == 1u) p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(path | 0x80000000u));   // direction, tmin, tmax: uniforms of the queue
+            else {
+                p.qs.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f);
+                p.qs.b[k] = make_float4(p.f.sun_dir[0], p.f.sun_dir[1], p.f.sun_dir[2], 10000.0f);
+                p.qs.path[k] = path | 0x80000000u;
             }
         }
-    }
-    {
-        const unsigned m = __ballot_sync(full, emit_bounce);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&p.counts[4 * p.depth + 2], (uint32_t)__popc(m));
-            base = __shfl_sync(full, base, __ffs(m) - 1);
-            if (emit_bounce) {
-                const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                p.qn.b[k] = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
-                if (p.qn.kind == 2u) p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(path));                 // tmin: uniform of the queue
-                else { p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f); p.qn.path[k] = path; }
-            }
+        if (emit_bounce) {
+            const uint32_t k = pre_b + (uint32_t)__popc(mb & below);
+            p.qn.b[k] = make_float4(rd.x, rd.y, rd.z, p.f.cam.far);
+            if (p.qn.kind == 2u) p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(path));                 // tmin: uniform of the queue
+            else { p.qn.a[k] = make_float4(ro.x, ro.y, ro.z, 0.1f); p.qn.path[k] = path; }
         }
     }
 }
