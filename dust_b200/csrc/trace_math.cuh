@@ -64,12 +64,14 @@ __device__ __forceinline__ void cossin_2pi(float u, float &c, float &s)
 }
 
 // x / l for a finite l > 0.  A zero numerator — every axis-aligned normal has two — is answered without the divider: FCHK sends
-// x == 0 to the ~100-instruction slow path of the IEEE division (profiles/r02_history.md 9), and +-0 / l is +-0 bit for bit.
+// x == 0 to the out-of-line slow path of the IEEE division (profiles/r02_history.md 9), and +-0 / l is +-0 bit for bit.  The
+// substitute numerator goes through inline PTX: written in C, the compiler folds it away again and divides x itself.
 __device__ __forceinline__ float div_pos(float x, float l)
 {
-    const bool z = x == 0.0f;
-    const float r = (z ? 1.0f : x) / l;
-    return z ? x : r;
+    float num;
+    asm("{ .reg .pred z; setp.eq.f32 z, %1, 0f00000000; selp.f32 %0, 0f3F800000, %1, z; }" : "=f"(num) : "f"(x));
+    const float r = num / l;
+    return x == 0.0f ? x : r;
 }
 
 // headers/normal.glsl:31-37
