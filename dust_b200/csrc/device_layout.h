@@ -60,12 +60,24 @@ struct alignas(16) DBvhNode {
 };
 static_assert(sizeof(DBvhNode) == 64, "DBvhNode layout");
 
+// WIDE BVH (the layout the kernels walk unless built with -DDUST_BINARY_BVH): the binary SAH tree collapsed to FOUR children per
+// node, child boxes QUANTISED to 16 bits per plane on ONE power-of-two grid per scene (DSceneView::grid_org / grid_step; boxes are
+// rounded outwards and widened by one step, which also covers the rounding of the decode below).  One node = 4 x 128 bit, the same
+// 64 bytes as a binary node but for twice the children, and all four loads are independent:
+//   word 0 / 1 / 2   x / y / z of children 0..3: lo | hi << 16      (an unused slot has lo = 0xFFFF, hi = 0: never hit)
+//   word 3           child references 0..3 (>= 0 wide node index, < 0 instance ~ref)
+// plane(q) = org + q * step.  A ray computes S = step / d and A = (org - o) / d - 2^23 S ONCE (the grid is the scene's), and then
+// t(q) = fma(2^23 + q, S, A), where the operand 2^23 + q is built by ONE byte permute (PRMT) that also picks lo or hi by the sign
+// of d: 6 PRMT + 6 FFMA + 4 min / max per child box, where the float boxes took 6 FADD + 6 FMUL + 10 min / max.
+#define DUST_BVH_WIDTH 4
+
 struct DSceneView {
     const DInstance *inst;
-    const DBvhNode *bvh;           // n_inst - 1 inner nodes (none for 0 / 1 instances)
+    const DBvhNode *bvh;           // binary: n_inst - 1 nodes of 64 bytes; wide (default): 4 x uint4 per node (none for 0 / 1 instances)
     const float4 *prev_o2w;        // 3 rows per instance: last frame's object -> world (G-buffer motion)
     const float4 *inst_boxes;      // 2 per instance: padded world box lo.xyz, hi.xyz (the boxes the BVH is built over; per-tile candidate lists test them directly)
     float root_lo[3], root_hi[3];  // padded world box of the whole scene
+    float grid_org[3], grid_step[3];   // the wide BVH's quantisation grid (steps are powers of two)
     int32_t root_ref;              // >= 0 inner node, < 0 instance ~root_ref
     uint32_t n_inst;
     uint32_t id_bits;              // low bits of a candidate key that hold the instance index

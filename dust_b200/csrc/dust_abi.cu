@@ -278,6 +278,79 @@ int build_bvh(std::vector<DBvhNode> &nodes, std::vector<uint32_t> &ids, const st
     return me;
 }
 
+// The wide BVH's quantisation grid (device_layout.h "WIDE BVH"): per axis a power-of-two step that spreads the scene box over at most
+// 65 000 of the 65 536 positions and is at least 4 ulp of the coordinates (so the float origin's own rounding stays below 1/8 step).
+struct BvhGrid { float org[3]; double step[3]; };
+
+BvhGrid bvh_grid(const Box &root)
+{
+    BvhGrid g;
+    for (int a = 0; a < 3; a++) {
+        const double maxabs = std::max({ std::fabs((double)root.lo[a]), std::fabs((double)root.hi[a]), 1e-30 });
+        const double pad = 4e-7 * maxabs;
+        const double lo = (double)root.lo[a] - pad, hi = (double)root.hi[a] + pad;
+        int e = (int)std::ceil(std::log2(std::max(hi - lo, 1e-300) / 65000.0));
+        e = std::min(std::max({ e, std::ilogb(maxabs) - 21, -100 }), 100);
+        g.step[a] = std::ldexp(1.0, e);
+        float o = (float)(lo - 2.0 * g.step[a]);
+        while ((double)o > lo - g.step[a]) o = std::nextafterf(o, -INFINITY);
+        g.org[a] = o;
+    }
+    return g;
+}
+
+// Collapse the binary SAH tree into the wide, quantised layout the kernels walk.  A wide node takes the shallowest inner child first
+// (the larger box among those), so every path absorbs two binary levels per wide node where it has them and the wide tree is at most
+// half as deep as the binary one.  Child boxes are quantised in double, outwards, and widened by one grid step: the decode on the
+// device (trace_core.cuh cull_plane) is off by at most half a step plus a few 2^-24 relative roundings of (org - o), which the
+// 4e-7 * |coordinate| term covers for ray origins within about the scene's own distance of it.
+int build_wide(std::vector<uint4> &out, const std::vector<DBvhNode> &nodes, const BvhGrid &g, int ref, int depth, int &max_depth, bool &ok)
+{
+    struct Child { int ref; Box box; int depth; };
+    max_depth = std::max(max_depth, depth);
+    std::vector<Child> ch;
+    auto push_kids = [&](int b, int d) {
+        const DBvhNode &n = nodes[(size_t)b];
+        Child c0{ n.child0, Box{ { n.lo0[0], n.lo0[1], n.lo0[2] }, { n.hi0[0], n.hi0[1], n.hi0[2] } }, d };
+        Child c1{ n.child1, Box{ { n.lo1[0], n.lo1[1], n.lo1[2] }, { n.hi1[0], n.hi1[1], n.hi1[2] } }, d };
+        ch.push_back(c0); ch.push_back(c1);
+    };
+    push_kids(ref, 1);
+    while (ch.size() < (size_t)DUST_BVH_WIDTH) {
+        int best = -1;
+        for (int k = 0; k < (int)ch.size(); k++) {
+            if (ch[k].ref < 0) continue;
+            if (best < 0 || ch[k].depth < ch[best].depth || (ch[k].depth == ch[best].depth && box_area(ch[k].box) > box_area(ch[best].box))) best = k;
+        }
+        if (best < 0) break;
+        const Child c = ch[best];
+        ch.erase(ch.begin() + best);
+        push_kids(c.ref, c.depth + 1);
+    }
+    const size_t me = out.size() / 4;
+    out.resize(out.size() + 4, make_uint4(0, 0, 0, 0));
+    uint32_t q[3][DUST_BVH_WIDTH], refs[DUST_BVH_WIDTH];
+    for (int k = 0; k < DUST_BVH_WIDTH; k++) { q[0][k] = q[1][k] = q[2][k] = 0x0000FFFFu; refs[k] = 0; }   // unused slot: lo = 0xFFFF, hi = 0
+    for (size_t k = 0; k < ch.size(); k++)
+        for (int a = 0; a < 3; a++) {
+            const double maxabs = std::max(std::fabs((double)ch[k].box.lo[a]), std::fabs((double)ch[k].box.hi[a]));
+            const double pad = 4e-7 * maxabs;
+            const double ql = std::floor(((double)ch[k].box.lo[a] - pad - (double)g.org[a]) / g.step[a]) - 1.0;
+            const double qh = std::ceil(((double)ch[k].box.hi[a] + pad - (double)g.org[a]) / g.step[a]) + 1.0;
+            if (!(ql >= 0.0) || !(qh <= 65535.0)) { ok = false; return 0; }       // cannot happen by construction (checked, not assumed)
+            q[a][k] = (uint32_t)ql | ((uint32_t)qh << 16);
+        }
+    for (size_t k = 0; k < ch.size(); k++) {
+        int r = ch[k].ref;
+        if (r >= 0) { r = build_wide(out, nodes, g, r, depth + 1, max_depth, ok); if (!ok) return 0; }
+        refs[k] = (uint32_t)r;
+    }
+    uint4 *node = out.data() + me * 4;                                           // (after the recursion: `out` may have moved)
+    for (int a = 0; a < 3; a++) node[a] = make_uint4(q[a][0], q[a][1], q[a][2], q[a][3]);
+    node[3] = make_uint4(refs[0], refs[1], refs[2], refs[3]);
+    return (int)me;
+}
+
 // sun_radiance (assets/shaders/headers/sky.glsl:80-113) on the host, for the uniform-only NEE term
 void sun_radiance_host(const DustSky &sky, float ar2, const float dir[3], float out[3])
 {
@@ -838,10 +911,33 @@ int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out)
 }
 
 // Instance records, padded world boxes and the SAH BVH over them for `n` (tree, transform) pairs.
+// what the kernels walk: the wide nodes, or (-DDUST_BINARY_BVH) the binary nodes as they are
+struct BvhBlob {
+    std::vector<DBvhNode> nodes;                                         // binary SAH tree (the source of the collapse)
+    std::vector<uint4> wide;
+    BvhGrid grid{};
+    const void *data() const {
+#ifdef DUST_BINARY_BVH
+        return nodes.data();
+#else
+        return wide.data();
+#endif
+    }
+    size_t bytes() const {
+#ifdef DUST_BINARY_BVH
+        return nodes.size() * sizeof(DBvhNode);
+#else
+        return wide.size() * sizeof(uint4);
+#endif
+    }
+    static size_t capacity(uint32_t n) { return (size_t)n * sizeof(DBvhNode); }   // n leaves: at most n - 1 nodes of either kind, 64 bytes each
+};
+
 static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *trees, const float *o2w, std::vector<DInstance> &inst,
-                            std::vector<DBvhNode> &nodes, Box &root_box, int &root_ref, uint32_t &max_levels, uint32_t &min_levels,
+                            BvhBlob &bvh, Box &root_box, int &root_ref, uint32_t &max_levels, uint32_t &min_levels,
                             std::vector<float4> &iboxes)
 {
+    std::vector<DBvhNode> &nodes = bvh.nodes;
     inst.assign(n, DInstance{});
     std::vector<Box> boxes(n);
     max_levels = 3; min_levels = 4;
@@ -893,12 +989,26 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         nodes.reserve((size_t)n);
         root_ref = build_bvh(nodes, ids, boxes, 0, n, root_box, 0, depth);
         if (depth > DUST_MAX_BVH_DEPTH) return fail(ctx, DUST_ERR_UNSUPPORTED, "instance BVH deeper than the traversal stack");
+#ifndef DUST_BINARY_BVH
+        bvh.wide.clear();
+        if (root_ref >= 0) {
+            int wdepth = 0;
+            bool ok = true;
+            bvh.wide.reserve((size_t)n * 4);
+            bvh.grid = bvh_grid(root_box);
+            root_ref = build_wide(bvh.wide, nodes, bvh.grid, root_ref, 0, wdepth, ok);
+            if (!ok) return fail(ctx, DUST_ERR_UNSUPPORTED, "instance boxes do not fit the wide BVH's 16-bit grid");
+            // one stack entry per level, and an empty candidate list must always find room for one more expansion (cull_room)
+            if (wdepth + 1 + DUST_BVH_WIDTH + 1 > DUST_SCRATCH_WORDS) return fail(ctx, DUST_ERR_UNSUPPORTED, "instance BVH deeper than the traversal stack");
+        }
+#endif
     }
     return DUST_OK;
 }
 
-static void scene_set_view(DustScene *s, const Box &root_box, int root_ref)
+static void scene_set_view(DustScene *s, const Box &root_box, int root_ref, const BvhBlob &bvh)
 {
+    for (int a = 0; a < 3; a++) { s->view.grid_org[a] = bvh.grid.org[a]; s->view.grid_step[a] = (float)bvh.grid.step[a]; }
     s->view.inst = s->d_inst; s->view.bvh = s->d_bvh; s->view.prev_o2w = s->d_prev; s->view.inst_boxes = s->d_boxes;
     for (int a = 0; a < 3; a++) { s->view.root_lo[a] = root_box.lo[a]; s->view.root_hi[a] = root_box.hi[a]; }
     s->view.root_ref = root_ref; s->view.n_inst = s->n_inst;
@@ -914,24 +1024,24 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     std::vector<float> o2w(12 * (size_t)n);
     for (uint32_t k = 0; k < n; k++) { trees[k] = instances[k].tree; memcpy(&o2w[12 * (size_t)k], instances[k].obj2world, 12 * sizeof(float)); }
     std::vector<DInstance> inst;
-    std::vector<DBvhNode> nodes;
+    BvhBlob bvh;
     Box root_box{};
     int root_ref = -1;
     uint32_t max_levels = 3, min_levels = 4;
     std::vector<float4> iboxes;
-    const int32_t rc = scene_arrays(ctx, n, trees.data(), o2w.data(), inst, nodes, root_box, root_ref, max_levels, min_levels, iboxes);
+    const int32_t rc = scene_arrays(ctx, n, trees.data(), o2w.data(), inst, bvh, root_box, root_ref, max_levels, min_levels, iboxes);
     if (rc != DUST_OK) return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     DustScene *s = new (std::nothrow) DustScene();
     if (!s) return DUST_ERR_OUT_OF_MEMORY;
-    s->n_inst = n; s->n_bvh = (uint32_t)nodes.size(); s->max_levels = max_levels; s->min_levels = std::min(min_levels, max_levels);
+    s->n_inst = n; s->n_bvh = (uint32_t)bvh.nodes.size(); s->max_levels = max_levels; s->min_levels = std::min(min_levels, max_levels);
     if (n) {
         cudaError_t e = cudaMalloc(&s->d_inst, sizeof(DInstance) * n);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, sizeof(DBvhNode) * (size_t)n);           // a binary tree over n leaves has n - 1 nodes
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_bvh, BvhBlob::capacity(n));
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMalloc(&s->d_prev, sizeof(float) * 12 * n);
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_prev, o2w.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess && !nodes.empty()) e = cudaMemcpyAsync(s->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && bvh.bytes()) e = cudaMemcpyAsync(s->d_bvh, bvh.data(), bvh.bytes(), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMalloc(&s->d_boxes, sizeof(float4) * iboxes.size());
         if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_boxes, iboxes.data(), sizeof(float4) * iboxes.size(), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -946,7 +1056,7 @@ int32_t dust_scene_create(DustCtx *ctx, const DustInstance *instances, uint32_t 
     }
     s->trees = std::move(trees);
     s->o2w = std::move(o2w);
-    scene_set_view(s, root_box, root_ref);
+    scene_set_view(s, root_box, root_ref, bvh);
     *out = s;
     return DUST_OK;
 }
@@ -957,23 +1067,23 @@ int32_t dust_scene_update_transforms(DustCtx *ctx, DustScene *scene, const float
     if (n != scene->n_inst) return fail(ctx, DUST_ERR_INVALID_ARGUMENT, "one transform per instance");
     if (!n) return DUST_OK;
     std::vector<DInstance> inst;
-    std::vector<DBvhNode> nodes;
+    BvhBlob bvh;
     Box root_box{};
     int root_ref = -1;
     uint32_t max_levels = 3, min_levels = 4;
     std::vector<float4> iboxes;
-    const int32_t rc = scene_arrays(ctx, n, scene->trees.data(), obj2world, inst, nodes, root_box, root_ref, max_levels, min_levels, iboxes);
+    const int32_t rc = scene_arrays(ctx, n, scene->trees.data(), obj2world, inst, bvh, root_box, root_ref, max_levels, min_levels, iboxes);
     if (rc != DUST_OK) return rc;                                        // the scene is unchanged on error
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     // this frame's transforms become "last frame" for DustGBuffer.motion (PreviousFrameGlobalTransform, standard.rs:845-854)
     CU_TRY(ctx, cudaMemcpyAsync(scene->d_prev, scene->o2w.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(scene->d_inst, inst.data(), sizeof(DInstance) * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (!nodes.empty()) CU_TRY(ctx, cudaMemcpyAsync(scene->d_bvh, nodes.data(), sizeof(DBvhNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (bvh.bytes()) CU_TRY(ctx, cudaMemcpyAsync(scene->d_bvh, bvh.data(), bvh.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(scene->d_boxes, iboxes.data(), sizeof(float4) * iboxes.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));                     // stream-ordered after the frames in flight; host arrays die at return
     memcpy(scene->o2w.data(), obj2world, sizeof(float) * 12 * n);
-    scene->n_bvh = (uint32_t)nodes.size();
-    scene_set_view(scene, root_box, root_ref);
+    scene->n_bvh = (uint32_t)bvh.nodes.size();
+    scene_set_view(scene, root_box, root_ref, bvh);
     return DUST_OK;
 }
 

@@ -82,12 +82,14 @@ __device__ __forceinline__ float box_entry(float lx, float ly, float lz, float h
     return t0 <= t1 ? t0 : CUDART_INF_F;
 }
 
-// 1/d for the box tests only: a zero component gets a huge FINITE inverse so (lo - o) * inv is never 0 * inf
+// 1/d for the box tests only: a (near-)zero component gets a huge FINITE inverse so (lo - o) * inv is never 0 * inf.  The bound is
+// 1e24 (a component below 1e-24 moves the ray by less than the boxes' padding over any distance that matters): with it the wide
+// node's decode, fma(2^23 + q, step * inv, ..), cannot overflow for grid steps below 2^24 world units.
 __device__ __forceinline__ f3 cull_inverse(f3 rd)
 {
-    return mk3(fabsf(rd.x) < 1e-30f ? copysignf(1e30f, rd.x) : 1.0f / rd.x,
-               fabsf(rd.y) < 1e-30f ? copysignf(1e30f, rd.y) : 1.0f / rd.y,
-               fabsf(rd.z) < 1e-30f ? copysignf(1e30f, rd.z) : 1.0f / rd.z);
+    return mk3(fabsf(rd.x) < 1e-24f ? copysignf(1e24f, rd.x) : 1.0f / rd.x,
+               fabsf(rd.y) < 1e-24f ? copysignf(1e24f, rd.y) : 1.0f / rd.y,
+               fabsf(rd.z) < 1e-24f ? copysignf(1e24f, rd.z) : 1.0f / rd.z);
 }
 
 // ---------------------------------------------------------------------------------------- the cull
@@ -140,15 +142,20 @@ __device__ __forceinline__ void cull_from_list(const DSceneView &sc, const uint3
     }
 }
 
+#ifdef DUST_BINARY_BVH
 // room for one more expansion (2 candidates + 1 stack entry)?
 __device__ __forceinline__ bool cull_room(int sp, int nc) { return nc + 3 <= sp; }
+
+struct CullRay { f3 ro, winv; };
+__device__ __forceinline__ CullRay cull_ray(const DSceneView &, f3 ro, f3 winv) { CullRay r; r.ro = ro; r.winv = winv; return r; }
 
 // expand BVH node `pend` (both children: one 64-byte node); instances go to the candidate list, inner
 // nodes to `pend` / the stack
 template <bool STATS>
-__device__ __forceinline__ void cull_expand(const DSceneView &sc, f3 ro, f3 winv, float tmin, float tmax, uint32_t id_mask,
+__device__ __forceinline__ void cull_expand(const DSceneView &sc, const CullRay &cr, float tmin, float tmax, uint32_t id_mask,
                                             uint32_t *sm, int &sp, int &pend, int &nc, Counters &st)
 {
+    const f3 ro = cr.ro, winv = cr.winv;
     const float4 *n = reinterpret_cast<const float4 *>(sc.bvh + pend);
     const float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), e = __ldg(n + 3);
     if (STATS) st.dbg[13]++;
@@ -181,6 +188,84 @@ __device__ __forceinline__ void cull_expand(const DSceneView &sc, f3 ro, f3 winv
     if (next < 0 && sp < DUST_SCRATCH_WORDS) next = (int)sm[sp++ * DUST_THREADS];
     pend = next;
 }
+#else
+// room for one more expansion (up to DUST_BVH_WIDTH candidates + 1 stack entry)?
+__device__ __forceinline__ bool cull_room(int sp, int nc) { return nc + DUST_BVH_WIDTH + 1 <= sp; }
+
+// what a ray needs to test quantised boxes (device_layout.h "WIDE BVH"), computed once per ray:
+// t(q) = fma(2^23 + q, s, a) with s = step / d (exact scaling by a power of two) and a = (org - o) / d - 2^23 s
+struct CullRay {
+    float sx, sy, sz, ax, ay, az;
+    uint32_t nx, ny, nz;             // byte-permute selectors of the NEAR plane: {q.b0, q.b1, 0x00, 0x4B} = float 2^23 + lo for d > 0, .. + hi otherwise; far = near ^ 0x22
+};
+
+__device__ __forceinline__ CullRay cull_ray(const DSceneView &sc, f3 ro, f3 winv)
+{
+    CullRay r;
+    r.sx = sc.grid_step[0] * winv.x; r.sy = sc.grid_step[1] * winv.y; r.sz = sc.grid_step[2] * winv.z;
+    r.ax = __fmaf_rn(-8388608.0f, r.sx, (sc.grid_org[0] - ro.x) * winv.x);
+    r.ay = __fmaf_rn(-8388608.0f, r.sy, (sc.grid_org[1] - ro.y) * winv.y);
+    r.az = __fmaf_rn(-8388608.0f, r.sz, (sc.grid_org[2] - ro.z) * winv.z);
+    r.nx = winv.x > 0.0f ? 0x7410u : 0x7432u; r.ny = winv.y > 0.0f ? 0x7410u : 0x7432u; r.nz = winv.z > 0.0f ? 0x7410u : 0x7432u;
+    return r;
+}
+
+__device__ __forceinline__ float cull_plane(uint32_t q, uint32_t sel, float s, float a)
+{
+    return __fmaf_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, sel)), s, a);
+}
+
+// expand wide node `pend`: instances go to the candidate list, the first inner child that is hit becomes `pend`, the others
+// are ONE stack entry (node << 8 | mask of children still to visit), so the stack is as deep as the tree (the host keeps
+// that depth within the scratch column: dust_abi.cu build_wide).  The quantised boxes contain the padded instance boxes, so an
+// entry time from here is a lower bound like box_entry's.
+template <bool STATS>
+__device__ __forceinline__ void cull_expand(const DSceneView &sc, const CullRay &cr, float tmin, float tmax, uint32_t id_mask,
+                                            uint32_t *sm, int &sp, int &pend, int &nc, Counters &st)
+{
+    const uint4 *n = reinterpret_cast<const uint4 *>(sc.bvh) + 4u * (size_t)pend;
+    const uint4 X = __ldg(n), Y = __ldg(n + 1), Z = __ldg(n + 2), R = __ldg(n + 3);
+    if (STATS) st.dbg[13]++;
+    const uint32_t fx = cr.nx ^ 0x22u, fy = cr.ny ^ 0x22u, fz = cr.nz ^ 0x22u;
+    int next = -1;
+    uint32_t rem = 0;
+    // (the four tests first without a branch and ONE insertion loop over what they found was tried: wf_cull 0.66 ms against 0.56)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t qx = c == 0 ? X.x : (c == 1 ? X.y : (c == 2 ? X.z : X.w));
+        const uint32_t qy = c == 0 ? Y.x : (c == 1 ? Y.y : (c == 2 ? Y.z : Y.w));
+        const uint32_t qz = c == 0 ? Z.x : (c == 1 ? Z.y : (c == 2 ? Z.z : Z.w));
+        const int ch = (int)(c == 0 ? R.x : (c == 1 ? R.y : (c == 2 ? R.z : R.w)));
+        const float t0 = fmaxf(fmaxf(cull_plane(qx, cr.nx, cr.sx, cr.ax), cull_plane(qy, cr.ny, cr.sy, cr.ay)),
+                               fmaxf(cull_plane(qz, cr.nz, cr.sz, cr.az), tmin));
+        const float t1 = fminf(fminf(cull_plane(qx, fx, cr.sx, cr.ax), cull_plane(qy, fy, cr.sy, cr.ay)),
+                               fminf(cull_plane(qz, fz, cr.sz, cr.az), tmax));
+        if (!(t0 <= t1)) continue;
+        if (ch >= 0) {
+            if (next < 0) next = ch; else rem |= 1u << c;
+        } else {                                                      // instance: insertion sort by key
+            const uint32_t key = cand_key(t0, (uint32_t)~ch, id_mask);
+            int k = nc++;
+            if (STATS) st.dbg[14]++;
+            while (k > 0) {
+                const uint32_t prev = sm[(k - 1) * DUST_THREADS];
+                if (prev <= key) break;
+                sm[k * DUST_THREADS] = prev; --k;
+            }
+            sm[k * DUST_THREADS] = key;
+        }
+    }
+    if (rem) sm[--sp * DUST_THREADS] = ((uint32_t)pend << 8) | rem;
+    if (next < 0 && sp < DUST_SCRATCH_WORDS) {                          // pop: the lowest child still to visit of the top entry
+        const uint32_t e = sm[sp * DUST_THREADS];
+        const uint32_t c = (uint32_t)__ffs((int)(e & 0xFFu)) - 1u;
+        const uint32_t left = e & (e - 1u);                              // the low byte is non-zero: clears that child's bit
+        if (left & 0xFFu) sm[sp * DUST_THREADS] = left; else sp++;
+        next = __ldg(reinterpret_cast<const int *>(reinterpret_cast<const uint4 *>(sc.bvh) + 4u * (size_t)(e >> 8) + 3u) + c);
+    }
+    pend = next;
+}
+#endif
 
 // ------------------------------------------------------------------------------- the instance walk
 // State of one ray inside one instance.  Coordinates are in LEAF units (voxel >> 2): no consumer reads
@@ -380,6 +465,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     const uint32_t id_mask = (1u << sc.id_bits) - 1u;
     if (STATS && (threadIdx.x & 31u) == 0) st.dbg[15]++;
     const f3 winv = cull_inverse(rd);
+    const CullRay cr = cull_ray(sc, ro, winv);
     int sp = DUST_SCRATCH_WORDS, pend = -1, nc = 0;
     if (live) {
         // warp-uniform: a tile list (camera rays of one tile) replaces the BVH walk unless the tile overflowed its list
@@ -391,7 +477,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
     w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
     for (;;) {
         // ---- phase 1: cull
-        while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, ro, winv, tmin, cur, id_mask, sm, sp, pend, nc, st);
+        while (pend >= 0 && cull_room(sp, nc)) cull_expand<STATS>(sc, cr, tmin, cur, id_mask, sm, sp, pend, nc, st);
 
         // ---- phase 2: walk.  NEXT: enter the next candidate; WALK: one cell; LEAF: the 4x4x4 DDA.  Each trip
         // the warp votes and executes the ONE operation most lanes wait for (ties to the cheaper one).

@@ -221,9 +221,10 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
         const f3 winv = cull_inverse(rd);
         int sp, pend, nc;
         cull_begin(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc);
+        const CullRay cr = cull_ray(sc, ro, winv);
         bool trunc = false;
         while (pend >= 0 && cull_room(sp, nc)) {
-            cull_expand<STATS>(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc, st);
+            cull_expand<STATS>(sc, cr, tmin, tmax, id_mask, sm, sp, pend, nc, st);
             // The record holds WF_CANDS keys: drop the farthest ones as the walk goes (the list is sorted, and the last kept key only
             // moves nearer afterwards, so every dropped candidate starts at or behind it) — the scratch then always has room for
             // the BVH stack and the walk completes.
