@@ -650,8 +650,8 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 // One thread per ray of the closest queue of depth p.depth: apply the pending sun term, consume the
 // hit, emit the vertex's shadow and bounce rays.  The per-path arithmetic is frame_kernel's, in order.
 #ifndef DUST_SHADE_MIN_BLOCKS
-#define DUST_SHADE_MIN_BLOCKS 8
-#endif
+#define DUST_SHADE_MIN_BLOCKS 10              // 48 registers: the kernel waits for its dependent loads (hit -> instance -> leaf -> material -> palette), so
+#endif                                        // warps in flight beat registers: 6 / 8 / 10 / 12 CTAs per SM = 2 775 / 2 772 / 2 804 / 2 802 Mrays/s on configs[2]
 // All threads of a CTA of DUST_THREADS call this together (the emitted rays are compacted with warp votes and one
 // reservation per CTA); threads without a ray pass live = false.  `hw_in` != NULL: the hit record of slot i is passed in registers instead of read from p.hits
 // (the fused depth-0 kernel below).
@@ -786,6 +786,8 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_SHADE_MIN_BLOCKS) wf_shade(
     if (blockIdx.x * DUST_THREADS >= n) return;
     const uint32_t i = blockIdx.x * DUST_THREADS + threadIdx.x;
     Counters st = {};
+    // (Dealing the CTA's bounce rays out again, hits to the low threads and misses behind them, so that a warp runs either the sky
+    // path or the surface path, was tried: two barriers and 24 more bytes of spills cost what the shorter paths saved — 2 788 against 2 800 Mrays/s.)
     wf_shade_vertex<STATS>(p, i, i < n, nullptr, st);
     if (STATS) flush_counters(p.f.counters, st);
 }
