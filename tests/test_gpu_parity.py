@@ -504,6 +504,63 @@ def test_two_thousand_instances(teapot, host, oracle, ctx):
         _assert_radiance_close(g, of)
 
 
+def test_wide_bvh_far_from_origin_and_mixed_scales(teapot, host, oracle, ctx):
+    """The instance BVH's 16-bit quantisation grid (device_layout.h "WIDE BVH") under stress: a scene 65 000 units away from the
+    origin (the grid step is then bounded by the floats' own spacing, not by the extent), instances scaled 0.05x .. 20x and sheared,
+    boxes that touch and nest, rays from inside, from far outside, exactly axis-parallel ones, and rays that graze box faces.
+    The oracle visits every instance in a linear loop, so any candidate the quantised boxes lose shows up as a missing hit."""
+    from dust_b200 import scenes
+    from dust_b200.pipeline import Scene
+    rng = np.random.default_rng(77)
+    base = np.array([65000.0, -30000.0, 12000.0], np.float32)
+    mats = []
+    for k in range(300):
+        s = np.float32([0.05, 0.3, 1.0, 1.0, 4.0, 20.0][k % 6])
+        A = np.eye(3, dtype=np.float32) * s
+        if k % 5 == 0:
+            A[0, 1] = 0.3 * s; A[2, 0] = -0.2 * s                # shear
+        if k % 7 == 0:
+            A = A[[1, 2, 0]]                                     # an axis permutation (rotation)
+        t = base + rng.integers(-900, 900, 3).astype(np.float32) * np.float32(0.5 if k % 2 else 3.0)
+        if k % 11 == 0 and mats:
+            t = mats[-1].reshape(3, 4)[:, 3] + np.float32([256.0 * float(s), 0.0, 0.0])   # touching / nested neighbours
+        mats.append(np.concatenate([A, t[:, None]], axis=1).astype(np.float32).reshape(12))
+    mid = teapot.ovox.instances[0][0]
+    gscene = Scene(ctx, [(m, teapot.loaded.trees[mid]) for m in mats])
+    om = teapot.omodels[mid]
+    oscene = oracle.Scene([(m, om.tree._h, om.materials, teapot.ovox.palette) for m in mats])
+    n = 120_000
+    rays = scenes.ray_batch(n, 1.0, seed=78)
+    span = np.float32([6000.0, 6000.0, 6000.0])
+    rays["o"] = base - span / 2 + rays["o"] * span
+    far = slice(0, n // 4)                                       # a quarter start far outside and aim into the scene
+    rays["o"][far] = base + (rays["o"][far] - base) * np.float32(40.0)
+    aim = base + (rng.random((n // 4, 3)).astype(np.float32) - 0.5) * np.float32(3000.0)
+    d = aim - rays["o"][far]
+    rays["d"][far] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    ax = slice(n // 4, n // 4 + n // 8)                          # exactly axis-parallel rays (two zero components)
+    dax = np.zeros((n // 8, 3), np.float32)
+    dax[np.arange(n // 8), rng.integers(0, 3, n // 8)] = rng.choice(np.float32([-1.0, 1.0]), n // 8)
+    rays["d"][ax] = dax
+    graze = slice(n // 2, n // 2 + n // 8)                       # rays in the plane of a box face of some instance
+    for j, i in enumerate(range(graze.start, graze.stop)):
+        M = mats[j % len(mats)].reshape(3, 4)
+        rays["o"][i] = M[:, 3] + np.float32([-50.0, 0.0, 7.0])
+        rays["d"][i] = np.float32([1.0, 0.0, 1e-3 * (j % 5)])
+    o, _ = oscene.trace_rays(rays)
+    hit = o["instance"] != 0xFFFFFFFF
+    assert 0.05 < hit.mean() < 0.95 and hit[far].any() and hit[ax].any()
+    assert np.array_equal(gscene.trace_rays(rays).view(np.uint32), o.view(np.uint32))
+    W, H = 128, 72
+    cam = host.camera_look_at(tuple(base + np.float32([2500.0, 1800.0, 2200.0])), tuple(base), width=W, height=H)
+    sky = host.sunlight_bake()
+    for pipeline in PIPELINES:
+        g = gscene.trace(cam, sky, W, H, spp=2, max_bounces=1, seed=3, hits=True, pipeline=pipeline)
+        of = oscene.render(cam, sky, W, H, spp=2, max_bounces=1, seed=3)
+        _assert_hits_equal(g, of)
+        _assert_radiance_close(g, of)
+
+
 def test_ray_batch_rough_block_hits(castle_small, teapot, host, oracle, ctx):
     """DUST_RAYS_ROUGH (final_gather/rough.rint): block-granular leaves, far-field ray interval [8, far], against the oracle bit for
     bit — multi-instance scene (pre-cull + persistent lanes + slow path) and a single-instance one (no cull pass)."""
