@@ -172,4 +172,15 @@ __global__ void __launch_bounds__(64) vb_emit_root(const uint32_t *__restrict__ 
     }
 }
 
+// The dense 4^3-node table of a 3-level tree (device_layout.h DInstance::dense_mids): cell i of the root gets the word of its child, or zero.
+__global__ void __launch_bounds__(256) vb_dense_mids(const DNode16 *root, const uint4 *mids, uint4 *dense)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;                 // 16 CTAs: 4096 cells
+    const uint4 q = root->word[i >> 6];
+    const uint32_t b = i & 63u;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((((uint64_t)q.y << 32) | q.x) >> b & 1ull) v = mids[q.z + (uint32_t)__popcll(((((uint64_t)q.y << 32) | q.x) << (63u - b))) - 1u];
+    dense[i] = v;
+}
+
 }  // namespace dust

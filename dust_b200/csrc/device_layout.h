@@ -24,6 +24,10 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+#if !defined(DUST_NO_DENSE_MIDS) && !defined(DUST_TMA_TOP)
+#define DUST_DENSE_MIDS 1            // walk 3-level trees through DInstance::dense_mids (below)
+#endif
+
 namespace dust {
 
 struct alignas(16) DNode16 {
@@ -45,7 +49,11 @@ struct alignas(16) DInstance {
     const uchar4 *palette_raw;     // 256 x RGBA8 as uploaded (G-buffer albedo)
     float o2w[9];                  // linear part of object -> world (normals)
     float o2w_t[3];                // its translation (block centres of the far-field gather, final_gather.rchit:42)
-    uint32_t _pad1[2];
+    // 3-level trees: the root 16^3 node's 4096 cells with their 4^3 node words filled in ({mask lo, mask hi, first leaf slot, 0};
+    // all zero = no child): one load answers "is there a 4^3 node here" AND delivers it, where the compact layout needs the
+    // root word, a bit test, a rank and a second, dependent load.  A derived table (64 KB per tree, built on the device from the
+    // blob by vb_dense_mids), NOT part of the blob contract of dust_tree_layout / dust_tree_download.  NULL for 4-level trees.
+    const uint4 *dense_mids;
 };
 static_assert(sizeof(DInstance) == 176, "DInstance layout");
 

@@ -691,6 +691,19 @@ int32_t dust_ctx_synchronize(DustCtx *ctx)
 
 const char *dust_last_error_string(const DustCtx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// 3-level trees get the dense 4^3-node table (a derived, separate allocation: the blob contract is untouched)
+static cudaError_t tree_make_dense(DustCtx *ctx, DustTree *t)
+{
+    if (t->n_levels != 3) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&t->dense_mids, 4096 * sizeof(uint4));
+    if (e != cudaSuccess) return e;
+    vb_dense_mids<<<16, 256, 0, ctx->stream>>>(t->n16, t->mids, t->dense_mids);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(t->dense_mids); t->dense_mids = nullptr; }
+    return e;
+}
+
 int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
 {
     if (!ctx || !desc || !out) return DUST_ERR_INVALID_ARGUMENT;
@@ -759,6 +772,8 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
     t->n_leaves = r.leaves.size(); t->n_mids = r.mids.size(); t->n_n16 = r.n16.size(); t->n_materials = desc->n_materials;
     if (r.leaves.empty()) { for (int a = 0; a < 3; a++) { t->bmin[a] = 0; t->bmax[a] = 0; } }
     else for (int a = 0; a < 3; a++) { t->bmin[a] = r.bmin[a]; t->bmax[a] = r.bmax[a]; }
+    e = tree_make_dense(ctx, t);
+    if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, e == cudaErrorMemoryAllocation ? DUST_ERR_OUT_OF_MEMORY : DUST_ERR_CUDA, cudaGetErrorString(e)); }
     *out = t;
     return DUST_OK;
 }
@@ -860,6 +875,8 @@ int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n
     t->n_levels = 3;
     t->n_leaves = h_counts.n_leaves; t->n_mids = h_counts.n_mids; t->n_n16 = 1; t->n_materials = h_counts.n_materials;
     for (int a = 0; a < 3; a++) { t->bmin[a] = h_counts.n_leaves ? h_counts.bmin[a] : 0; t->bmax[a] = h_counts.n_leaves ? h_counts.bmax[a] : 0; }
+    e = tree_make_dense(ctx, t);
+    if (e != cudaSuccess) { cudaFree(t->blob); delete t; return fail(ctx, e == cudaErrorMemoryAllocation ? DUST_ERR_OUT_OF_MEMORY : DUST_ERR_CUDA, cudaGetErrorString(e)); }
     *out = t;
     return DUST_OK;
 }
@@ -892,6 +909,7 @@ int32_t dust_tree_destroy(DustCtx *ctx, DustTree *tree)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (tree->blob) cudaFree(tree->blob);
+    if (tree->dense_mids) cudaFree(tree->dense_mids);
     delete tree;
     return DUST_OK;
 }
@@ -952,7 +970,7 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin; d.palette_raw = t->palette_raw;
         // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
         for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
-        for (uint32_t &w : d._pad1) w = 0;
+        d.dense_mids = t->dense_mids;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove

@@ -327,6 +327,10 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     w.topw = w.n16->word; w.topb = w.blocks;
 #endif
     if (NL == 0) w.four = bw.w == 4u;
+#ifdef DUST_DENSE_MIDS
+    // 3-level trees are walked through the dense table of their root's 4096 cells (DInstance::dense_mids): `mids` IS that table
+    if (NL == 3 || (NL == 0 && !w.four)) w.mids = in.dense_mids;
+#endif
     if (NL == 3 || (NL == 0 && !w.four)) { const uint2 b = __ldg(w.blocks); w.blk_lo = b.x; w.blk_hi = b.y; }
     w.have_mid = false;
     w.L4 = 0;
@@ -406,14 +410,25 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
         const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
         if (STATS) { st.mask_words++; st.mask_words_strict++; }
-#ifdef DUST_TMA_TOP
-        const uint4 q = four ? __ldg(&node->word[ridx >> 6]) : w.topw[ridx >> 6];
-#else
-        const uint4 q = __ldg(&node->word[ridx >> 6]);
+        uint4 mid;
+#ifdef DUST_DENSE_MIDS
+        if (!four) {
+            // the cell's 4^3 node word straight from the dense table: zero = no child (a 4^3 node that exists has a leaf).  Counted
+            // like the compact look-up it replaces (the algorithmic words are a property of the walk, not of the table).
+            mid = __ldg(&w.mids[ridx]);
+            if ((mid.x | mid.y) == 0u) { w.L4 = 4; return WS_WALK; }
+        } else
 #endif
-        const uint32_t b = ridx & 63u;
-        if (!bit64(q.x, q.y, b)) { w.L4 = 4; return WS_WALK; }
-        const uint4 mid = __ldg(&w.mids[q.z + rank64(q.x, q.y, b)]);
+        {
+#ifdef DUST_TMA_TOP
+            const uint4 q = four ? __ldg(&node->word[ridx >> 6]) : w.topw[ridx >> 6];
+#else
+            const uint4 q = __ldg(&node->word[ridx >> 6]);
+#endif
+            const uint32_t b = ridx & 63u;
+            if (!bit64(q.x, q.y, b)) { w.L4 = 4; return WS_WALK; }
+            mid = __ldg(&w.mids[q.z + rank64(q.x, q.y, b)]);
+        }
         if (STATS) st.mask_words_strict++;                              // a mid node entered
         w.mid_lo = mid.x; w.mid_hi = mid.y; w.mid_base = mid.z;
         w.have_mid = true;
