@@ -59,7 +59,8 @@ struct DustTree {
     const uint8_t *materials = nullptr;
     const float4 *palette_lin = nullptr;
     const uchar4 *palette_raw = nullptr;
-    uint4 *dense_mids = nullptr;     // 3-level trees: own allocation of 4096 words (device_layout.h DInstance::dense_mids)
+    uint4 *dense_root = nullptr;     // own allocation of 4096 words (device_layout.h DInstance::dense_root)
+    uint2 root_blocks = { 0u, 0u };  // host copy of blocks[0]
     uint64_t n_leaves = 0, n_mids = 0, n_n16 = 0, n_materials = 0;
     int32_t bmin[3] = { 0, 0, 0 }, bmax[3] = { 0, 0, 0 };   // occupied bounds in object voxels
 };

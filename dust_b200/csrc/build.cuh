@@ -172,14 +172,19 @@ __global__ void __launch_bounds__(64) vb_emit_root(const uint32_t *__restrict__ 
     }
 }
 
-// The dense 4^3-node table of a 3-level tree (device_layout.h DInstance::dense_mids): cell i of the root gets the word of its child, or zero.
-__global__ void __launch_bounds__(256) vb_dense_mids(const DNode16 *root, const uint4 *mids, uint4 *dense)
+// The dense root table of a tree (device_layout.h DInstance::dense_root): cell i of the root gets what the walk wants of its child, or zero.
+__global__ void __launch_bounds__(256) vb_dense_root(const DNode16 *n16, const uint2 *blocks, const uint4 *mids, uint32_t n_levels, uint4 *dense)
 {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;                 // 16 CTAs: 4096 cells
-    const uint4 q = root->word[i >> 6];
+    const uint4 q = n16[0].word[i >> 6];
+    const uint64_t m = ((uint64_t)q.y << 32) | q.x;
     const uint32_t b = i & 63u;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if ((((uint64_t)q.y << 32) | q.x) >> b & 1ull) v = mids[q.z + (uint32_t)__popcll(((((uint64_t)q.y << 32) | q.x) << (63u - b))) - 1u];
+    if ((m >> b) & 1ull) {
+        const uint32_t child = q.z + (uint32_t)__popcll(m << (63u - b)) - 1u;
+        if (n_levels == 3) v = mids[child];
+        else { const uint2 cb = blocks[child]; v = make_uint4(cb.x, cb.y, child, 0u); }
+    }
     dense[i] = v;
 }
 

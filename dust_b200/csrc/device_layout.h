@@ -25,7 +25,7 @@
 #include <cuda_runtime.h>
 
 #if !defined(DUST_NO_DENSE_MIDS) && !defined(DUST_TMA_TOP)
-#define DUST_DENSE_MIDS 1            // walk 3-level trees through DInstance::dense_mids (below)
+#define DUST_DENSE_MIDS 1            // walk the root level through DInstance::dense_root (below)
 #endif
 
 namespace dust {
@@ -49,13 +49,17 @@ struct alignas(16) DInstance {
     const uchar4 *palette_raw;     // 256 x RGBA8 as uploaded (G-buffer albedo)
     float o2w[9];                  // linear part of object -> world (normals)
     float o2w_t[3];                // its translation (block centres of the far-field gather, final_gather.rchit:42)
-    // 3-level trees: the root 16^3 node's 4096 cells with their 4^3 node words filled in ({mask lo, mask hi, first leaf slot, 0};
-    // all zero = no child): one load answers "is there a 4^3 node here" AND delivers it, where the compact layout needs the
-    // root word, a bit test, a rank and a second, dependent load.  A derived table (64 KB per tree, built on the device from the
-    // blob by vb_dense_mids), NOT part of the blob contract of dust_tree_layout / dust_tree_download.  NULL for 4-level trees.
-    const uint4 *dense_mids;
+    // dense_root: the root node's 4096 cells, dense (a derived table of 64 KB per tree, built on the device from the blob by vb_dense_root; NOT
+    // part of the blob contract of dust_tree_layout / dust_tree_download).  One load answers "is there a child" AND delivers what
+    // the walk wants of it, where the compact layout needs the root word, a bit test, a rank and a second, dependent load:
+    //   3 levels: the child 4^3 node's word {mask lo, mask hi, first leaf slot, 0}
+    //   4 levels: {block mask lo, block mask hi of the child 16^3 node, its index, 0}
+    // All zero = no child (a node that exists has a non-empty mask).
+    uint32_t _pad2[2];
+    const uint4 *dense_root;       //                                                      (128 bit with root_blocks)
+    uint2 root_blocks;             // block mask of the root node (blocks[0]): in registers from walk_enter on, no load through `blocks`
 };
-static_assert(sizeof(DInstance) == 176, "DInstance layout");
+static_assert(sizeof(DInstance) == 192, "DInstance layout");
 
 // Binary BVH over instance world boxes (replaces the TLAS).  A node holds the padded boxes of BOTH
 // children, so one node fetch (4 x 128 bit) decides both.  child >= 0: inner node index;

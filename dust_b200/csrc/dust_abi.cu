@@ -691,16 +691,16 @@ int32_t dust_ctx_synchronize(DustCtx *ctx)
 
 const char *dust_last_error_string(const DustCtx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-// 3-level trees get the dense 4^3-node table (a derived, separate allocation: the blob contract is untouched)
+// every tree gets the dense root table and a host copy of the root's block mask (derived data: the blob contract is untouched)
 static cudaError_t tree_make_dense(DustCtx *ctx, DustTree *t)
 {
-    if (t->n_levels != 3) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&t->dense_mids, 4096 * sizeof(uint4));
+    cudaError_t e = cudaMalloc(&t->dense_root, 4096 * sizeof(uint4));
     if (e != cudaSuccess) return e;
-    vb_dense_mids<<<16, 256, 0, ctx->stream>>>(t->n16, t->mids, t->dense_mids);
+    vb_dense_root<<<16, 256, 0, ctx->stream>>>(t->n16, t->blocks, t->mids, t->n_levels, t->dense_root);
     e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&t->root_blocks, t->blocks, sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cudaFree(t->dense_mids); t->dense_mids = nullptr; }
+    if (e != cudaSuccess) { cudaFree(t->dense_root); t->dense_root = nullptr; }
     return e;
 }
 
@@ -909,7 +909,7 @@ int32_t dust_tree_destroy(DustCtx *ctx, DustTree *tree)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (tree->blob) cudaFree(tree->blob);
-    if (tree->dense_mids) cudaFree(tree->dense_mids);
+    if (tree->dense_root) cudaFree(tree->dense_root);
     delete tree;
     return DUST_OK;
 }
@@ -970,7 +970,7 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin; d.palette_raw = t->palette_raw;
         // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
         for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
-        d.dense_mids = t->dense_mids;
+        d.dense_root = t->dense_root; d.root_blocks = t->root_blocks; d._pad2[0] = d._pad2[1] = 0;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);
         // world box of the occupied object-space bounds, padded so that culling can never remove

@@ -277,13 +277,17 @@ struct Walk {
     int L4;                          // != 0: the cell of that edge (leaf units) containing (jx,jy,jz) is empty / done: leave it first
     float t_exit, t_box;             // inclusive end of the walk (box exit or padded tmax); exit time of the occupied bounds
     const DNode16 *n16;
+#ifdef DUST_DENSE_MIDS
+    const uint4 *dense;              // DInstance::dense_root
+#else
     const uint2 *blocks;
+#endif
 #ifdef DUST_TMA_TOP
     const uint4 *topw;               // 64 words of the root 16^3 node: global, or the CTA's TMA-staged shared copy (generic loads)
     const uint2 *topb;               // its block mask (4-level trees)
 #endif
     const uint4 *mids, *leaves;
-    uint32_t blk_lo, blk_hi;         // block mask of the 16^3 node above the mids (kept in registers for 3-level trees)
+    uint32_t blk_lo, blk_hi;         // block mask of the ROOT node (of the 16^3 node above the mids only for 3-level trees)
     uint32_t mid_lo, mid_hi, mid_base;
     uint32_t inst, leaf_i;
     bool have_mid;                   // the 4^3 node of the current 16-cell is in registers
@@ -322,16 +326,21 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     w.n16 = reinterpret_cast<const DNode16 *>(p01.x);
     w.mids = reinterpret_cast<const uint4 *>(p01.y);
     w.leaves = in.leaves;
+    if (NL == 0) w.four = bw.w == 4u;
+#ifdef DUST_DENSE_MIDS
+    // the root level is walked through the dense table (DInstance::dense_root) and the root's block mask comes with the instance
+    {
+        const ulonglong2 dr = __ldg(reinterpret_cast<const ulonglong2 *>(&in.dense_root));
+        w.dense = reinterpret_cast<const uint4 *>(dr.x);
+        w.blk_lo = (uint32_t)dr.y; w.blk_hi = (uint32_t)(dr.y >> 32);
+    }
+#else
     w.blocks = in.blocks;
 #ifdef DUST_TMA_TOP
     w.topw = w.n16->word; w.topb = w.blocks;
 #endif
-    if (NL == 0) w.four = bw.w == 4u;
-#ifdef DUST_DENSE_MIDS
-    // 3-level trees are walked through the dense table of their root's 4096 cells (DInstance::dense_mids): `mids` IS that table
-    if (NL == 3 || (NL == 0 && !w.four)) w.mids = in.dense_mids;
-#endif
     if (NL == 3 || (NL == 0 && !w.four)) { const uint2 b = __ldg(w.blocks); w.blk_lo = b.x; w.blk_hi = b.y; }
+#endif
     w.have_mid = false;
     w.L4 = 0;
     return true;
@@ -384,6 +393,19 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (four) {
             // (keeping the 16^3 node of the current 256-cell in registers, like the 4^3 node below, was tried:
             //  these words are L1 hits and the extra state cost more than the three loads — config 5 lost 9 %)
+#ifdef DUST_DENSE_MIDS
+            if (STATS) st.mask_words++;
+            if (!bit64(w.blk_lo, w.blk_hi, ((uint32_t)((jx >> 8) & 3) << 4) | ((uint32_t)((jy >> 8) & 3) << 2) | (uint32_t)((jz >> 8) & 3))) { w.L4 = 256; return WS_WALK; }
+            const uint32_t tidx = ((uint32_t)(jx >> 6) << 8) | ((uint32_t)(jy >> 6) << 4) | (uint32_t)(jz >> 6);
+            // the root cell's entry of the dense table: the child 16^3 node's block mask and index, zero = no child.  Counted like
+            // the compact look-up it replaces (root word, child link).
+            const uint4 e = __ldg(&w.dense[tidx]);
+            if (STATS) { st.mask_words++; st.mask_words_strict++; }
+            if ((e.x | e.y) == 0u) { w.L4 = 64; return WS_WALK; }
+            if (STATS) st.child_ptrs++;
+            node = w.n16 + e.z;
+            blo = e.x; bhi = e.y;
+#else
 #ifdef DUST_TMA_TOP
             const uint2 tb = *w.topb;
 #else
@@ -405,6 +427,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
             node = w.n16 + ni;
             const uint2 cb = __ldg(w.blocks + ni);
             blo = cb.x; bhi = cb.y;
+#endif
         }
         if (STATS) st.mask_words++;
         if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
@@ -415,7 +438,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
         if (!four) {
             // the cell's 4^3 node word straight from the dense table: zero = no child (a 4^3 node that exists has a leaf).  Counted
             // like the compact look-up it replaces (the algorithmic words are a property of the walk, not of the table).
-            mid = __ldg(&w.mids[ridx]);
+            mid = __ldg(&w.dense[ridx]);
             if ((mid.x | mid.y) == 0u) { w.L4 = 4; return WS_WALK; }
         } else
 #endif
