@@ -37,9 +37,12 @@ static_assert(sizeof(DNode16) == 1024, "DNode16 layout");
 
 struct alignas(16) DInstance {
     float w2o[12];                 // world -> object, row-major 3x4                       (3 x 128 bit)
-    // occupied bounds in LEAF units (voxel / 4), per axis: lo | (size << 16); the walk is clipped to it
-    uint32_t bounds[3];
-    uint32_t n_levels;             // 3: (4,2,2)   4: (4,4,2,2)                            (128 bit with bounds)
+    // occupied bounds in voxels (multiples of 4: whole leaves), as floats: the walk is clipped to them and only ever wants them as
+    // floats (plane times, the clamp of the entry point) — packed integers cost 21 unpack / convert instructions per instance entered
+    float bounds_lo[3];
+    uint32_t n_levels;             // 3: (4,2,2)   4: (4,4,2,2)                            (128 bit with bounds_lo)
+    float bounds_hi[3];
+    uint32_t _pad1;                //                                                      (128 bit with bounds_hi)
     const DNode16 *n16;            // [0] = root; for 4 levels [1..] = the 16^3 nodes below it
     const uint4 *mids;             // 4^3 internal nodes                                   (128 bit with n16)
     const uint4 *leaves;
@@ -59,7 +62,7 @@ struct alignas(16) DInstance {
     const uint4 *dense_root;       //                                                      (128 bit with root_blocks)
     uint2 root_blocks;             // block mask of the root node (blocks[0]): in registers from walk_enter on, no load through `blocks`
 };
-static_assert(sizeof(DInstance) == 192, "DInstance layout");
+static_assert(sizeof(DInstance) == 208, "DInstance layout");
 
 // Binary BVH over instance world boxes (replaces the TLAS).  A node holds the padded boxes of BOTH
 // children, so one node fetch (4 x 128 bit) decides both.  child >= 0: inner node index;

@@ -969,7 +969,8 @@ static int32_t scene_arrays(DustCtx *ctx, uint32_t n, const DustTree *const *tre
         d.n_levels = t->n_levels;
         d.n16 = t->n16; d.blocks = t->blocks; d.mids = t->mids; d.leaves = t->leaves; d.materials = t->materials; d.palette_lin = t->palette_lin; d.palette_raw = t->palette_raw;
         // occupied bounds are multiples of 4 voxels (whole leaves): leaf units, lo | size << 16
-        for (int a = 0; a < 3; a++) d.bounds[a] = (uint32_t)(t->bmin[a] >> 2) | ((uint32_t)((t->bmax[a] - t->bmin[a]) >> 2) << 16);
+        for (int a = 0; a < 3; a++) { d.bounds_lo[a] = (float)t->bmin[a]; d.bounds_hi[a] = (float)t->bmax[a]; }
+        d._pad1 = 0;
         d.dense_root = t->dense_root; d.root_blocks = t->root_blocks; d._pad2[0] = d._pad2[1] = 0;
         max_levels = std::max(max_levels, t->n_levels);
         min_levels = std::min(min_levels, t->n_levels);

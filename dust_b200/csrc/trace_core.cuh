@@ -306,27 +306,27 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     const DInstance &in = sc.inst[inst];
     object_ray(in, ro, rd, w.o, w.d);
     w.inv = mk3(1.0f / w.d.x, 1.0f / w.d.y, 1.0f / w.d.z);
-    const uint4 bw = __ldg(reinterpret_cast<const uint4 *>(in.bounds));
-    const int bx0 = (int)(bw.x & 0xFFFFu) << 2, by0 = (int)(bw.y & 0xFFFFu) << 2, bz0 = (int)(bw.z & 0xFFFFu) << 2;
-    const int bx1 = bx0 + ((int)(bw.x >> 16) << 2), by1 = by0 + ((int)(bw.y >> 16) << 2), bz1 = bz0 + ((int)(bw.z >> 16) << 2);
+    const float4 blo = __ldg(reinterpret_cast<const float4 *>(in.bounds_lo)), bhi = __ldg(reinterpret_cast<const float4 *>(in.bounds_hi));
     // plane times are (plane - o) * inv: difference first, plane*inv - o*inv would cancel (|o/d| >> t)
-    const float t0x = ((float)bx0 - w.o.x) * w.inv.x, t0y = ((float)by0 - w.o.y) * w.inv.y, t0z = ((float)bz0 - w.o.z) * w.inv.z;
-    const float t1x = ((float)bx1 - w.o.x) * w.inv.x, t1y = ((float)by1 - w.o.y) * w.inv.y, t1z = ((float)bz1 - w.o.z) * w.inv.z;
+    const float t0x = (blo.x - w.o.x) * w.inv.x, t0y = (blo.y - w.o.y) * w.inv.y, t0z = (blo.z - w.o.z) * w.inv.z;
+    const float t1x = (bhi.x - w.o.x) * w.inv.x, t1y = (bhi.y - w.o.y) * w.inv.y, t1z = (bhi.z - w.o.z) * w.inv.z;
     const float t_enter = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
     // walk a hair past tmax (acceptance stays exact): DESIGN.md "Traversal semantics"
     const float tmax_pad = cur + (fabsf(cur) * 3.814697265625e-06f + 9.5367431640625e-07f);
     w.t_box = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
     w.t_exit = fminf(w.t_box, tmax_pad);
-    if (!(t_enter <= w.t_exit) || bx1 <= bx0) return false;
-    const int ix = __float2int_rd(__fmaf_rn(w.d.x, t_enter, w.o.x));
-    const int iy = __float2int_rd(__fmaf_rn(w.d.y, t_enter, w.o.y));
-    const int iz = __float2int_rd(__fmaf_rn(w.d.z, t_enter, w.o.z));
-    w.jx = min(max(ix, bx0), bx1 - 1) >> 2; w.jy = min(max(iy, by0), by1 - 1) >> 2; w.jz = min(max(iz, bz0), bz1 - 1) >> 2;
+    if (!(t_enter <= w.t_exit) || bhi.x <= blo.x) return false;
+    // entry cell = floor(fma(d, t_enter, o)) clamped into the bounds: clamping the float to [lo, hi - 1] before the floor gives the
+    // same integer (lo, hi are integers below 2^24; floor is monotone), and a NaN goes to lo either way
+    const int ix = __float2int_rd(fminf(fmaxf(__fmaf_rn(w.d.x, t_enter, w.o.x), blo.x), bhi.x - 1.0f));
+    const int iy = __float2int_rd(fminf(fmaxf(__fmaf_rn(w.d.y, t_enter, w.o.y), blo.y), bhi.y - 1.0f));
+    const int iz = __float2int_rd(fminf(fmaxf(__fmaf_rn(w.d.z, t_enter, w.o.z), blo.z), bhi.z - 1.0f));
+    w.jx = ix >> 2; w.jy = iy >> 2; w.jz = iz >> 2;
     const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2 *>(&in.n16));
     w.n16 = reinterpret_cast<const DNode16 *>(p01.x);
     w.mids = reinterpret_cast<const uint4 *>(p01.y);
     w.leaves = in.leaves;
-    if (NL == 0) w.four = bw.w == 4u;
+    if (NL == 0) w.four = __float_as_uint(blo.w) == 4u;
 #ifdef DUST_DENSE_MIDS
     // the root level is walked through the dense table (DInstance::dense_root) and the root's block mask comes with the instance
     {
@@ -381,6 +381,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
             nz = tz <= t_next ? (pz_ ? cz + L4 : cz - 1) : rz;
         }
         // the cached 4^3 node survives a step that stays inside its 16-cell
+        // (with the dense root table a 4^3 node word is one L1 hit away; NOT keeping it in registers measured the same: 2 884 against 2 880 Mrays/s)
         w.have_mid = w.have_mid && (((uint32_t)((nx ^ w.jx) | (ny ^ w.jy) | (nz ^ w.jz)) >> 2) == 0u);
         w.jx = nx; w.jy = ny; w.jz = nz;
         w.L4 = 0;
