@@ -179,10 +179,15 @@ __global__ void __launch_bounds__(256) vb_dense_root(const DNode16 *n16, const u
     const uint4 q = n16[0].word[i >> 6];
     const uint64_t m = ((uint64_t)q.y << 32) | q.x;
     const uint32_t b = i & 63u;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    // 3 levels: w = 1 marks a cell whose whole 4x4x4 block of cells is empty (the walk leaves such a block as one cell of 4x the edge
+    // and would otherwise ask the root's block mask first)
+    const uint2 rb = blocks[0];
+    const uint32_t blk = ((i >> 10) << 4) | (((i >> 6) & 3u) << 2) | ((i >> 2) & 3u);
+    const bool block_empty = !(((((uint64_t)rb.y << 32) | rb.x) >> blk) & 1ull);
+    uint4 v = make_uint4(0u, 0u, 0u, n_levels == 3 && block_empty ? 1u : 0u);
     if ((m >> b) & 1ull) {
         const uint32_t child = q.z + (uint32_t)__popcll(m << (63u - b)) - 1u;
-        if (n_levels == 3) v = mids[child];
+        if (n_levels == 3) { v = mids[child]; v.w = 0u; }
         else { const uint2 cb = blocks[child]; v = make_uint4(cb.x, cb.y, child, 0u); }
     }
     dense[i] = v;

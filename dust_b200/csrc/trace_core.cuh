@@ -332,7 +332,7 @@ __device__ __forceinline__ bool walk_enter(const DSceneView &sc, Walk &w, uint32
     {
         const ulonglong2 dr = __ldg(reinterpret_cast<const ulonglong2 *>(&in.dense_root));
         w.dense = reinterpret_cast<const uint4 *>(dr.x);
-        w.blk_lo = (uint32_t)dr.y; w.blk_hi = (uint32_t)(dr.y >> 32);
+        w.blk_lo = (uint32_t)dr.y; w.blk_hi = (uint32_t)(dr.y >> 32);     // (only 4-level trees ask it: the table answers for 3-level ones)
     }
 #else
     w.blocks = in.blocks;
@@ -430,20 +430,28 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
             blo = cb.x; bhi = cb.y;
 #endif
         }
-        if (STATS) st.mask_words++;
-        if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
-        const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
-        if (STATS) { st.mask_words++; st.mask_words_strict++; }
         uint4 mid;
 #ifdef DUST_DENSE_MIDS
         if (!four) {
-            // the cell's 4^3 node word straight from the dense table: zero = no child (a 4^3 node that exists has a leaf).  Counted
-            // like the compact look-up it replaces (the algorithmic words are a property of the walk, not of the table).
+            // the cell's entry of the dense root table: the 4^3 node's word; zero = no child (a 4^3 node that exists has a leaf), and
+            // then w says whether the whole 4x4x4 block of cells is empty (what the root's block mask would have said first).
+            // Counted like the compact look-ups it replaces (the algorithmic words are a property of the walk, not of the table).
+            const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
             mid = __ldg(&w.dense[ridx]);
-            if ((mid.x | mid.y) == 0u) { w.L4 = 4; return WS_WALK; }
+            if (STATS) st.mask_words++;
+            if ((mid.x | mid.y) == 0u) {
+                if (STATS && !mid.w) { st.mask_words++; st.mask_words_strict++; }
+                w.L4 = mid.w ? 16 : 4;
+                return WS_WALK;
+            }
+            if (STATS) { st.mask_words++; st.mask_words_strict++; }
         } else
 #endif
         {
+            if (STATS) st.mask_words++;
+            if (!bit64(blo, bhi, ((uint32_t)((jx >> 4) & 3) << 4) | ((uint32_t)((jy >> 4) & 3) << 2) | (uint32_t)((jz >> 4) & 3))) { w.L4 = 16; return WS_WALK; }
+            const uint32_t ridx = ((uint32_t)((jx >> 2) & 15) << 8) | ((uint32_t)((jy >> 2) & 15) << 4) | (uint32_t)((jz >> 2) & 15);
+            if (STATS) { st.mask_words++; st.mask_words_strict++; }
 #ifdef DUST_TMA_TOP
             const uint4 q = four ? __ldg(&node->word[ridx >> 6]) : w.topw[ridx >> 6];
 #else
