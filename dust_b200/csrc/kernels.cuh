@@ -18,7 +18,7 @@ namespace dust {
 #define DUST_FRAME_MIN_BLOCKS 5          // frame_kernel: 96 registers, no spills
 #endif
 #ifndef DUST_MIN_BLOCKS
-#define DUST_MIN_BLOCKS 6                // wf_trace
+#define DUST_MIN_BLOCKS 7                // wf_trace: 72 registers (6 / 7 / 8 CTAs per SM: 2 939 / 2 971 / 2 952 Mrays/s on configs[2] once the dense root table had freed registers)
 #endif
 
 struct FrameParams {

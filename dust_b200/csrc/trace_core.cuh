@@ -42,6 +42,9 @@ struct Counters {
 #ifndef DUST_WALK_REPS
 #define DUST_WALK_REPS 2                       // cells a lane may walk per voted WALK operation (persistent tracer)
 #endif
+#ifndef DUST_FAST_VOTE_LANES_TS
+#define DUST_FAST_VOTE_LANES_TS 16               // trace_scene: WALK runs without the full vote when at least this many lanes wait for it
+#endif
 #ifndef DUST_WALK_REPS_TS
 #define DUST_WALK_REPS_TS 3                    // the same inside trace_scene (one thread per ray: coherent queues)
 #endif
@@ -535,7 +538,7 @@ __device__ __forceinline__ void trace_scene(const DSceneView &sc, const f3 ro, c
             // fast path: half of the warp or more waits for WALK — the plurality whatever the others want (one ballot + popc)
             n_walk = __popc(__ballot_sync(full, mode == M_WALK));
             cnt = n_walk;
-            if (n_walk < 16)
+            if (n_walk < DUST_FAST_VOTE_LANES_TS)
 #endif
             {
                 // one REDUX of three packed 8-bit counters instead of three ballots + popcounts

@@ -325,6 +325,9 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
 #define DUST_PT_MIN_BLOCKS4 8                 // the same for 4-level / mixed scenes
 #endif
 
+#ifndef DUST_WALK_REPS3
+#define DUST_WALK_REPS3 1                   // cells per voted WALK of the persistent tracer in 3-level scenes
+#endif
 enum : int { W_NEXT = 0, W_WALK = 1, W_LEAF = 2, W_DEAD = 3 };
 
 // ---- TMA staging of the ray queue (BASELINE.json north_star: "stages ... through TMA into shared memory") --------------------------
@@ -385,7 +388,7 @@ __device__ __forceinline__ void wf_stage_refill(const WfParams &p, const WfQueue
     if (q.path) bulk_g2s(dst + WF_STAGE * (32u + 4u * WF_CANDS), q.path + b32, c4 * 4u, bar);
 }
 #ifndef DUST_FAST_VOTE_LANES
-#define DUST_FAST_VOTE_LANES 16u
+#define DUST_FAST_VOTE_LANES (NL == 3 ? 12u : 16u)   // 256^3 models: 8 / 12 / 16 lanes = 2 946 / 2 996 / 2 971 Mrays/s on configs[2]; the 4096^3 domain loses 1.5 % at 12
 #endif
 
 // CAND: the queue comes with pre-culled candidate records (p.cand, multi-instance scenes); without them the only candidate is the
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(DUST_THREADS, NL == 3 ? DUST_PT_MIN_BLOCKS2 : 
 #pragma unroll 1
             // cells per vote: two for the long empty runs of the 4096^3 domain (one: -5 % on config 5), one for 256^3 models, where
             // a second cell serves too few lanes (+0.9 % on config 2)
-            for (int rep = 0; rep < (NL == 3 ? 1 : DUST_WALK_REPS); rep++)
+            for (int rep = 0; rep < (NL == 3 ? DUST_WALK_REPS3 : DUST_WALK_REPS); rep++)
                 if (mode == W_WALK) {
                     const int r = walk_step<NL, STATS>(w, st);
                     mode = r == WS_LEAF ? W_LEAF : (r == WS_OUT ? W_NEXT : W_WALK);
