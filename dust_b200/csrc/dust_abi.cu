@@ -526,7 +526,7 @@ int32_t trace_wavefront(DustCtx *ctx, const FrameParams &fp, uint32_t tiles_per_
         else { if (stats) DUST_PT_BY_KIND(0, true); else DUST_PT_BY_KIND(0, false); }
 #undef DUST_PT_BY_KIND
         count_launch(ctx, "wf_trace_pt");
-        // rays that wf_cull could not pre-cull: one warp per ray, persistent grid (the list length lives on the device)
+        // rays that wf_cull could not pre-cull: one CTA per ray, persistent grid (the list length lives on the device)
         const uint32_t sgrid = std::min<uint32_t>(grid, (uint32_t)ctx->sms * 8u);
         if (nl == 3) { if (stats) wf_trace_slow<3, true><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); else wf_trace_slow<3, false><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); }
         else if (nl == 4) { if (stats) wf_trace_slow<4, true><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); else wf_trace_slow<4, false><<<sgrid, DUST_THREADS, 0, ctx->stream>>>(p, q, ovf_counts + slot, p.overflow); }
@@ -1393,7 +1393,7 @@ static cudaError_t launch_ray_chunk(DustCtx *ctx, const DustScene *scene, const 
     if (need_cull) DUST_BY_NL(wf_trace_pt, true); else DUST_BY_NL(wf_trace_pt, false);
 #undef LAUNCH
     count_launch(ctx);
-    if (need_cull) {                                                   // rays whose candidate list was not conclusive: one warp per ray
+    if (need_cull) {                                                   // rays whose candidate list was not conclusive: one CTA per ray
         const uint32_t sgrid = std::min<uint32_t>(grid, (uint32_t)ctx->sms * 8u);
 #define LAUNCH <<<sgrid, DUST_THREADS, 0, stream>>>(p, q, ovf_count, p.overflow)
         DUST_BY_NL(wf_trace_slow);

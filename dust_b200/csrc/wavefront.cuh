@@ -255,23 +255,25 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
     if (STATS) flush_counters(p.f.counters, st);
 }
 
-// ---- the slow path: ONE WARP PER RAY ------------------------------------------------------------------------------
+// ---- the slow path: ONE CTA PER RAY ------------------------------------------------------------------------------
 // Rays whose candidate list was not conclusive (they graze dozens of instance boxes and hit nothing early; a few hundred per frame) used to be
 // re-traced one thread per ray: a handful of warps, each walking 30+ instances in sequence, held the whole pass for 0.19 ms.
-// Here the 32 lanes of a warp take the INSTANCES of one ray in parallel: lane k enters instances k, k + 32, ... (walk_enter
-// is the exact box clip, the BVH is only an accelerator), walks each to its closest hit, and the warp reduces the
-// lexicographic minimum of (t, instance) — the same result as any other visiting order.  Persistent grid: warps stride
+// Here the threads of a CTA take the INSTANCES of one ray in parallel: thread k enters instances k, k + 128, ... (walk_enter
+// is the exact box clip, the BVH is only an accelerator), walks each to its closest hit, and the CTA reduces the
+// lexicographic minimum of (t, instance) — the same result as any other visiting order.  Persistent grid: CTAs stride
 // over the list, whose length lives on the device.
 template <int NL, bool STATS, bool ROUGH = false>
 __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_constant__ WfParams p, const WfQueue q, const uint32_t *count, const uint32_t *list)
 {
+    // ONE CTA PER RAY since v13 (a warp per ray before: 110 instances = 4 in sequence per lane, and the pass is nothing but that chain's latency)
+    __shared__ float s_t[DUST_THREADS / 32];
+    __shared__ uint32_t s_i[DUST_THREADS / 32];
     const unsigned full = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const DSceneView &sc = p.f.scene;
     const uint32_t n = *count;
-    const uint32_t warps = gridDim.x * (DUST_THREADS / 32u);
     Counters st = {};
-    for (uint32_t k = blockIdx.x * (DUST_THREADS / 32u) + (threadIdx.x >> 5); k < n; k += warps) {
+    for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
         const uint32_t i = __ldg(&list[k]);
         float4 a, b;
         uint32_t pw;
@@ -284,8 +286,8 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
         uint32_t b_inst = 0xFFFFFFFFu, b_leaf = 0, b_pos = 0, b_vox = 0;
         Walk w;
         w.four = NL == 4; w.have_mid = false; w.L4 = 0; w.blk_lo = w.blk_hi = 0;
-        for (uint32_t inst = lane; inst < sc.n_inst; inst += 32u) {
-            if (!walk_enter<NL, STATS>(sc, w, inst, ro, rd, tmin, bt, st)) continue;       // bt: this lane's own best so far (tmax shrinks per lane)
+        for (uint32_t inst = threadIdx.x; inst < sc.n_inst; inst += DUST_THREADS) {
+            if (!walk_enter<NL, STATS>(sc, w, inst, ro, rd, tmin, bt, st)) continue;       // bt: this thread's own best so far (tmax shrinks per thread)
             for (;;) {
                 const int r = walk_step<NL, STATS>(w, st);
                 if (r == WS_OUT) break;
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
             }
             if (any && hit) break;
         }
-        // lexicographic minimum of (t, instance) over the lanes
+        // lexicographic minimum of (t, instance) over the threads: shuffles inside a warp, shared memory across the warps
         float rt = hit ? bt : CUDART_INF_F;
         uint32_t ri = hit ? b_inst : 0xFFFFFFFFu;
 #pragma unroll
@@ -309,11 +311,20 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
             const uint32_t oi = __shfl_xor_sync(full, ri, ofs);
             if (ot < rt || (ot == rt && oi < ri)) { rt = ot; ri = oi; }
         }
+        if (lane == 0) { s_t[wid] = rt; s_i[wid] = ri; }
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < DUST_THREADS / 32; v++) {
+            const float ot = s_t[v];
+            const uint32_t oi = s_i[v];
+            if (ot < rt || (ot == rt && oi < ri)) { rt = ot; ri = oi; }
+        }
+        __syncthreads();                                                                    // s_t / s_i are rewritten by the CTA's next ray
         const bool any_hit = ri != 0xFFFFFFFFu;
-        if (any) { if (lane == 0) p.vis[pw & 0x7FFFFFFFu] = any_hit ? 1 : 0; }
-        else if (!any_hit) { if (lane == 0) wf_store_hit(p, i, false, tmax, 0xFFFFFFFFu, 0u, 0u, 0u); }
-        else if (hit && b_inst == ri) wf_store_hit(p, i, true, bt, b_inst, b_leaf, b_pos, b_vox);        // exactly one lane owns the winner
-        if (STATS && q.stride == 2u && lane == 0) st.primary_rays++;
+        if (any) { if (threadIdx.x == 0) p.vis[pw & 0x7FFFFFFFu] = any_hit ? 1 : 0; }
+        else if (!any_hit) { if (threadIdx.x == 0) wf_store_hit(p, i, false, tmax, 0xFFFFFFFFu, 0u, 0u, 0u); }
+        else if (hit && b_inst == ri) wf_store_hit(p, i, true, bt, b_inst, b_leaf, b_pos, b_vox);        // exactly one thread owns the winner
+        if (STATS && q.stride == 2u && threadIdx.x == 0) st.primary_rays++;
     }
     if (STATS) flush_counters(p.f.counters, st);
 }
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_trace_slow(const __grid_const
 #define DUST_PT_MIN_BLOCKS2 8                 // 64 registers: 8 CTAs / SM beat 6 with no spills that matter (A/B in profiles/r01_history.md)
 #endif
 #ifndef DUST_PT_MIN_BLOCKS4
-#define DUST_PT_MIN_BLOCKS4 8                 // the same for 4-level / mixed scenes
+#define DUST_PT_MIN_BLOCKS4 10                // 4-level / mixed scenes: 48 registers; the 523 MB tree of configs[4] misses L2, warps in flight pay (7 / 8 / 10 CTAs: 2 120 / 2 125 / 2 199 Mrays/s)
 #endif
 
 #ifndef DUST_WALK_REPS3
