@@ -476,6 +476,7 @@ __device__ __forceinline__ int walk_step(Walk &w, Counters &st)
     if (!bit64(w.mid_lo, w.mid_hi, midx)) { w.L4 = 1; return WS_WALK; }
     if (STATS) { st.child_ptrs++; st.mask_words++; }
     w.leaf_i = w.mid_base + rank64(w.mid_lo, w.mid_hi, midx);
+    // (a prefetch.global.L1 of the leaf word here, a vote before the LEAF operation reads it: 2 988 against 3 003 Mrays/s — not kept)
     return WS_LEAF;
 }
 
