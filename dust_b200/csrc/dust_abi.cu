@@ -924,7 +924,7 @@ int32_t dust_tree_leaf_count(const DustTree *tree, uint64_t *out)
 int32_t dust_tree_device_bytes(const DustTree *tree, uint64_t *out)
 {
     if (!tree || !out) return DUST_ERR_INVALID_ARGUMENT;
-    *out = tree->blob_bytes;
+    *out = tree->blob_bytes + (tree->dense_root ? 4096 * sizeof(uint4) : 0);            // the blob + the derived dense root table
     return DUST_OK;
 }
 

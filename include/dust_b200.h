@@ -203,7 +203,10 @@ int32_t dust_tree_upload(DustCtx *ctx, const DustTreeDesc *desc, DustTree **out)
 typedef struct DustVoxel { uint8_t x, y, z, i; } DustVoxel;
 int32_t dust_tree_build_voxels(DustCtx *ctx, const DustVoxel *voxels, uint64_t n, const uint32_t *size, const uint8_t *palette,
                                uint32_t memory, DustTree **out);
-/* Inspection: section offsets / counts of a tree's device blob, and a copy of it (tests compare both build paths). */
+/* Inspection: section offsets / counts of a tree's device blob, and a copy of it (tests compare both build paths).
+ * Besides the blob every tree owns a derived 64 KB look-up table of its root node's 4096 cells (built on the device from the
+ * blob; the kernels descend through it).  It is not part of the blob, dust_tree_layout and dust_tree_download do not show it;
+ * dust_tree_device_bytes counts it. */
 typedef struct DustTreeLayout {
     uint32_t n_levels, _pad;
     uint64_t n_nodes16, n_mids, n_leaves, n_materials;
