@@ -492,7 +492,7 @@ def castle_record(env, S, cfg, cfg_id, scaling, steps, warmup, *, kernels=True, 
     traffic, traffic_note = traffic_record("config%d_dram_bytes_per_step" % cfg_id) if world == 1 else (None, None)
     n_trace_launches = launches / max(1, steps) - (1 if world > 1 else 0)           # resolve_kernel follows the all-gather
     pipeline = "frame_kernel (megakernel, 1 launch)" if cfg["max_bounces"] == 0 else \
-        "wavefront pipeline: wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_trace_slow, wf_resolve (%d launches)" % n_trace_launches
+        "wavefront pipeline: wf_tile_cull, wf_sun_grid, wf_trace, wf_shade, wf_cull, wf_trace_pt, wf_trace_slow, wf_resolve (%d launches)" % n_trace_launches
     klist, total_ms = [], sum(r["ms"] for r in per_launch) or 1.0
     for r in per_launch:
         px = 16 * my_pixels if r["kernel"] in ("wf_resolve", "frame_kernel") else 0

@@ -26,6 +26,7 @@ struct DustCtx {
     uint32_t *d_wf_counters = nullptr;
     uint32_t *d_tile_lists = nullptr;        // per local tile: candidate instances of its camera frustum (wf_tile_cull)
     size_t tile_lists_words = 0;
+    uint32_t *d_sun_lists = nullptr;         // per cell of the sun grid: candidate instances of the sun shadow rays (wf_sun_grid)
     int sms = 148;
     DustStats stats{};
     // DUST_TRACE_TIMING: one event after every launch of the last dust_trace call (+ a counter snapshot with DUST_TRACE_STATS)

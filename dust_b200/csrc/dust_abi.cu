@@ -659,6 +659,7 @@ int32_t dust_ctx_destroy(DustCtx *ctx)
     if (ctx->wf_scratch) cudaFree(ctx->wf_scratch);
     if (ctx->d_wf_counters) cudaFree(ctx->d_wf_counters);
     if (ctx->d_tile_lists) cudaFree(ctx->d_tile_lists);
+    if (ctx->d_sun_lists) cudaFree(ctx->d_sun_lists);
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->h_snaps) cudaFreeHost(ctx->h_snaps);
@@ -1262,6 +1263,42 @@ static int32_t trace_impl(DustCtx *ctx, const DustScene *scene, const DustCamera
         wf_tile_cull<<<(tiles_per_shard + 3) / 4, 128, 0, ctx->stream>>>(p, ctx->d_tile_lists);
         count_launch(ctx, "wf_tile_cull");
         p.tile_lists = ctx->d_tile_lists;
+    }
+#endif
+#ifndef DUST_NO_SUN_GRID
+    if (wavefront && scene->n_inst > 1 && scene->d_boxes) {
+        // sun shadow rays: a 2D look-up by where the origin projects along the sun direction instead of a BVH walk per ray (kernels.cuh sun_list_of)
+        const double sx = p.sun_dir[0], sy = p.sun_dir[1], sz = p.sun_dir[2];
+        double ax[3] = { 1.0, 0.0, 0.0 };
+        if (std::fabs(sx) > std::fabs(sy) || std::fabs(sx) > std::fabs(sz)) { ax[0] = 0.0; if (std::fabs(sy) <= std::fabs(sz)) ax[1] = 1.0; else ax[2] = 1.0; }
+        double u[3] = { sy * ax[2] - sz * ax[1], sz * ax[0] - sx * ax[2], sx * ax[1] - sy * ax[0] };
+        const double ul = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (std::isfinite(ul) && ul > 1e-6) {
+            for (double &c : u) c /= ul;
+            const double v[3] = { sy * u[2] - sz * u[1], sz * u[0] - sx * u[2], sx * u[1] - sy * u[0] };
+            double umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY, big = 0.0;
+            for (int corner = 0; corner < 8; corner++) {
+                const double c[3] = { corner & 1 ? scene->view.root_hi[0] : scene->view.root_lo[0], corner & 2 ? scene->view.root_hi[1] : scene->view.root_lo[1],
+                                      corner & 4 ? scene->view.root_hi[2] : scene->view.root_lo[2] };
+                const double pu = c[0] * u[0] + c[1] * u[1] + c[2] * u[2], pv = c[0] * v[0] + c[1] * v[1] + c[2] * v[2];
+                umin = std::min(umin, pu); umax = std::max(umax, pu); vmin = std::min(vmin, pv); vmax = std::max(vmax, pv);
+                big = std::max({ big, std::fabs(c[0]), std::fabs(c[1]), std::fabs(c[2]) });
+            }
+            const double eu = 1e-3 * (umax - umin) + 1e-6, ev = 1e-3 * (vmax - vmin) + 1e-6;
+            umin -= eu; umax += eu; vmin -= ev; vmax += ev;
+            const double du = (umax - umin) / DUST_SUN_GRID, dv = (vmax - vmin) / DUST_SUN_GRID;
+            if (std::isfinite(du) && std::isfinite(dv) && du > 0.0 && dv > 0.0) {
+                if (!ctx->d_sun_lists) CU_TRY(ctx, cudaMalloc(&ctx->d_sun_lists, (size_t)DUST_SUN_GRID * DUST_SUN_GRID * DUST_TILE_LIST_WORDS * sizeof(uint32_t)));
+                for (int k = 0; k < 3; k++) { p.sun_u[k] = (float)u[k]; p.sun_v[k] = (float)v[k]; }
+                p.sun_u0 = (float)umin; p.sun_v0 = (float)vmin; p.sun_du = (float)du; p.sun_dv = (float)dv;
+                p.sun_inv_du = (float)(1.0 / du); p.sun_inv_dv = (float)(1.0 / dv);
+                // margin: float rounding of a ray's projection (a few 2^-24 of its coordinates), of the cell index, of the float basis
+                p.sun_eps = (float)(1e-3 * std::max(du, dv) + 2e-5 * (big + (umax - umin) + (vmax - vmin)));
+                wf_sun_grid<<<DUST_SUN_GRID * DUST_SUN_GRID / 4, 128, 0, ctx->stream>>>(p, ctx->d_sun_lists);
+                count_launch(ctx, "wf_sun_grid");
+                p.sun_lists = ctx->d_sun_lists;
+            }
+        }
     }
 #endif
     if (wavefront) {

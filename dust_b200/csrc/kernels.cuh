@@ -40,7 +40,28 @@ struct FrameParams {
     DustGBuffer gb;            // optional G-buffer of the sample-0 primary hit (NULL members are skipped)
     DCounters *counters;
     const uint32_t *tile_lists;   // per local tile: DUST_TILE_LIST_WORDS words (wf_tile_cull), or NULL
+    // sun grid (wf_sun_grid): candidate instances of the sun shadow rays by where their origin projects along the sun direction
+    const uint32_t *sun_lists;    // per cell: DUST_TILE_LIST_WORDS words, or NULL
+    float sun_u[3], sun_v[3];     // orthonormal basis of the plane perpendicular to sun_dir
+    float sun_u0, sun_v0, sun_inv_du, sun_inv_dv, sun_du, sun_dv, sun_eps;   // grid origin, 1 / cell size, cell size, conservative margin
 };
+
+#ifndef DUST_SUN_GRID
+#define DUST_SUN_GRID 128                // cells per side of the sun grid
+#endif
+
+// Sun shadow rays all run along sun_dir, so a ray can only touch the instances whose box, projected along that direction, covers the
+// projection of its origin: a 2D look-up replaces the BVH walk (the rays then run the exact box test on the listed instances, like
+// the camera rays do on their tile's list).  Returns the cell's list, or NULL when the origin projects outside the grid (the ray walks the BVH).
+__device__ __forceinline__ const uint32_t *sun_list_of(const FrameParams &f, f3 o)
+{
+    const float pu = (o.x * f.sun_u[0] + o.y * f.sun_u[1]) + o.z * f.sun_u[2];
+    const float pv = (o.x * f.sun_v[0] + o.y * f.sun_v[1]) + o.z * f.sun_v[2];
+    const float fu = (pu - f.sun_u0) * f.sun_inv_du, fv = (pv - f.sun_v0) * f.sun_inv_dv;
+    if (!(fu >= 0.0f && fu < (float)DUST_SUN_GRID && fv >= 0.0f && fv < (float)DUST_SUN_GRID)) return nullptr;
+    const uint32_t cell = (uint32_t)fv * DUST_SUN_GRID + (uint32_t)fu;
+    return f.sun_lists + (size_t)cell * DUST_TILE_LIST_WORDS;
+}
 
 enum : int { RAY_NONE = 0, RAY_PRIMARY = 1, RAY_SHADOW = 2, RAY_BOUNCE = 3 };
 
@@ -248,6 +269,41 @@ __global__ void __launch_bounds__(128) wf_tile_cull(const __grid_constant__ Fram
                 const float dmin = (n[k].x * vx + n[k].y * vy) + n[k].z * vz;
                 if (dmin > 1e-4f * nl[k] * (far_ * 3.0f + 1.0f)) keep = false;
             }
+        }
+        const unsigned m = __ballot_sync(full, keep);
+        if (keep) {
+            const uint32_t k = count + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (k < DUST_TILE_LIST_MAX) list[1u + k] = inst;
+        }
+        count += (uint32_t)__popc(m);
+    }
+    if (lane == 0) list[0] = count > DUST_TILE_LIST_MAX ? 0xFFFFFFFFu : count;
+}
+
+// One warp per cell of the sun grid: the instances whose padded world box, projected onto the plane perpendicular to the sun direction
+// (centre +- the box's half extents weighted by |u|, |v|: the bounding rectangle of the projected box), overlaps the cell widened by
+// sun_eps (rounding of the rays' own projection, of the cell index, and of this test).  list[0] = count (0xFFFFFFFF: more than
+// DUST_TILE_LIST_MAX, the rays of that cell walk the BVH), list[1..] = instance indices.
+__global__ void __launch_bounds__(128) wf_sun_grid(const __grid_constant__ FrameParams p, uint32_t *__restrict__ lists)
+{
+    const unsigned full = 0xffffffffu;
+    const uint32_t cell = blockIdx.x * 4u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (cell >= DUST_SUN_GRID * DUST_SUN_GRID) return;
+    uint32_t *list = lists + (size_t)cell * DUST_TILE_LIST_WORDS;
+    const uint32_t cu = cell % DUST_SUN_GRID, cv = cell / DUST_SUN_GRID;
+    const float ulo = p.sun_u0 + (float)cu * p.sun_du - p.sun_eps, uhi = p.sun_u0 + (float)(cu + 1u) * p.sun_du + p.sun_eps;
+    const float vlo = p.sun_v0 + (float)cv * p.sun_dv - p.sun_eps, vhi = p.sun_v0 + (float)(cv + 1u) * p.sun_dv + p.sun_eps;
+    uint32_t count = 0;
+    for (uint32_t base = 0; base < p.scene.n_inst; base += 32u) {
+        const uint32_t inst = base + lane;
+        bool keep = false;
+        if (inst < p.scene.n_inst) {
+            const float4 lo = __ldg(&p.scene.inst_boxes[2u * inst]), hi = __ldg(&p.scene.inst_boxes[2u * inst + 1u]);
+            const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+            const float hx = 0.5f * (hi.x - lo.x), hy = 0.5f * (hi.y - lo.y), hz = 0.5f * (hi.z - lo.z);
+            const float pu = (cx * p.sun_u[0] + cy * p.sun_u[1]) + cz * p.sun_u[2], ru = (hx * fabsf(p.sun_u[0]) + hy * fabsf(p.sun_u[1])) + hz * fabsf(p.sun_u[2]);
+            const float pv = (cx * p.sun_v[0] + cy * p.sun_v[1]) + cz * p.sun_v[2], rv = (hx * fabsf(p.sun_v[0]) + hy * fabsf(p.sun_v[1])) + hz * fabsf(p.sun_v[2]);
+            keep = pu - ru <= uhi && pu + ru >= ulo && pv - rv <= vhi && pv + rv >= vlo;
         }
         const unsigned m = __ballot_sync(full, keep);
         if (keep) {

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(DUST_THREADS, DUST_MIN_BLOCKS) wf_trace(const 
         const uint32_t i0 = blockIdx.x * DUST_THREADS + (threadIdx.x & ~31u);
         tl = p.f.tile_lists + (size_t)min((i0 / p.batch_spp) >> 10, p.f.n_local_tiles - 1u) * DUST_TILE_LIST_WORDS;
     }
+    // sun shadow rays (queue kind 1: every ray runs along sun_dir): the list of the sun-grid cell the origin projects into (per lane)
+    else if (q.kind == 1u && p.f.sun_lists && live) tl = sun_list_of(p.f, mk3(a.x, a.y, a.z));
     trace_scene<NL, STATS>(p.f.scene, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, (pw >> 31) != 0u, live, s_scratch + threadIdx.x, h, st, ROUGH, tl);
     if (live) {
         if (STATS && q.stride == 2u) st.primary_rays++;
@@ -224,9 +226,16 @@ __global__ void __launch_bounds__(DUST_THREADS) wf_cull(const __grid_constant__ 
         const float tmin = a.w, tmax = b.w;
         const f3 winv = cull_inverse(rd);
         int sp, pend, nc;
+        bool trunc = false;
+        const uint32_t *sl = q.kind == 1u && p.f.sun_lists ? sun_list_of(p.f, ro) : nullptr;
+        if (sl && __ldg(&sl[0]) != 0xFFFFFFFFu) {
+            // sun shadow rays: the candidates come from the sun grid (kernels.cuh sun_list_of), no BVH walk
+            sp = DUST_SCRATCH_WORDS; pend = -1; nc = 0;
+            cull_from_list(sc, sl, ro, winv, tmin, tmax, id_mask, sm, nc);
+            if (nc > WF_CANDS) { nc = WF_CANDS; trunc = true; }         // sorted: the farthest ones go
+        } else
         cull_begin(sc, ro, winv, tmin, tmax, id_mask, sm, sp, pend, nc);
         const CullRay cr = cull_ray(sc, ro, winv);
-        bool trunc = false;
         while (pend >= 0 && cull_room(sp, nc)) {
             cull_expand<STATS>(sc, cr, tmin, tmax, id_mask, sm, sp, pend, nc, st);
             // The record holds WF_CANDS keys: drop the farthest ones as the walk goes (the list is sorted, and the last kept key only

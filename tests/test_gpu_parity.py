@@ -406,13 +406,13 @@ def test_launch_info_timing_and_counter_deltas(castle_small, host):
     out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     ctx.use_torch_stream()
     try:
-        for pipeline, names in (("wavefront", {"wf_tile_cull", "wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace_slow"}),
+        for pipeline, names in (("wavefront", {"wf_tile_cull", "wf_sun_grid", "wf_trace", "wf_shade", "wf_cull", "wf_trace_pt", "wf_resolve", "wf_trace_slow"}),
                                 ("megakernel", {"wf_tile_cull", "frame_kernel"})):
             castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1, stats=True, timing=True, pipeline=pipeline)
             info = ctx.launch_info()
             tot = ctx.stats()
             assert {r["kernel"] for r in info} == names and all(r["ms"] > 0 for r in info)
-            assert len(info) == (12 if pipeline == "wavefront" else 2)          # + wf_tile_cull (the camera-ray candidate lists)
+            assert len(info) == (13 if pipeline == "wavefront" else 2)          # + wf_tile_cull, wf_sun_grid (the candidate lists of camera / sun rays)
             for k in ("primary_rays", "bounce_rays", "shadow_rays", "mask_words", "child_ptrs", "hits_shaded"):
                 assert sum(r[k] for r in info) == tot[k], k
         castle_small.loaded.scene.trace_device(cam, sky, W, H, out, spp=2, max_bounces=1, seed=1)     # no flag: the records of the last timed call stay
