@@ -11,14 +11,15 @@
 //     trace          closest hit of every ray of the queue                           -> hit records
 //     wf_shade       apply the previous vertex's sun visibility, consume the hit (sky on a miss,
 //                    surface on a hit), emit the sun-shadow ray -> shadow queue and the cosine-weighted
-//                    bounce ray -> next closest queue (compacted, one atomic per warp)
+//                    bounce ray -> next closest queue (compacted, one atomic per CTA)
 //     trace          any hit of every shadow ray                                     -> visibility byte per path
 //   wf_resolve       last visibility, sRGB -> ACEScg, mean over samples in sample order -> frame
 //
 // trace = wf_trace (one thread per ray) for the coherent depth-0 queues; for the incoherent queues
 // behind a bounce it is wf_cull + wf_trace_pt + wf_trace_slow: candidate instances are collected with all lanes
 // busy (the 8 nearest per ray), persistent lanes walk them and CLAIM THE NEXT RAY of the queue the moment their own
-// is finished, and the few rays whose truncated list was not conclusive are redone one WARP per ray.
+// is finished, and the few rays whose truncated list was not conclusive are redone one CTA per ray.  Sun shadow rays take
+// their candidates from the sun grid (kernels.cuh wf_sun_grid) instead of the BVH, camera rays from their tile's list.
 // Every ray is traced by the same walk code as in the megakernel and every float of a path is
 // accumulated in the same order, so results are bit-identical to frame_kernel; queue order (atomics)
 // varies from run to run but no result depends on it.  (Sorting the bounce rays by direction bin was
